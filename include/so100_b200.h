@@ -1,0 +1,218 @@
+/*
+ * so100_b200.h — C ABI of the B200-native batched so100 simulator (libso100_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of PieterBecking/so100-mujoco-rl: the per-step work of
+ * Env01 / Env02 / Env05 (`reset()` / `step(a)`), which in the reference is Python task logic wrapped around
+ * MuJoCo's `mj_step(model, data, nstep=16)`.  Reference interfaces replaced (paths relative to the reference repo):
+ *
+ *   so100_create      <- So100BaseEnv.__init__            src/so100_mujoco_rl/envs/env_base_01.py:35-61
+ *                        (MjModel.from_xml_path + MujocoEnv.__init__, frame_skip 16) and
+ *                        Env03._set_initial_values         src/so100_mujoco_rl/envs/env03_v1.py:35-57
+ *   so100_reset       <- MujocoEnv.reset -> reset_model    env01_v1.py:39-63, env02_v1.py:70-81, env03_v1.py:203-215
+ *   so100_step        <- Env01.step / Env02.step / Env03.step (used by Env05) + Env05._get_obs
+ *                        env01_v1.py:15-37, env02_v1.py:18-50, env03_v1.py:124-201, env05_v1.py:32-75,
+ *                        the 16x mujoco.mj_step at env01_v1.py:26 / env02_v1.py:39 / env03_v1.py:142,
+ *                        the gymnasium TimeLimit wrapper (src/so100_mujoco_rl/__init__.py:5-45) and the
+ *                        auto-reset that SB3's DummyVecEnv performs around a done env
+ *   so100_get_state / so100_set_state  <- direct reads/writes of mjData (data.qpos, data.qvel, ...) used for tests
+ *   so100_forward_dynamics <- one mj_forward restricted to the arm (debug/parity entry; not on the step path)
+ *
+ * Conventions
+ *   - every entry point returns SO100_OK (0) or a negative error code; the message is available per thread through
+ *     so100_last_error().  No C++ exception crosses this boundary.
+ *   - all *_dev pointers are DEVICE pointers owned by the caller (e.g. torch tensors); the library never
+ *     allocates or frees them.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work
+ *     is enqueued on it and the call returns without synchronising.
+ *   - the *_host entry points take HOST pointers (pinned memory recommended), do the H2D/D2H copies themselves
+ *     on `stream` and synchronise that stream before returning: this is the reference-facing call.
+ *   - external observation / action layout is row-major [num_envs, dim] float32 (what SB3 / torch policies
+ *     consume).  Internal state is structure-of-arrays.
+ *   - one ctx per (device, task); calls on one ctx must be serialised by the caller.
+ */
+#ifndef SO100_B200_H
+#define SO100_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SO100_ABI_VERSION 1
+#define SO100_NJ 6            /* arm hinges incl. the jaw */
+#define SO100_MAX_START 64    /* rows available for Env01 start poses (reference: 36) */
+
+/* error codes */
+#define SO100_OK 0
+#define SO100_ERR_ARG (-1)
+#define SO100_ERR_CUDA (-2)
+#define SO100_ERR_MODEL (-3)
+#define SO100_ERR_STATE (-4)
+
+/* tasks (reference env ids "Env01-v1", "Env02-v1", "Env05-v1") */
+#define SO100_TASK_ENV01 1
+#define SO100_TASK_ENV02 2
+#define SO100_TASK_ENV05 5
+
+/* quirk flags (task_cfg.flags). Default 0 reproduces the reference bit for bit in behaviour. */
+#define SO100_FLAG_FRESH_FK_ON_RESET 1u /* run kinematics in reset (the reference does not: SURVEY Q2) */
+#define SO100_FLAG_CLIP_ACTIONS 2u      /* clip actions to [-1,1] on device (the reference env does not) */
+
+/*
+ * Model constants as they stand in the MJCF (so_arm100_camera.xml + env01.xml), nothing derived.
+ * Index 0..5 = Rotation, Pitch, Elbow, Wrist_Pitch, Wrist_Roll, Jaw; body i carries joint i and is the child of
+ * body i-1 (body -1 = the welded Base).  Quaternions are (w,x,y,z) and need not be normalised.
+ */
+typedef struct so100_model {
+  int32_t struct_size;       /* = sizeof(so100_model), checked by so100_create */
+  int32_t nsubstep;          /* frame_skip, 16 (env_base_01.py:45) */
+  double timestep;           /* 0.002 */
+  double gravity[3];         /* 0 0 -9.81 */
+  double base_pos[3];        /* Base body in the world (welded) */
+  double base_quat[4];
+  double body_pos[SO100_NJ][3];
+  double body_quat[SO100_NJ][4];
+  double body_ipos[SO100_NJ][3];
+  double body_iquat[SO100_NJ][4];
+  double body_mass[SO100_NJ];
+  double body_inertia[SO100_NJ][3]; /* diaginertia in the inertial frame */
+  double jnt_axis[SO100_NJ][3];     /* in the body frame; joint anchor is the body origin */
+  double jnt_range[SO100_NJ][2];
+  double jnt_armature[SO100_NJ];
+  double jnt_frictionloss[SO100_NJ];
+  double jnt_solref_limit[SO100_NJ][2];
+  double jnt_solimp_limit[SO100_NJ][5];
+  double dof_solref_friction[SO100_NJ][2];
+  double dof_solimp_friction[SO100_NJ][5];
+  double act_kp[SO100_NJ];
+  double act_dampratio[SO100_NJ];   /* >0: kv = dampratio*2*sqrt(kp*dof_M0) (MuJoCo mj_setConst) */
+  double act_kv[SO100_NJ];          /* used when act_dampratio <= 0 */
+  double act_ctrlrange[SO100_NJ][2];
+  double act_forcerange[SO100_NJ][2];
+  int32_t ee_body;           /* Fixed_Jaw = 4 */
+  int32_t wrist_body;        /* Wrist_Pitch_Roll = 3 */
+  int32_t cam_body;          /* body carrying so100_end_point_camera = 4 */
+  int32_t _pad0;
+  double ee_offset[3];       /* (0,-0.1,0) in the Fixed_Jaw frame, env_base_01.py:125 */
+  double cam_pos[3];
+  double cam_quat[4];
+  double cam_fovy_deg;       /* 120 */
+} so100_model;
+
+/* Task constants: the literals of envs/utils.py, env03_v1.py, env05_v1.py, env_base_02.py, __init__.py. */
+typedef struct so100_task_cfg {
+  int32_t struct_size;       /* = sizeof(so100_task_cfg) */
+  int32_t task;              /* SO100_TASK_* */
+  int32_t num_envs;          /* envs owned by this ctx */
+  int32_t max_episode_steps; /* TimeLimit: 4000 (Env01) / 6000 (Env02, Env05) */
+  int64_t env_offset;        /* global id of local env 0 (RNG is keyed by the global id) */
+  uint64_t seed;
+  uint32_t flags;            /* SO100_FLAG_* */
+  int32_t n_start;           /* rows used in start_positions (Env01) */
+  double joint_step_scale;   /* 0.075, utils.py:9 */
+  double start_positions[SO100_MAX_START][SO100_NJ]; /* VALID_START_POSITIONS, utils.py:13-50 */
+  double rest_position[SO100_NJ];                     /* REST_POSITION (Env02), utils.py:11 */
+  double start_position05[SO100_NJ];                  /* START_POSITION (Env05), env03_v1.py:10 */
+  double block_dist_range[2];   /* Env01 (0.18,0.42) env01_v1.py:45; Env02 (0.22,0.42) env02_v1.py:55 */
+  double block_theta_half;      /* pi/4 */
+  double reach_threshold;       /* 0.03, env02_v1.py:29 */
+  double block_space_start[2][3]; /* env05_v1.py:13-16 */
+  double block_space_end[2][3];   /* env05_v1.py:17-20 */
+  double block_speed_min, block_speed_max; /* env03_v1.py:21-22 */
+  double ramp_seconds;          /* 12.0, env03_v1.py:126 */
+  double cam_res_w, cam_res_h;  /* 1080 x 1920, env_base_02.py:22-23 */
+  double obs_noise;             /* 0.05, env05_v1.py:44-45 */
+  int32_t lost_limit;           /* 30, env03_v1.py:155 */
+  int32_t _pad0;
+} so100_task_cfg;
+
+/*
+ * Flat view of the per-env simulation state for parity tests.  All pointers are DEVICE pointers to arrays the
+ * caller owns, laid out structure-of-arrays: field[k][env] at  ptr[k * num_envs + env].  NULL = skip the field.
+ */
+typedef struct so100_state_view {
+  float *qpos;          /* [6][N] */
+  float *qvel;          /* [6][N] */
+  float *qacc_warm;     /* [6][N]  previous substep's qacc (solver warm start, mjData.qacc_warmstart) */
+  float *block;         /* [3][N]  block position (qpos[6:9] of the reference) */
+  float *snap;          /* [12][N] stale kinematics snapshot: Env01/02 end_pos(0..2), wrist_z(3), block_xpos(4..6);
+                                    Env05 cam_xpos(0..2), cam_xmat(3..11 row-major) */
+  float *aux;           /* [24][N] task scalars: Env02 block_pos(0..2), last_block_pos(3..5); Env05 cmd(0..5),
+                                    last_angvel(6..11), target(12..14), target_dt(15), last_centre(16..17) */
+  int32_t *counters;    /* [4][N]  elapsed_steps, flags (1 ever_stepped, 2 has_last_block, 4 angvel_valid,
+                                    8 centre_valid), miss_count, target_t0_step */
+  float *ep_return;     /* [N] */
+} so100_state_view;
+
+typedef struct so100_ctx so100_ctx;
+
+int so100_abi_version(void);
+const char *so100_last_error(void);
+
+int so100_obs_dim(int task);   /* 15 for Env01/Env02, 8 for Env05; <0 on unknown task */
+int so100_act_dim(int task);   /* 6 */
+
+/* Parse-free construction: the caller has read the MJCF (see so100_mujoco_rl_b200/model.py) and hands over constants. */
+int so100_create(const so100_model *model, const so100_task_cfg *cfg, int device, so100_ctx **out);
+void so100_destroy(so100_ctx *ctx);
+
+/*
+ * Reset.  mask_dev == NULL resets every env, else only envs with mask_dev[i] != 0.  Writes the reset observation
+ * of the envs that were reset into obs_dev[N, obs_dim] (rows of other envs are left untouched).
+ */
+int so100_reset(so100_ctx *ctx, const uint8_t *mask_dev, float *obs_dev, void *stream);
+
+/*
+ * One env step for all envs: pre-step task logic, 16 physics substeps, observation, reward, termination,
+ * TimeLimit truncation, and auto-reset of finished envs (SB3 VecEnv semantics: obs_dev holds the first observation
+ * of the next episode for finished envs and terminal_obs_dev their last observation).
+ * Optional outputs may be NULL: terminal_obs_dev [N, obs_dim], ep_return_dev [N] / ep_len_dev [N] (return and
+ * length of the episode that just finished; only written for finished envs).
+ */
+int so100_step(so100_ctx *ctx, const float *actions_dev, float *obs_dev, float *reward_dev,
+               uint8_t *terminated_dev, uint8_t *truncated_dev, float *terminal_obs_dev,
+               float *ep_return_dev, int32_t *ep_len_dev, void *stream);
+
+/* Host-buffer variants (the reference-facing call): copies + kernel on `stream`, synchronised on return. */
+int so100_reset_host(so100_ctx *ctx, float *obs_host, void *stream);
+int so100_step_host(so100_ctx *ctx, const float *actions_host, float *obs_host, float *reward_host,
+                    uint8_t *terminated_host, uint8_t *truncated_host, float *terminal_obs_host,
+                    float *ep_return_host, int32_t *ep_len_host, void *stream);
+
+int so100_get_state(so100_ctx *ctx, const so100_state_view *view, void *stream);
+int so100_set_state(so100_ctx *ctx, const so100_state_view *view, void *stream);
+
+/* global step counter t (number of so100_step calls so far); part of the RNG key. */
+int so100_get_tick(so100_ctx *ctx, int64_t *tick);
+int so100_set_tick(so100_ctx *ctx, int64_t tick);
+
+/*
+ * Debug / parity entry: for n arbitrary (qpos,qvel,ctrl) triples (SoA [6][n] each, device) evaluate one forward
+ * dynamics pass with a cold start: M (21 lower-triangle entries, row-major i>=j), bias (6), qacc (6),
+ * and the kinematics snapshot (end_pos 3, wrist 3, cam_xpos 3, cam_xmat 9 = 18).  Any output may be NULL.
+ */
+int so100_forward_dynamics(so100_ctx *ctx, int n, const float *qpos_dev, const float *qvel_dev,
+                           const float *ctrl_dev, float *M_dev, float *bias_dev, float *qacc_dev,
+                           float *kin_dev, void *stream);
+
+/*
+ * Host-side fp64 evaluation of the SAME recursion templates the kernels instantiate in fp32 (csrc/so100_dyn.cuh);
+ * needs no GPU.  It exists so that the kernel mathematics can be checked against the oracle on a CPU-only machine
+ * and is how so100_create derives dof_M0 / kv / invweight0.  Row-major host arrays: qpos/qvel/ctrl [n][6],
+ * M [n][21] (packed lower triangle), bias [n][6], qacc [n][6] (cold start, `sweeps` Gauss-Seidel sweeps),
+ * kin [n][18] (end_pos 3, wrist 3, cam_xpos 3, cam_xmat 9).  Outputs may be NULL.
+ */
+int so100_host_forward(const so100_model *model, int n, const double *qpos, const double *qvel, const double *ctrl,
+                       double *M, double *bias, double *qacc, double *kin, int sweeps);
+
+/* Derived constants as the library computed them (host, fp64): dof_M0[6], kv[6], invweight0[6]. */
+int so100_get_derived(so100_ctx *ctx, double *dof_M0, double *kv, double *invweight0);
+
+/* Kernel launches issued by this ctx so far; env steps whose Gauss-Seidel solve had not converged to 1e-4
+   (relative) in its last sweep; envs force-reset because their state went non-finite (device counters, syncs). */
+int so100_get_stats(so100_ctx *ctx, int64_t *launches, int64_t *solver_fallbacks, int64_t *nan_resets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SO100_B200_H */

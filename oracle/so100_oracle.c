@@ -1,0 +1,763 @@
+/*
+ * so100_oracle.c — CPU fp64 ORACLE for the so100 hot path.  TEST INFRASTRUCTURE ONLY (see so100_oracle.h).
+ *
+ * PARITY UNPINNED: the reference ships no tests / golden vectors, and its arithmetic lives in the un-vendored
+ * wheel mujoco==3.3.1 (reference pyproject.toml:9, pixi.lock:1511).  Physics below RESTATES MuJoCo's published
+ * mj_step pipeline specialised to the so100 MJCF; task logic TRANSLITERATES the reference:
+ *   Env01   src/so100_mujoco_rl/envs/env01_v1.py:15-63
+ *   Env02   src/so100_mujoco_rl/envs/env02_v1.py:18-81
+ *   Env05   src/so100_mujoco_rl/envs/env03_v1.py:35-215 (inherited) + env05_v1.py:13-75 + env_base_02.py:85-127
+ *   reward  src/so100_mujoco_rl/envs/env_base_01.py:144-239,  obs :241-270
+ *   TimeLimit / auto-reset: src/so100_mujoco_rl/__init__.py:5-45 + SB3 DummyVecEnv semantics.
+ *
+ * The formulation is deliberately NOT the one the CUDA kernels use: quaternion world-frame kinematics, mass matrix
+ * from per-body Jacobians, world-frame Newton-Euler bias, dense Cholesky, and MuJoCo-style primal Newton with an
+ * exact piecewise-quadratic line search (the kernels use rotation-matrix recursion, composite rigid bodies and a
+ * projected Gauss-Seidel solve).
+ *
+ * Build: see oracle/Makefile  (gcc -O2 -ffp-contract=off -pthread -shared -fPIC).
+ */
+#include "so100_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+#define NJ ORC_NJ
+#define MJMINVAL 1e-15
+
+struct orc_sim {
+  orc_model m;
+  orc_task_cfg cfg;
+  int n;
+  int64_t tick;
+  orc_env_state *env;
+  /* derived (what MuJoCo's compiler + mj_setConst produce) */
+  double base_quat[4], body_quat[NJ][4], cam_mat[9];
+  double body_I[NJ][9]; /* inertia about COM, body frame */
+  double dof_M0[NJ], kv[NJ], invw[NJ];
+  double fy;            /* focal length in pixels, env_base_02.py:100 */
+};
+
+/* ------------------------------------------------------------------ small math */
+static void q_norm(const double *q, double *o) {
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; i++) o[i] = q[i] / n;
+}
+static void q_mul(const double *a, const double *b, double *o) {
+  double r[4];
+  r[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  r[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  r[2] = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  r[3] = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  memcpy(o, r, sizeof r);
+}
+static void q_mat(const double *q, double *R) { /* row-major */
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0] = w * w + x * x - y * y - z * z; R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
+}
+static void mv(const double *R, const double *v, double *o) {
+  double r[3];
+  for (int i = 0; i < 3; i++) r[i] = R[3 * i] * v[0] + R[3 * i + 1] * v[1] + R[3 * i + 2] * v[2];
+  memcpy(o, r, sizeof r);
+}
+static void mtv(const double *R, const double *v, double *o) {
+  double r[3];
+  for (int i = 0; i < 3; i++) r[i] = R[i] * v[0] + R[3 + i] * v[1] + R[6 + i] * v[2];
+  memcpy(o, r, sizeof r);
+}
+static void mm(const double *A, const double *B, double *o) {
+  double r[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) r[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+  memcpy(o, r, sizeof r);
+}
+static void cross(const double *a, const double *b, double *o) {
+  double r[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+  memcpy(o, r, sizeof r);
+}
+static double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+/* Cholesky of a 6x6 SPD (row-major) in place (lower); returns 0 on success */
+static int chol6(double *A) {
+  for (int j = 0; j < NJ; j++) {
+    double d = A[j * NJ + j];
+    for (int k = 0; k < j; k++) d -= A[j * NJ + k] * A[j * NJ + k];
+    if (!(d > 0)) return -1;
+    d = sqrt(d);
+    A[j * NJ + j] = d;
+    for (int i = j + 1; i < NJ; i++) {
+      double s = A[i * NJ + j];
+      for (int k = 0; k < j; k++) s -= A[i * NJ + k] * A[j * NJ + k];
+      A[i * NJ + j] = s / d;
+    }
+  }
+  return 0;
+}
+static void chol6_solve(const double *L, const double *b, double *x) {
+  double y[NJ];
+  for (int i = 0; i < NJ; i++) {
+    double s = b[i];
+    for (int k = 0; k < i; k++) s -= L[i * NJ + k] * y[k];
+    y[i] = s / L[i * NJ + i];
+  }
+  for (int i = NJ - 1; i >= 0; i--) {
+    double s = y[i];
+    for (int k = i + 1; k < NJ; k++) s -= L[k * NJ + i] * x[k];
+    x[i] = s / L[i * NJ + i];
+  }
+}
+
+/* ------------------------------------------------------------------ RNG: Philox4x32-10 (Salmon et al., SC'11) */
+void orc_philox(uint64_t seed, uint32_t env_id, uint32_t tick, uint32_t stream, uint32_t out[4]) {
+  uint32_t c0 = env_id, c1 = tick, c2 = stream, c3 = 0;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+/* 24-bit uniform in [0,1): exactly representable in fp32 and fp64, so GPU and oracle see the same draw */
+static double u01(uint32_t x) { return (double)(x >> 8) * (1.0 / 16777216.0); }
+
+/* RNG streams (counter word 2) */
+enum { STREAM_RESET = 0, STREAM_TASK = 1, STREAM_NOISE = 2, STREAM_API_RESET = 3, STREAM_RESET_NOISE = 4 };
+
+/* ------------------------------------------------------------------ kinematics */
+void orc_fk(const orc_sim *s, const double *qpos, orc_kin *k) {
+  const orc_model *m = &s->m;
+  double ppos[3] = {m->base_pos[0], m->base_pos[1], m->base_pos[2]}, pquat[4];
+  memcpy(pquat, s->base_quat, sizeof pquat);
+  for (int i = 0; i < NJ; i++) {
+    double R[9], off[3], quat[4], ql[4], ax[3];
+    q_mat(pquat, R);
+    mv(R, m->body_pos[i], off);
+    for (int c = 0; c < 3; c++) k->xpos[i][c] = ppos[c] + off[c];
+    q_mul(pquat, s->body_quat[i], quat);
+    q_mat(quat, R);
+    mv(R, m->jnt_axis[i], ax);
+    memcpy(k->xaxis[i], ax, sizeof ax);
+    double half = 0.5 * qpos[i], sn = sin(half);
+    ql[0] = cos(half); ql[1] = m->jnt_axis[i][0] * sn; ql[2] = m->jnt_axis[i][1] * sn; ql[3] = m->jnt_axis[i][2] * sn;
+    q_mul(quat, ql, quat);
+    q_norm(quat, quat);
+    q_mat(quat, k->xmat[i]);
+    double off2[3], iq[4], Ri[9];
+    mv(k->xmat[i], m->body_ipos[i], off2);
+    for (int c = 0; c < 3; c++) k->xipos[i][c] = k->xpos[i][c] + off2[c];
+    q_norm(m->body_iquat[i], iq);
+    q_mat(iq, Ri);
+    mm(k->xmat[i], Ri, k->ximat[i]);
+    memcpy(ppos, k->xpos[i], sizeof ppos);
+    memcpy(pquat, quat, sizeof pquat);
+  }
+  double t[3];
+  mv(k->xmat[m->ee_body], m->ee_offset, t); /* env_base_01.py:118-127 */
+  for (int c = 0; c < 3; c++) k->end_pos[c] = k->xpos[m->ee_body][c] + t[c];
+  memcpy(k->wrist_pos, k->xpos[m->wrist_body], sizeof k->wrist_pos); /* env_base_01.py:114-116 */
+  mv(k->xmat[m->cam_body], m->cam_pos, t);
+  for (int c = 0; c < 3; c++) k->cam_xpos[c] = k->xpos[m->cam_body][c] + t[c];
+  mm(k->xmat[m->cam_body], s->cam_mat, k->cam_xmat);
+}
+
+/* world inertia of body i about its COM */
+static void world_inertia(const orc_sim *s, const orc_kin *k, int i, double *Iw) {
+  double D[9] = {0}, T[9], Rt[9];
+  D[0] = s->m.body_inertia[i][0]; D[4] = s->m.body_inertia[i][1]; D[8] = s->m.body_inertia[i][2];
+  mm(k->ximat[i], D, T);
+  for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) Rt[3 * a + b] = k->ximat[i][3 * b + a];
+  mm(T, Rt, Iw);
+}
+
+/* joint-space inertia from per-body Jacobians: M = sum_i m_i Jv^T Jv + Jw^T I_i Jw, + armature */
+static void mass_from_kin(const orc_sim *s, const orc_kin *k, double *M) {
+  memset(M, 0, sizeof(double) * NJ * NJ);
+  for (int i = 0; i < NJ; i++) {
+    double Iw[9], Jv[NJ][3], Jw[NJ][3], IJw[NJ][3];
+    world_inertia(s, k, i, Iw);
+    for (int j = 0; j <= i; j++) {
+      double r[3];
+      for (int c = 0; c < 3; c++) r[c] = k->xipos[i][c] - k->xpos[j][c];
+      memcpy(Jw[j], k->xaxis[j], sizeof Jw[j]);
+      cross(k->xaxis[j], r, Jv[j]);
+      mv(Iw, Jw[j], IJw[j]);
+    }
+    for (int a = 0; a <= i; a++)
+      for (int b = 0; b <= i; b++)
+        M[a * NJ + b] += s->m.body_mass[i] * dot3(Jv[a], Jv[b]) + dot3(Jw[a], IJw[b]);
+  }
+  for (int j = 0; j < NJ; j++) M[j * NJ + j] += s->m.jnt_armature[j];
+}
+void orc_mass_matrix(const orc_sim *s, const double *qpos, double *M) {
+  orc_kin k;
+  orc_fk(s, qpos, &k);
+  mass_from_kin(s, &k, M);
+}
+
+/* qfrc_bias = RNE(q, qd, qdd=0) incl. gravity, world frame */
+static void bias_from_kin(const orc_sim *s, const orc_kin *k, const double *qvel, double *bias) {
+  double w[NJ][3], al[NJ][3], a[NJ][3], F[NJ][3], N[NJ][3];
+  double pw[3] = {0, 0, 0}, pal[3] = {0, 0, 0}, pa[3], ppos[3];
+  for (int c = 0; c < 3; c++) { pa[c] = -s->m.gravity[c]; ppos[c] = s->m.base_pos[c]; }
+  for (int i = 0; i < NJ; i++) {
+    double r[3], t1[3], t2[3], zq[3];
+    for (int c = 0; c < 3; c++) { r[c] = k->xpos[i][c] - ppos[c]; zq[c] = k->xaxis[i][c] * qvel[i]; }
+    /* origin acceleration of body i (rigidly attached to the parent at r) */
+    cross(pal, r, t1);
+    cross(pw, r, t2);
+    cross(pw, t2, t2);
+    for (int c = 0; c < 3; c++) a[i][c] = pa[c] + t1[c] + t2[c];
+    cross(pw, zq, t1);
+    for (int c = 0; c < 3; c++) { w[i][c] = pw[c] + zq[c]; al[i][c] = pal[c] + t1[c]; }
+    /* COM acceleration, inertial force and moment */
+    double rc[3], ac[3], Iw[9], Iw_w[3], Ial[3];
+    for (int c = 0; c < 3; c++) rc[c] = k->xipos[i][c] - k->xpos[i][c];
+    cross(al[i], rc, t1);
+    cross(w[i], rc, t2);
+    cross(w[i], t2, t2);
+    for (int c = 0; c < 3; c++) ac[c] = a[i][c] + t1[c] + t2[c];
+    world_inertia(s, k, i, Iw);
+    mv(Iw, w[i], Iw_w);
+    mv(Iw, al[i], Ial);
+    cross(w[i], Iw_w, t1);
+    for (int c = 0; c < 3; c++) { F[i][c] = s->m.body_mass[i] * ac[c]; N[i][c] = Ial[c] + t1[c]; }
+    memcpy(pw, w[i], sizeof pw); memcpy(pal, al[i], sizeof pal); memcpy(pa, a[i], sizeof pa);
+    memcpy(ppos, k->xpos[i], sizeof ppos);
+  }
+  double f[3] = {0, 0, 0}, n[3] = {0, 0, 0}; /* wrench of the distal sub-chain about origin of body i+1 */
+  for (int i = NJ - 1; i >= 0; i--) {
+    double rc[3], t1[3], t2[3] = {0, 0, 0};
+    for (int c = 0; c < 3; c++) rc[c] = k->xipos[i][c] - k->xpos[i][c];
+    cross(rc, F[i], t1);
+    if (i < NJ - 1) {
+      double d[3];
+      for (int c = 0; c < 3; c++) d[c] = k->xpos[i + 1][c] - k->xpos[i][c];
+      cross(d, f, t2);
+    }
+    for (int c = 0; c < 3; c++) { n[c] = N[i][c] + t1[c] + n[c] + t2[c]; f[c] = F[i][c] + f[c]; }
+    bias[i] = dot3(k->xaxis[i], n);
+  }
+}
+void orc_bias(const orc_sim *s, const double *qpos, const double *qvel, double *bias) {
+  orc_kin k;
+  orc_fk(s, qpos, &k);
+  bias_from_kin(s, &k, qvel, bias);
+}
+
+void orc_energy(const orc_sim *s, const double *qpos, const double *qvel, double *kinetic, double *potential) {
+  orc_kin k;
+  double M[NJ * NJ], T = 0, V = 0;
+  orc_fk(s, qpos, &k);
+  mass_from_kin(s, &k, M);
+  for (int a = 0; a < NJ; a++) for (int b = 0; b < NJ; b++) T += 0.5 * qvel[a] * M[a * NJ + b] * qvel[b];
+  for (int i = 0; i < NJ; i++) V -= s->m.body_mass[i] * dot3(s->m.gravity, k.xipos[i]);
+  *kinetic = T; *potential = V;
+}
+
+/* ------------------------------------------------------------------ constraints + solver */
+typedef struct { int dof; double sign, aref, D, R, floss; int friction; } crow;
+
+static double impedance(const double *solimp, double pos) { /* MuJoCo getimpedance, margin 0 */
+  if (solimp[0] == solimp[1] || solimp[2] <= MJMINVAL) return 0.5 * (solimp[0] + solimp[1]);
+  double x = fabs(pos / solimp[2]);
+  if (x >= 1) return solimp[1];
+  if (x <= 0) return solimp[0];
+  double y;
+  if (solimp[4] == 1) y = x;
+  else if (x <= solimp[3]) y = pow(x, solimp[4]) / pow(solimp[3], solimp[4] - 1);
+  else y = 1 - pow(1 - x, solimp[4]) / pow(1 - solimp[3], solimp[4] - 1);
+  return solimp[0] + y * (solimp[1] - solimp[0]);
+}
+static void kb_from_solref(const double *solref, const double *solimp, double h, double *K, double *B) {
+  double tc = solref[0], dr = solref[1], dmax = solimp[1];
+  if (tc > 0) {
+    if (tc < 2 * h) tc = 2 * h; /* refsafe */
+    *K = 1.0 / fmax(MJMINVAL, dmax * dmax * tc * tc * dr * dr);
+    *B = 2.0 / fmax(MJMINVAL, dmax * tc);
+  } else { *K = -solref[0] / (dmax * dmax); *B = -solref[1] / dmax; }
+}
+static int make_rows(const orc_sim *s, const double *qpos, const double *qvel, crow *rows) {
+  const orc_model *m = &s->m;
+  int n = 0;
+  for (int j = 0; j < NJ; j++) { /* friction-loss rows first (MuJoCo order: equality, friction, limit, contact) */
+    if (m->jnt_frictionloss[j] <= 0) continue;
+    double K, B, imp = impedance(m->dof_solimp_friction[j], 0.0);
+    kb_from_solref(m->dof_solref_friction[j], m->dof_solimp_friction[j], m->timestep, &K, &B);
+    crow *r = &rows[n++];
+    r->dof = j; r->sign = 1; r->friction = 1; r->floss = m->jnt_frictionloss[j];
+    r->R = fmax(MJMINVAL, (1 - imp) / imp * s->invw[j]); r->D = 1 / r->R;
+    r->aref = -B * qvel[j]; /* K = 0 for friction rows */
+  }
+  for (int j = 0; j < NJ; j++) {
+    for (int side = 0; side < 2; side++) {
+      double dist = side == 0 ? qpos[j] - m->jnt_range[j][0] : m->jnt_range[j][1] - qpos[j];
+      if (!(dist < 0)) continue;
+      double K, B, imp = impedance(m->jnt_solimp_limit[j], dist);
+      kb_from_solref(m->jnt_solref_limit[j], m->jnt_solimp_limit[j], m->timestep, &K, &B);
+      crow *r = &rows[n++];
+      r->dof = j; r->sign = side == 0 ? 1 : -1; r->friction = 0; r->floss = 0;
+      r->R = fmax(MJMINVAL, (1 - imp) / imp * s->invw[j]); r->D = 1 / r->R;
+      r->aref = -B * (r->sign * qvel[j]) - K * imp * dist;
+    }
+  }
+  return n;
+}
+/* cost, gradient contribution and curvature of one row at residual r = J a - aref */
+static void row_eval(const crow *r, double res, double *cost, double *force, double *curv) {
+  if (r->friction) {
+    double rf = r->R * r->floss;
+    if (res <= -rf) { *cost = -0.5 * rf * r->floss - r->floss * res; *force = r->floss; *curv = 0; }
+    else if (res >= rf) { *cost = -0.5 * rf * r->floss + r->floss * res; *force = -r->floss; *curv = 0; }
+    else { *cost = 0.5 * r->D * res * res; *force = -r->D * res; *curv = r->D; }
+  } else if (res < 0) { *cost = 0.5 * r->D * res * res; *force = -r->D * res; *curv = r->D; }
+  else { *cost = 0; *force = 0; *curv = 0; }
+}
+static double total_cost(const double *M, const double *as, const crow *rows, int nr, const double *a) {
+  double c = 0, d[NJ];
+  for (int i = 0; i < NJ; i++) d[i] = a[i] - as[i];
+  for (int i = 0; i < NJ; i++) for (int j = 0; j < NJ; j++) c += 0.5 * d[i] * M[i * NJ + j] * d[j];
+  for (int k = 0; k < nr; k++) {
+    double rc, f, cv;
+    row_eval(&rows[k], rows[k].sign * a[rows[k].dof] - rows[k].aref, &rc, &f, &cv);
+    c += rc;
+  }
+  return c;
+}
+static int cmp_d(const void *a, const void *b) { double x = *(const double *)a, y = *(const double *)b; return (x > y) - (x < y); }
+
+static int newton_solve(const double *M, const double *as, const crow *rows, int nr, double *a) {
+  int it;
+  for (it = 0; it < 100; it++) {
+    double g[NJ], H[NJ * NJ], p[NJ], d[NJ];
+    for (int i = 0; i < NJ; i++) d[i] = a[i] - as[i];
+    for (int i = 0; i < NJ; i++) { g[i] = 0; for (int j = 0; j < NJ; j++) g[i] += M[i * NJ + j] * d[j]; }
+    memcpy(H, M, sizeof H);
+    for (int k = 0; k < nr; k++) {
+      double rc, f, cv;
+      row_eval(&rows[k], rows[k].sign * a[rows[k].dof] - rows[k].aref, &rc, &f, &cv);
+      g[rows[k].dof] -= rows[k].sign * f;
+      H[rows[k].dof * NJ + rows[k].dof] += cv;
+    }
+    double gn = 0, scale = 1;
+    for (int i = 0; i < NJ; i++) {
+      double f = 0;
+      for (int j = 0; j < NJ; j++) f += M[i * NJ + j] * as[j];
+      gn += g[i] * g[i]; scale += fabs(f);
+    }
+    if (sqrt(gn) <= 1e-14 * scale) break;
+    if (chol6(H)) return -1;
+    for (int i = 0; i < NJ; i++) g[i] = -g[i];
+    chol6_solve(H, g, p);
+    /* exact line search: phi'(alpha) is piecewise linear and increasing; walk its breakpoints */
+    double bp[3 * 2 * NJ + 2];
+    int nb = 0;
+    for (int k = 0; k < nr; k++) {
+      double slope = rows[k].sign * p[rows[k].dof], r0 = rows[k].sign * a[rows[k].dof] - rows[k].aref;
+      if (slope == 0) continue;
+      if (rows[k].friction) {
+        double rf = rows[k].R * rows[k].floss, a1 = (-rf - r0) / slope, a2 = (rf - r0) / slope;
+        if (a1 > 0) bp[nb++] = a1;
+        if (a2 > 0) bp[nb++] = a2;
+      } else { double a1 = -r0 / slope; if (a1 > 0) bp[nb++] = a1; }
+    }
+    qsort(bp, nb, sizeof(double), cmp_d);
+    bp[nb++] = INFINITY;
+    double Mp[NJ], pMp = 0, lo = 0, alpha = 0;
+    for (int i = 0; i < NJ; i++) { Mp[i] = 0; for (int j = 0; j < NJ; j++) Mp[i] += M[i * NJ + j] * p[j]; pMp += p[i] * Mp[i]; }
+    for (int b = 0; b < nb; b++) {
+      /* derivative and curvature just inside the segment (lo, bp[b]) */
+      double mid = isinf(bp[b]) ? lo + 1.0 : 0.5 * (lo + bp[b]);
+      double dphi = 0, cphi = pMp, x[NJ];
+      for (int i = 0; i < NJ; i++) { x[i] = a[i] + mid * p[i]; dphi += Mp[i] * (x[i] - as[i]); }
+      for (int k = 0; k < nr; k++) {
+        double rc, f, cv, sp = rows[k].sign * p[rows[k].dof];
+        row_eval(&rows[k], rows[k].sign * x[rows[k].dof] - rows[k].aref, &rc, &f, &cv);
+        dphi -= f * sp; cphi += cv * sp * sp;
+      }
+      double root = mid - dphi / cphi; /* phi' is linear inside the segment */
+      if (root <= bp[b]) { alpha = root < lo ? lo : root; break; }
+      lo = bp[b]; alpha = lo;
+    }
+    if (!(alpha > 0)) break;
+    for (int i = 0; i < NJ; i++) a[i] += alpha * p[i];
+  }
+  return it;
+}
+
+static void forward_from_kin(const orc_sim *s, const orc_kin *k, const double *qpos, const double *qvel,
+                             const double *ctrl, const double *warm, double *qacc, double *qacc_smooth,
+                             double *qfrc_constraint, int *niter_out) {
+  const orc_model *m = &s->m;
+  double M[NJ * NJ], L[NJ * NJ], bias[NJ], fs[NJ], as[NJ];
+  mass_from_kin(s, k, M);
+  bias_from_kin(s, k, qvel, bias);
+  for (int j = 0; j < NJ; j++) { /* position servo, SURVEY B.4 */
+    double c = fmin(fmax(ctrl[j], m->act_ctrlrange[j][0]), m->act_ctrlrange[j][1]);
+    double f = m->act_kp[j] * c - m->act_kp[j] * qpos[j] - s->kv[j] * qvel[j];
+    f = fmin(fmax(f, m->act_forcerange[j][0]), m->act_forcerange[j][1]);
+    fs[j] = f - bias[j];
+  }
+  memcpy(L, M, sizeof L);
+  chol6(L);
+  chol6_solve(L, fs, as);
+  crow rows[3 * NJ];
+  int nr = make_rows(s, qpos, qvel, rows);
+  double a[NJ];
+  if (warm && total_cost(M, as, rows, nr, warm) < total_cost(M, as, rows, nr, as)) memcpy(a, warm, sizeof a);
+  else memcpy(a, as, sizeof a);
+  int it = newton_solve(M, as, rows, nr, a);
+  memcpy(qacc, a, sizeof a);
+  if (qacc_smooth) memcpy(qacc_smooth, as, sizeof as);
+  if (qfrc_constraint) {
+    memset(qfrc_constraint, 0, sizeof(double) * NJ);
+    for (int r = 0; r < nr; r++) {
+      double rc, f, cv;
+      row_eval(&rows[r], rows[r].sign * a[rows[r].dof] - rows[r].aref, &rc, &f, &cv);
+      qfrc_constraint[rows[r].dof] += rows[r].sign * f;
+    }
+  }
+  if (niter_out) *niter_out = it;
+}
+void orc_forward(const orc_sim *s, const double *qpos, const double *qvel, const double *ctrl,
+                 const double *qacc_warm, double *qacc, double *qacc_smooth, double *qfrc_constraint, int *niter_out) {
+  orc_kin k;
+  orc_fk(s, qpos, &k);
+  forward_from_kin(s, &k, qpos, qvel, ctrl, qacc_warm, qacc, qacc_smooth, qfrc_constraint, niter_out);
+}
+
+/* n x mj_step on the arm; if kin_last != NULL it receives the kinematics computed in the LAST substep */
+static void substeps_kin(const orc_sim *s, double *qpos, double *qvel, double *warm, const double *ctrl, int n,
+                         orc_kin *kin_last) {
+  double h = s->m.timestep;
+  for (int t = 0; t < n; t++) {
+    orc_kin k;
+    double qacc[NJ];
+    orc_fk(s, qpos, &k);
+    forward_from_kin(s, &k, qpos, qvel, ctrl, warm, qacc, NULL, NULL, NULL);
+    for (int j = 0; j < NJ; j++) { /* mj_Euler, SURVEY B.8 (no joint damping -> no implicit term) */
+      qvel[j] += h * qacc[j];
+      qpos[j] += h * qvel[j];
+      warm[j] = qacc[j];
+    }
+    if (kin_last && t == n - 1) *kin_last = k;
+  }
+}
+void orc_substeps(const orc_sim *s, double *qpos, double *qvel, double *qacc_warm, const double *ctrl, int n) {
+  substeps_kin(s, qpos, qvel, qacc_warm, ctrl, n, NULL);
+}
+
+/* ------------------------------------------------------------------ construction */
+int orc_sizeof_model(void) { return (int)sizeof(orc_model); }
+int orc_sizeof_task_cfg(void) { return (int)sizeof(orc_task_cfg); }
+int orc_sizeof_env_state(void) { return (int)sizeof(orc_env_state); }
+
+orc_sim *orc_create(const orc_model *m, const orc_task_cfg *cfg) {
+  if (!m || !cfg || m->struct_size != (int)sizeof(orc_model) || cfg->struct_size != (int)sizeof(orc_task_cfg)) return NULL;
+  if (cfg->num_envs <= 0) return NULL;
+  if (cfg->task != 1 && cfg->task != 2 && cfg->task != 5) return NULL;
+  orc_sim *s = (orc_sim *)calloc(1, sizeof(orc_sim));
+  s->m = *m; s->cfg = *cfg; s->n = cfg->num_envs;
+  s->env = (orc_env_state *)calloc((size_t)s->n, sizeof(orc_env_state));
+  q_norm(m->base_quat, s->base_quat);
+  for (int i = 0; i < NJ; i++) q_norm(m->body_quat[i], s->body_quat[i]);
+  double cq[4];
+  q_norm(m->cam_quat, cq);
+  q_mat(cq, s->cam_mat);
+  s->fy = 0.5 * cfg->cam_res_h / tan(m->cam_fovy_deg * M_PI / 180.0 / 2);
+  /* mj_setConst: dof_M0, dof_invweight0 at qpos0 = 0; kv from dampratio */
+  double q0[NJ] = {0}, M[NJ * NJ], L[NJ * NJ];
+  orc_mass_matrix(s, q0, M);
+  memcpy(L, M, sizeof L);
+  chol6(L);
+  for (int j = 0; j < NJ; j++) {
+    double e[NJ] = {0}, x[NJ];
+    e[j] = 1;
+    chol6_solve(L, e, x);
+    s->invw[j] = x[j];
+    s->dof_M0[j] = M[j * NJ + j];
+    s->kv[j] = m->act_dampratio[j] > 0 ? m->act_dampratio[j] * 2 * sqrt(m->act_kp[j] * s->dof_M0[j]) : m->act_kv[j];
+  }
+  return s;
+}
+void orc_destroy(orc_sim *s) { if (s) { free(s->env); free(s); } }
+int orc_obs_dim(const orc_sim *s) { return s->cfg.task == 5 ? 8 : 15; }
+void orc_get_derived(const orc_sim *s, double *dof_M0, double *kv, double *invweight0) {
+  for (int j = 0; j < NJ; j++) { dof_M0[j] = s->dof_M0[j]; kv[j] = s->kv[j]; invweight0[j] = s->invw[j]; }
+}
+orc_env_state *orc_state(orc_sim *s, int env) { return (env >= 0 && env < s->n) ? &s->env[env] : NULL; }
+int64_t orc_get_tick(const orc_sim *s) { return s->tick; }
+void orc_set_tick(orc_sim *s, int64_t tick) { s->tick = tick; }
+
+/* ------------------------------------------------------------------ task logic */
+static void draw(const orc_sim *s, int env, int stream, double u[4], uint32_t raw[4]) {
+  uint32_t r[4];
+  int64_t gid = s->cfg.env_offset + env;
+  orc_philox(s->cfg.seed, (uint32_t)gid, (uint32_t)s->tick, (uint32_t)stream, r);
+  for (int i = 0; i < 4; i++) u[i] = u01(r[i]);
+  if (raw) memcpy(raw, r, sizeof r);
+}
+/* block (r, theta) draw of env01_v1.py:45-49 / env02_v1.py:55-59; slot 1 is the discarded theta */
+static void place_block(const orc_sim *s, orc_env_state *e, const double u[4]) {
+  double dist = s->cfg.block_dist_range[0] + (s->cfg.block_dist_range[1] - s->cfg.block_dist_range[0]) * u[0];
+  double theta = -0.5 * M_PI + (-s->cfg.block_theta_half + 2 * s->cfg.block_theta_half * u[2]);
+  e->block[0] = dist * cos(theta); e->block[1] = dist * sin(theta); e->block[2] = 0.0;
+}
+static void obs_env0102(const orc_env_state *e, float *obs) { /* env_base_01.py:241-270 */
+  for (int j = 0; j < NJ; j++) obs[j] = (float)e->qpos[j];
+  for (int c = 0; c < 3; c++) {
+    obs[6 + c] = (float)(e->block_xpos[c] - e->end_pos[c]);
+    obs[9 + c] = (float)e->block_xpos[c];
+    obs[12 + c] = (float)e->end_pos[c];
+  }
+}
+/* env_base_02.py:88-127 on the STALE camera pose and the fresh block position; returns 1 if detected */
+static int project05(const orc_sim *s, const orc_env_state *e, double *cx, double *cy) {
+  double rel[3], pc[3];
+  for (int c = 0; c < 3; c++) rel[c] = e->block[c] - e->cam_xpos[c];
+  mtv(e->cam_xmat, rel, pc);
+  double W = s->cfg.cam_res_w, H = s->cfg.cam_res_h;
+  double u = s->fy * pc[0] / pc[2] + W / 2, v = s->fy * pc[1] / pc[2] + H / 2;
+  if (isnan(u) || isnan(v)) return 0;
+  u = trunc(u); v = trunc(v); /* int(): toward zero, so (-1,0) passes the bounds test */
+  if (u < 0 || u >= W || v < 0 || v >= H) return 0;
+  *cx = (W - u) / W; *cy = (H - v) / H;
+  return 1;
+}
+static void obs_env05(const orc_sim *s, orc_env_state *e, int env, int stream, float *obs) { /* env05_v1.py:32-75 */
+  double cx = -1.0, cy = -1.0, px, py;
+  if (project05(s, e, &px, &py)) {
+    double u[4];
+    draw(s, env, stream, u, NULL);
+    cx = px + (-s->cfg.obs_noise + 2 * s->cfg.obs_noise * u[0]);
+    cy = py + (-s->cfg.obs_noise + 2 * s->cfg.obs_noise * u[1]);
+  }
+  for (int j = 0; j < NJ; j++) obs[j] = (float)e->cmd[j];
+  obs[6] = (float)cx; obs[7] = (float)cy;
+}
+static void snapshot(orc_env_state *e, const orc_kin *k) {
+  memcpy(e->end_pos, k->end_pos, sizeof e->end_pos);
+  memcpy(e->wrist_pos, k->wrist_pos, sizeof e->wrist_pos);
+  memcpy(e->cam_xpos, k->cam_xpos, sizeof e->cam_xpos);
+  memcpy(e->cam_xmat, k->cam_xmat, sizeof e->cam_xmat);
+  memcpy(e->block_xpos, e->block, sizeof e->block_xpos);
+}
+
+/* MujocoEnv.reset = mj_resetData + reset_model (no mj_forward: kinematics stay zero) */
+static void reset_env(const orc_sim *s, orc_env_state *e, int env, int stream, float *obs) {
+  const orc_task_cfg *c = &s->cfg;
+  double u[4];
+  uint32_t raw[4];
+  memset(e->qpos, 0, sizeof e->qpos); memset(e->qvel, 0, sizeof e->qvel);
+  memset(e->qacc_warm, 0, sizeof e->qacc_warm); memset(e->ctrl, 0, sizeof e->ctrl);
+  e->time = 0; e->elapsed_steps = 0; e->ep_return = 0;
+  memset(e->end_pos, 0, sizeof e->end_pos); memset(e->wrist_pos, 0, sizeof e->wrist_pos);
+  memset(e->block_xpos, 0, sizeof e->block_xpos);
+  memset(e->cam_xpos, 0, sizeof e->cam_xpos); memset(e->cam_xmat, 0, sizeof e->cam_xmat);
+  if (c->task == 1) { /* env01_v1.py:39-63 */
+    draw(s, env, stream, u, raw);
+    place_block(s, e, u);
+    int idx = (int)(((uint64_t)raw[3] * (uint64_t)c->n_start) >> 32);
+    for (int j = 0; j < NJ - 1; j++) e->qpos[j] = c->start_positions[idx][j]; /* Jaw skipped */
+  } else if (c->task == 2) { /* env02_v1.py:70-81, :52-68 */
+    draw(s, env, stream, u, NULL);
+    double prev[3] = {e->task_block_pos[0], e->task_block_pos[1], e->task_block_pos[2]};
+    place_block(s, e, u);
+    if (!e->has_last_block) memcpy(e->last_block_pos, e->block, sizeof e->last_block_pos);
+    else memcpy(e->last_block_pos, prev, sizeof prev);
+    memcpy(e->task_block_pos, e->block, sizeof e->task_block_pos);
+    e->has_last_block = 1;
+    for (int j = 0; j < NJ; j++) e->qpos[j] = c->rest_position[j];
+  } else { /* env03_v1.py:203-215, :35-57 */
+    for (int j = 0; j < NJ; j++) { e->qpos[j] = c->start_position05[j]; e->cmd[j] = c->start_position05[j]; }
+    for (int k = 0; k < 3; k++) {
+      e->target[k] = (c->block_space_start[0][k] + c->block_space_start[1][k]) / 2;
+      e->block[k] = e->target[k];
+    }
+    e->target_dt = 0.01; e->target_time = 0.0;
+    e->centre_valid = 0; e->miss_count = 0;
+  }
+  if (c->flags & 1u) { /* SO100_FLAG_FRESH_FK_ON_RESET: what a mj_forward in reset_model would give */
+    orc_kin k;
+    orc_fk(s, e->qpos, &k);
+    snapshot(e, &k);
+  }
+  if (c->task == 5) obs_env05(s, e, env, STREAM_RESET_NOISE, obs); else obs_env0102(e, obs);
+}
+
+static double joint_penalty(const orc_sim *s, const double *ang) { /* env_base_01.py:144-163 */
+  double r = 0;
+  for (int j = 0; j < NJ; j++) {
+    double lo = s->m.jnt_range[j][0], hi = s->m.jnt_range[j][1];
+    double lt = lo + 0.05 * (hi - lo), ut = hi - 0.05 * (hi - lo);
+    if (ang[j] < lt) r -= (lt - ang[j]) * 10.0;
+    else if (ang[j] > ut) r -= (ang[j] - ut) * 10.0;
+  }
+  return r;
+}
+static double reward_env0102(const orc_sim *s, orc_env_state *e) { /* env_base_01.py:180-239 */
+  double reward = 0, d[3];
+  for (int c = 0; c < 3; c++) d[c] = e->block_xpos[c] - e->end_pos[c];
+  double distance = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  if (e->block_xpos[1] < -0.1) {
+    double pitch = e->qpos[1];
+    if (e->ever_stepped && pitch < -0.7 * M_PI) reward += (pitch + 0.7 * M_PI) * 0.7;
+  }
+  if (e->ever_stepped && e->end_pos[2] < 0.02) reward += (e->end_pos[2] - 0.02) * 20.0;
+  if (e->ever_stepped && e->wrist_pos[2] < 0.08) {
+    double w = (e->wrist_pos[2] - 0.08) * 10.0;
+    reward += fmin(fmax(w, -0.8), 0.8);
+  }
+  reward += fmin(-distance + 0.02, 0.0) * 0.5;
+  reward += joint_penalty(s, e->qpos);
+  e->ever_stepped = 1;
+  return reward;
+}
+
+static void step_env(const orc_sim *s, orc_env_state *e, int env, const float *act, float *obs, double *reward,
+                     uint8_t *terminated, uint8_t *truncated, float *terminal_obs, double *ep_return, int32_t *ep_len) {
+  const orc_task_cfg *c = &s->cfg;
+  const int od = c->task == 5 ? 8 : 15;
+  double a[NJ], rew = 0;
+  int term = 0;
+  for (int j = 0; j < NJ; j++) {
+    a[j] = (double)act[j];
+    if (c->flags & 2u) a[j] = fmin(fmax(a[j], -1.0), 1.0);
+  }
+  orc_kin kin;
+  if (c->task == 1 || c->task == 2) {
+    rew = reward_env0102(s, e); /* PRE-step reward on stale kinematics */
+    for (int j = 0; j < NJ; j++) e->ctrl[j] = e->qpos[j] + a[j] * c->joint_step_scale;
+    if (c->task == 2) {
+      double d[3];
+      for (int k = 0; k < 3; k++) d[k] = e->block_xpos[k] - e->end_pos[k];
+      if (sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) < c->reach_threshold) { /* env02_v1.py:29-37 */
+        double bd = 0, u[4];
+        for (int k = 0; k < 3; k++) bd += (e->task_block_pos[k] - e->last_block_pos[k]) * (e->task_block_pos[k] - e->last_block_pos[k]);
+        rew += sqrt(bd) * 20;
+        draw(s, env, STREAM_TASK, u, NULL);
+        memcpy(e->last_block_pos, e->task_block_pos, sizeof e->last_block_pos);
+        place_block(s, e, u);
+        memcpy(e->task_block_pos, e->block, sizeof e->task_block_pos);
+      }
+    }
+    substeps_kin(s, e->qpos, e->qvel, e->qacc_warm, e->ctrl, s->m.nsubstep, &kin);
+    snapshot(e, &kin);
+    obs_env0102(e, obs);
+  } else {
+    /* env03_v1.py:124-201 */
+    double time = e->elapsed_steps * (s->m.nsubstep * s->m.timestep);
+    double f = fmin(time / c->ramp_seconds, 1.0);
+    double smin[3], smax[3], speed;
+    for (int k = 0; k < 3; k++) {
+      smin[k] = c->block_space_start[0][k] + f * (c->block_space_end[0][k] - c->block_space_start[0][k]);
+      smax[k] = c->block_space_start[1][k] + f * (c->block_space_end[1][k] - c->block_space_start[1][k]);
+    }
+    speed = f <= 0.05 ? c->block_speed_min : c->block_speed_min + (f - 0.05) * (c->block_speed_max - c->block_speed_min) / (1.0 - 0.05);
+    double d[3], dist;
+    for (int k = 0; k < 3; k++) d[k] = e->target[k] - e->block[k];
+    dist = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    if (!(time - e->target_time < e->target_dt && dist > 0.02)) { /* :77-93 */
+      double u[4];
+      draw(s, env, STREAM_TASK, u, NULL);
+      for (int k = 0; k < 3; k++) e->target[k] = smin[k] + (smax[k] - smin[k]) * u[k];
+      e->target_dt = 1.2 + (5.1 - 1.2) * u[3];
+      e->target_time = time;
+    }
+    for (int k = 0; k < 3; k++) d[k] = e->target[k] - e->block[k]; /* :95-122 */
+    dist = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    if (dist > 0) {
+      double sd = fmin(speed * s->m.timestep, dist);
+      for (int k = 0; k < 3; k++) e->block[k] += d[k] / dist * sd;
+    }
+    double newcmd[NJ];
+    for (int j = 0; j < NJ; j++) { newcmd[j] = e->cmd[j] + a[j] * c->joint_step_scale; e->ctrl[j] = newcmd[j]; }
+    substeps_kin(s, e->qpos, e->qvel, e->qacc_warm, e->ctrl, s->m.nsubstep, &kin);
+    snapshot(e, &kin);
+    obs_env05(s, e, env, STREAM_NOISE, obs);
+    if (obs[6] == -1.0f && obs[7] == -1.0f) { /* :152-164 */
+      if (e->miss_count > c->lost_limit) term = 1;
+      e->miss_count += 1;
+    } else { e->last_centre[0] = obs[6]; e->last_centre[1] = obs[7]; e->centre_valid = 1; e->miss_count = 0; }
+    rew = 0.5;
+    if (e->centre_valid) rew += -sqrt((0.5 - e->last_centre[0]) * (0.5 - e->last_centre[0]) + (0.5 - e->last_centre[1]) * (0.5 - e->last_centre[1]));
+    rew += joint_penalty(s, e->cmd); /* commanded (old) angles, SURVEY Q7 */
+    double pen = 0, av[NJ]; /* env_base_01.py:165-178 with timestep = 0.002 */
+    for (int j = 0; j < NJ; j++) av[j] = (newcmd[j] - e->cmd[j]) / s->m.timestep;
+    if (e->angvel_valid) for (int j = 0; j < NJ; j++) pen += fabs(av[j] - e->last_angvel[j]) * 0.0025;
+    memcpy(e->last_angvel, av, sizeof av);
+    e->angvel_valid = 1;
+    rew += -pen * f;
+    obs[6] *= 5; obs[7] *= 5;
+    memcpy(e->cmd, newcmd, sizeof newcmd);
+  }
+  e->elapsed_steps += 1;
+  e->time = e->elapsed_steps * (s->m.nsubstep * s->m.timestep);
+  e->ep_return += rew;
+  int trunc_ = e->elapsed_steps >= c->max_episode_steps;
+  *reward = rew; *terminated = (uint8_t)term; *truncated = (uint8_t)(trunc_ && !term);
+  if (term || trunc_) {
+    if (terminal_obs) memcpy(terminal_obs, obs, sizeof(float) * od);
+    if (ep_return) *ep_return = e->ep_return;
+    if (ep_len) *ep_len = e->elapsed_steps;
+    reset_env(s, e, env, STREAM_RESET, obs);
+  }
+}
+
+/* ---- minimal pthread parallel-for over envs (this image's gcc has no libgomp) */
+typedef struct {
+  orc_sim *s; int lo, hi, is_step;
+  const uint8_t *mask; const float *actions; float *obs; double *reward; uint8_t *terminated, *truncated;
+  float *terminal_obs; double *ep_return; int32_t *ep_len;
+} job_t;
+static void *job_run(void *p) {
+  job_t *j = (job_t *)p;
+  orc_sim *s = j->s;
+  const int od = orc_obs_dim(s);
+  for (int i = j->lo; i < j->hi; i++) {
+    if (j->is_step)
+      step_env(s, &s->env[i], i, j->actions + (size_t)i * NJ, j->obs + (size_t)i * od, j->reward + i, j->terminated + i,
+               j->truncated + i, j->terminal_obs ? j->terminal_obs + (size_t)i * od : NULL,
+               j->ep_return ? j->ep_return + i : NULL, j->ep_len ? j->ep_len + i : NULL);
+    else if (!j->mask || j->mask[i]) reset_env(s, &s->env[i], i, STREAM_API_RESET, j->obs + (size_t)i * od);
+  }
+  return NULL;
+}
+int orc_hw_threads(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }
+static void run_jobs(job_t *proto, int nthreads) {
+  int n = proto->s->n;
+  if (nthreads <= 0) nthreads = orc_hw_threads();
+  if (nthreads > n) nthreads = n;
+  if (nthreads > 256) nthreads = 256;
+  if (nthreads <= 1) { proto->lo = 0; proto->hi = n; job_run(proto); return; }
+  pthread_t th[256];
+  job_t jobs[256];
+  for (int t = 0; t < nthreads; t++) {
+    jobs[t] = *proto;
+    jobs[t].lo = (int)((int64_t)n * t / nthreads); jobs[t].hi = (int)((int64_t)n * (t + 1) / nthreads);
+    pthread_create(&th[t], NULL, job_run, &jobs[t]);
+  }
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+}
+
+void orc_reset(orc_sim *s, const uint8_t *mask, float *obs, int nthreads) {
+  job_t j = {0};
+  j.s = s; j.is_step = 0; j.mask = mask; j.obs = obs;
+  run_jobs(&j, nthreads);
+}
+
+void orc_step(orc_sim *s, const float *actions, float *obs, double *reward, uint8_t *terminated,
+              uint8_t *truncated, float *terminal_obs, double *ep_return, int32_t *ep_len, int nthreads) {
+  s->tick += 1;
+  job_t j = {0};
+  j.s = s; j.is_step = 1; j.actions = actions; j.obs = obs; j.reward = reward; j.terminated = terminated;
+  j.truncated = truncated; j.terminal_obs = terminal_obs; j.ep_return = ep_return; j.ep_len = ep_len;
+  run_jobs(&j, nthreads);
+}

@@ -1,0 +1,84 @@
+"""ctypes loader of libso100_b200.so — the C ABI declared in include/so100_b200.h.
+
+There is NO fallback: if the library has not been built (`python __graft_entry__.py build`) the import of anything that
+needs it raises, and every call that needs a GPU raises `So100Error` when CUDA reports a failure.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from .model import So100Model
+from .tasks import So100TaskCfg
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libso100_b200.so")
+
+# every symbol include/so100_b200.h declares (tests/test_abi.py checks the two lists against each other)
+EXPORTS = [
+    "so100_abi_version", "so100_last_error", "so100_obs_dim", "so100_act_dim", "so100_create", "so100_destroy",
+    "so100_reset", "so100_step", "so100_reset_host", "so100_step_host", "so100_get_state", "so100_set_state",
+    "so100_get_tick", "so100_set_tick", "so100_forward_dynamics", "so100_host_forward", "so100_get_derived",
+    "so100_get_stats",
+]
+
+
+class So100Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libso100_b200 error {code}: {msg}")
+        self.code = code
+
+
+class StateView(ctypes.Structure):
+    """ctypes mirror of `so100_state_view`."""
+    _fields_ = [(n, ctypes.c_void_p) for n in
+                ("qpos", "qvel", "qacc_warm", "block", "snap", "aux", "counters", "ep_return")]
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+            "so100_mujoco_rl_b200 has no CPU or PyTorch fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    dp = ctypes.POINTER(ctypes.c_double)
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    L.so100_abi_version.restype = ci
+    L.so100_last_error.restype = ctypes.c_char_p
+    L.so100_obs_dim.argtypes = [ci]
+    L.so100_act_dim.argtypes = [ci]
+    L.so100_create.argtypes = [ctypes.POINTER(So100Model), ctypes.POINTER(So100TaskCfg), ci, ctypes.POINTER(vp)]
+    L.so100_destroy.argtypes = [vp]
+    L.so100_destroy.restype = None
+    L.so100_reset.argtypes = [vp, vp, vp, vp]
+    L.so100_step.argtypes = [vp] + [vp] * 8 + [vp]
+    L.so100_reset_host.argtypes = [vp, vp, vp]
+    L.so100_step_host.argtypes = [vp] + [vp] * 8 + [vp]
+    L.so100_get_state.argtypes = [vp, ctypes.POINTER(StateView), vp]
+    L.so100_set_state.argtypes = [vp, ctypes.POINTER(StateView), vp]
+    L.so100_get_tick.argtypes = [vp, i64p]
+    L.so100_set_tick.argtypes = [vp, ctypes.c_int64]
+    L.so100_forward_dynamics.argtypes = [vp, ci] + [vp] * 7 + [vp]
+    L.so100_host_forward.argtypes = [ctypes.POINTER(So100Model), ci, dp, dp, dp, dp, dp, dp, dp, ci]
+    L.so100_get_derived.argtypes = [vp, dp, dp, dp]
+    L.so100_get_stats.argtypes = [vp, i64p, i64p, i64p]
+    for name in EXPORTS:
+        if name not in ("so100_last_error", "so100_destroy"):
+            getattr(L, name).restype = ci
+    if L.so100_abi_version() != 1:
+        raise ImportError("libso100_b200.so has an unexpected ABI version; rebuild it")
+    _lib = L
+    return L
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        raise So100Error(rc, lib().so100_last_error().decode("utf-8", "replace"))
+    return rc

@@ -1,0 +1,942 @@
+// so100_b200.cu — libso100_b200.so: C ABI (include/so100_b200.h) + sm_100a kernels of the batched so100 env step.
+//
+// One thread owns one environment for the whole env step: it loads the env's structure-of-arrays state (coalesced),
+// runs the task's pre-step logic, 16 physics substeps entirely in registers (so100_dyn.cuh), the observation /
+// reward / termination / TimeLimit logic and the in-kernel auto-reset, and stores the state back.  Observations and
+// actions cross the ABI as row-major [N, dim] fp32; they are staged through shared memory so that global accesses
+// stay coalesced.  No tensor cores: nothing here is a large dense contraction (6x6 systems per env).
+//
+// Reference behaviour replaced (paths relative to the reference repo, src/so100_mujoco_rl/):
+//   envs/env01_v1.py:15-63, envs/env02_v1.py:18-81, envs/env03_v1.py:35-215, envs/env05_v1.py:32-75,
+//   envs/env_base_01.py:107-270, envs/env_base_02.py:85-127, __init__.py:5-45, and mujoco.mj_step (3rd party).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <cmath>
+#include <new>
+#include <string>
+
+#include "../../include/so100_b200.h"
+#include "so100_dyn.cuh"
+
+// ------------------------------------------------------------------------------------------------ error plumbing
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(SO100_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ device constants
+constexpr int kBlock = 64;          // threads per CTA (one env each); 7 CTAs/SM keep 65 536 envs in one wave on 148 SMs
+constexpr int kMaxStart = SO100_MAX_START;
+constexpr int kSnap = 12, kAux = 24, kCnt = 4;
+enum { F_EVER_STEPPED = 1, F_HAS_LAST_BLOCK = 2, F_ANGVEL_VALID = 4, F_CENTRE_VALID = 8 };
+enum { STREAM_RESET = 0, STREAM_TASK = 1, STREAM_NOISE = 2, STREAM_API_RESET = 3, STREAM_RESET_NOISE = 4 };
+
+struct TaskC {
+  int task, n, max_steps, n_start, lost_limit, nsub;
+  unsigned flags;
+  unsigned seed_lo, seed_hi;
+  long long env_offset;
+  float h, dt_env, step_scale;
+  float kp[SO_NJ], kv[SO_NJ], ctrl_lo[SO_NJ], ctrl_hi[SO_NJ], frc_lo[SO_NJ], frc_hi[SO_NJ];
+  float pen_lo[SO_NJ], pen_hi[SO_NJ];  // joint-penalty thresholds, env_base_01.py:155-156
+  float rest[SO_NJ], start05[SO_NJ];
+  float dist_lo, dist_hi, theta_half, reach;
+  float space_s[2][3], space_e[2][3], speed_min, speed_max, ramp, res_w, res_h, fy, noise;
+};
+
+struct Consts {
+  DynC<float> dyn;
+  ConC<float> con;
+  KinC<float> kin;
+  TaskC t;
+};
+
+struct Bufs {
+  float *qpos, *qvel, *warm, *block, *snap, *aux, *ep_return;
+  int* cnt;
+  const float* start_tab;  // [n_start][6]
+  unsigned long long* stats;  // [0] solver non-converged, [1] nan resets
+};
+
+struct StepIO {
+  const float* actions;
+  float *obs, *reward, *terminal_obs, *ep_return_out;
+  uint8_t *terminated, *truncated;
+  int* ep_len_out;
+  unsigned tick;
+};
+
+// ------------------------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ uint4 philox4x32(unsigned k0, unsigned k1, unsigned c0, unsigned c1, unsigned c2, unsigned c3) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ float u01(unsigned x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ uint4 draw(const TaskC& t, int env, unsigned tick, unsigned stream) {
+  return philox4x32(t.seed_lo, t.seed_hi, (unsigned)(t.env_offset + env), tick, stream, 0u);
+}
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+struct EnvRegs {  // everything one env carries through a step, in registers
+  float q[SO_NJ], v[SO_NJ], w[SO_NJ];
+  float blk[3];
+  float snap[kSnap];
+  float aux[kAux];
+  int elapsed, flags, miss, t0step;
+  float ep_ret;
+};
+
+template <int TASK>
+__device__ __forceinline__ void load_env(const Bufs& B, int n, int i, EnvRegs& e) {
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) { e.q[j] = B.qpos[j * n + i]; e.v[j] = B.qvel[j * n + i]; e.w[j] = B.warm[j * n + i]; }
+#pragma unroll
+  for (int k = 0; k < 3; k++) e.blk[k] = B.block[k * n + i];
+  constexpr int ns = TASK == 5 ? 12 : 7, na = TASK == 5 ? 18 : (TASK == 2 ? 6 : 0);
+#pragma unroll
+  for (int k = 0; k < ns; k++) e.snap[k] = B.snap[k * n + i];
+#pragma unroll
+  for (int k = 0; k < na; k++) e.aux[k] = B.aux[k * n + i];
+  e.elapsed = B.cnt[i]; e.flags = B.cnt[n + i];
+  if (TASK == 5) { e.miss = B.cnt[2 * n + i]; e.t0step = B.cnt[3 * n + i]; }
+  e.ep_ret = B.ep_return[i];
+}
+template <int TASK>
+__device__ __forceinline__ void store_env(const Bufs& B, int n, int i, const EnvRegs& e) {
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) { B.qpos[j * n + i] = e.q[j]; B.qvel[j * n + i] = e.v[j]; B.warm[j * n + i] = e.w[j]; }
+#pragma unroll
+  for (int k = 0; k < 3; k++) B.block[k * n + i] = e.blk[k];
+  constexpr int ns = TASK == 5 ? 12 : 7, na = TASK == 5 ? 18 : (TASK == 2 ? 6 : 0);
+#pragma unroll
+  for (int k = 0; k < ns; k++) B.snap[k * n + i] = e.snap[k];
+#pragma unroll
+  for (int k = 0; k < na; k++) B.aux[k * n + i] = e.aux[k];
+  B.cnt[i] = e.elapsed; B.cnt[n + i] = e.flags;
+  if (TASK == 5) { B.cnt[2 * n + i] = e.miss; B.cnt[3 * n + i] = e.t0step; }
+  B.ep_return[i] = e.ep_ret;
+}
+
+// snapshot layout  Env01/02: end_pos[0..2], wrist_z[3], block_xpos[4..6];  Env05: cam_xpos[0..2], cam_xmat[3..11]
+// aux layout       Env02: task_block_pos[0..2], last_block_pos[3..5]
+//                  Env05: cmd[0..5], last_angvel[6..11], target[12..14], target_dt[15], last_centre[16..17]
+
+template <int TASK>
+__device__ __forceinline__ void take_snapshot(const Consts& C, const float* s, const float* c, EnvRegs& e) {
+  KinOut<float> ko;
+  task_kinematics<float, TASK == 5>(C.dyn, C.kin, s, c, ko);
+  if (TASK == 5) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) e.snap[k] = ko.cam_pos[k];
+#pragma unroll
+    for (int k = 0; k < 9; k++) e.snap[3 + k] = ko.cam_R[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { e.snap[k] = ko.end_pos[k]; e.snap[4 + k] = e.blk[k]; }
+    e.snap[3] = ko.wrist[2];
+  }
+}
+
+__device__ __forceinline__ void place_block(const TaskC& t, const uint4& r, float* blk) {
+  // env01_v1.py:45-49 / env02_v1.py:55-59; draw slot 1 is the reference's discarded theta
+  float dist = t.dist_lo + (t.dist_hi - t.dist_lo) * u01(r.x);
+  float theta = -1.57079632679489662f + (-t.theta_half + 2.0f * t.theta_half * u01(r.z));
+  float sn, cs;
+  sincosf(theta, &sn, &cs);
+  blk[0] = dist * cs; blk[1] = dist * sn; blk[2] = 0.0f;
+}
+
+// env_base_02.py:88-127 on the stale camera pose; returns detection flag, centre in (cx, cy) before noise
+__device__ __forceinline__ bool project05(const TaskC& t, const EnvRegs& e, float& cx, float& cy) {
+  float rx = e.blk[0] - e.snap[0], ry = e.blk[1] - e.snap[1], rz = e.blk[2] - e.snap[2];
+  const float* R = &e.snap[3];
+  float x = R[0] * rx + R[3] * ry + R[6] * rz, y = R[1] * rx + R[4] * ry + R[7] * rz, z = R[2] * rx + R[5] * ry + R[8] * rz;
+  float u = __fdiv_rn(t.fy * x, z) + 0.5f * t.res_w, v = __fdiv_rn(t.fy * y, z) + 0.5f * t.res_h;
+  if (isnan(u) || isnan(v)) return false;
+  u = truncf(u); v = truncf(v);
+  if (u < 0.0f || u >= t.res_w || v < 0.0f || v >= t.res_h) return false;
+  cx = (t.res_w - u) / t.res_w; cy = (t.res_h - v) / t.res_h;
+  return true;
+}
+
+template <int TASK>
+__device__ __forceinline__ void write_obs(const TaskC& t, EnvRegs& e, int env, unsigned tick, unsigned noise_stream, float* o) {
+  if (TASK == 5) {  // env05_v1.py:32-75: commanded angles + noisy projected centre, or (-1,-1)
+    float cx = -1.0f, cy = -1.0f, px, py;
+    if (project05(t, e, px, py)) {
+      uint4 r = draw(t, env, tick, noise_stream);
+      cx = px + (-t.noise + 2.0f * t.noise * u01(r.x));
+      cy = py + (-t.noise + 2.0f * t.noise * u01(r.y));
+    }
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) o[j] = e.aux[j];
+    o[6] = cx; o[7] = cy;
+  } else {  // env_base_01.py:241-270
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) o[j] = e.q[j];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { o[6 + k] = e.snap[4 + k] - e.snap[k]; o[9 + k] = e.snap[4 + k]; o[12 + k] = e.snap[k]; }
+  }
+}
+
+// MujocoEnv.reset = mj_resetData + reset_model; kinematics stay ZERO because the reference never calls mj_forward
+template <int TASK>
+__device__ __forceinline__ void reset_env(const Consts& C, const Bufs& B, EnvRegs& e, int env, unsigned tick, unsigned stream, float* obs) {
+  const TaskC& t = C.t;
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) { e.q[j] = 0.0f; e.v[j] = 0.0f; e.w[j] = 0.0f; }
+#pragma unroll
+  for (int k = 0; k < kSnap; k++) e.snap[k] = 0.0f;
+  e.elapsed = 0; e.ep_ret = 0.0f;
+  if (TASK == 1) {  // env01_v1.py:39-63
+    uint4 r = draw(t, env, tick, stream);
+    place_block(t, r, e.blk);
+    int idx = (int)__umulhi(r.w, (unsigned)t.n_start);
+#pragma unroll
+    for (int j = 0; j < SO_NJ - 1; j++) e.q[j] = B.start_tab[idx * SO_NJ + j];  // Jaw keeps qpos0
+  } else if (TASK == 2) {  // env02_v1.py:70-81 + :52-68
+    uint4 r = draw(t, env, tick, stream);
+    float prev[3] = {e.aux[0], e.aux[1], e.aux[2]};
+    place_block(t, r, e.blk);
+    bool has = e.flags & F_HAS_LAST_BLOCK;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { e.aux[3 + k] = has ? prev[k] : e.blk[k]; e.aux[k] = e.blk[k]; }
+    e.flags |= F_HAS_LAST_BLOCK;
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) e.q[j] = t.rest[j];
+  } else {  // env03_v1.py:203-215 + :35-57
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) { e.q[j] = t.start05[j]; e.aux[j] = t.start05[j]; }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { e.aux[12 + k] = 0.5f * (t.space_s[0][k] + t.space_s[1][k]); e.blk[k] = e.aux[12 + k]; }
+    e.aux[15] = 0.01f; e.t0step = 0; e.miss = 0;
+    e.flags &= ~F_CENTRE_VALID;
+  }
+  if (t.flags & SO100_FLAG_FRESH_FK_ON_RESET) {
+    float s[SO_NJ], c[SO_NJ];
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) sincosf(e.q[j], &s[j], &c[j]);
+    take_snapshot<TASK>(C, s, c, e);
+  }
+  write_obs<TASK>(t, e, env, tick, STREAM_RESET_NOISE, obs);
+}
+
+__device__ __forceinline__ float joint_penalty(const TaskC& t, const float* ang) {  // env_base_01.py:144-163
+  float r = 0.0f;
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) {
+    if (ang[j] < t.pen_lo[j]) r -= (t.pen_lo[j] - ang[j]) * 10.0f;
+    else if (ang[j] > t.pen_hi[j]) r -= (ang[j] - t.pen_hi[j]) * 10.0f;
+  }
+  return r;
+}
+
+// env_base_01.py:180-239 evaluated BEFORE the physics step on the previous step's (stale) kinematics
+__device__ __forceinline__ float reward_reach(const TaskC& t, EnvRegs& e) {
+  const float PI07 = 2.19911485751285527f;  // 0.7*pi
+  float dx = e.snap[4] - e.snap[0], dy = e.snap[5] - e.snap[1], dz = e.snap[6] - e.snap[2];
+  float distance = sqrtf(dx * dx + dy * dy + dz * dz);
+  bool ever = e.flags & F_EVER_STEPPED;
+  float r = 0.0f;
+  if (e.snap[5] < -0.1f && ever && e.q[1] < -PI07) r += (e.q[1] + PI07) * 0.7f;
+  if (ever && e.snap[2] < 0.02f) r += (e.snap[2] - 0.02f) * 20.0f;
+  if (ever && e.snap[3] < 0.08f) r += clampf((e.snap[3] - 0.08f) * 10.0f, -0.8f, 0.8f);
+  r += fminf(-distance + 0.02f, 0.0f) * 0.5f;
+  r += joint_penalty(t, e.q);
+  e.flags |= F_EVER_STEPPED;
+  return r;
+}
+
+// 16 x mj_step on the arm.  ctrl is constant over the env step, so kp*clip(ctrl) is hoisted.
+template <int TASK>
+__device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs& e, const float* ctrl) {
+  const TaskC& t = C.t;
+  float kc[SO_NJ];
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) kc[j] = t.kp[j] * clampf(ctrl[j], t.ctrl_lo[j], t.ctrl_hi[j]);
+  float worst = 0.0f;
+#pragma unroll 1
+  for (int sub = 0; sub < t.nsub; sub++) {
+    float s[SO_NJ], c[SO_NJ], bias[SO_NJ], M[21], b[SO_NJ];
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) sincosf(e.q[j], &s[j], &c[j]);
+    if (sub == t.nsub - 1) take_snapshot<TASK>(C, s, c, e);  // kinematics of the LAST substep's start state (Q3)
+    dyn_bias_mass<float>(C.dyn, s, c, e.v, bias, M);
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) {
+      float f = kc[j] - t.kp[j] * e.q[j] - t.kv[j] * e.v[j];
+      b[j] = clampf(f, t.frc_lo[j], t.frc_hi[j]) - bias[j];
+    }
+    float d = solve_qacc<float, 5>(C.con, M, b, e.q, e.v, e.w);
+    float amax = 1.0f;
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) {
+      amax = fmaxf(amax, fabsf(e.w[j]));
+      e.v[j] += t.h * e.w[j];   // mj_Euler (semi-implicit; no joint damping in this model)
+      e.q[j] += t.h * e.v[j];
+    }
+    worst = fmaxf(worst, d / amax);
+  }
+  if (worst > 1e-4f) atomicAdd(&B.stats[0], 1ULL);
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+template <int TASK>
+__global__ void __launch_bounds__(kBlock, 7) step_kernel(const __grid_constant__ Consts C, const Bufs B, const StepIO io) {
+  constexpr int OD = TASK == 5 ? 8 : 15;
+  __shared__ float sh[kBlock * OD];
+  const TaskC& t = C.t;
+  const int n = t.n, base = blockIdx.x * kBlock, i = base + threadIdx.x;
+  const bool live = i < n;
+  // coalesced load of the CTA's action rows through shared memory
+  for (int k = threadIdx.x; k < kBlock * SO_NJ; k += kBlock) {
+    int g = base * SO_NJ + k;
+    sh[k] = g < n * SO_NJ ? io.actions[g] : 0.0f;
+  }
+  __syncthreads();
+  float a[SO_NJ];
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) {
+    a[j] = sh[threadIdx.x * SO_NJ + j];
+    if (t.flags & SO100_FLAG_CLIP_ACTIONS) a[j] = clampf(a[j], -1.0f, 1.0f);
+  }
+  __syncthreads();
+  float obs[OD];
+  if (live) {
+    EnvRegs e;
+    load_env<TASK>(B, n, i, e);
+    float rew, ctrl[SO_NJ];
+    bool term = false;
+    if (TASK == 1 || TASK == 2) {
+      rew = reward_reach(t, e);
+#pragma unroll
+      for (int j = 0; j < SO_NJ; j++) ctrl[j] = e.q[j] + a[j] * t.step_scale;  // closed loop on qpos (Q6)
+      if (TASK == 2) {  // env02_v1.py:29-37, reach test on stale kinematics
+        float dx = e.snap[4] - e.snap[0], dy = e.snap[5] - e.snap[1], dz = e.snap[6] - e.snap[2];
+        if (sqrtf(dx * dx + dy * dy + dz * dz) < t.reach) {
+          float bx = e.aux[0] - e.aux[3], by = e.aux[1] - e.aux[4], bz = e.aux[2] - e.aux[5];
+          rew += sqrtf(bx * bx + by * by + bz * bz) * 20.0f;
+          uint4 r = draw(t, i, io.tick, STREAM_TASK);
+#pragma unroll
+          for (int k = 0; k < 3; k++) e.aux[3 + k] = e.aux[k];
+          place_block(t, r, e.blk);
+#pragma unroll
+          for (int k = 0; k < 3; k++) e.aux[k] = e.blk[k];
+        }
+      }
+      physics<TASK>(C, B, e, ctrl);
+      write_obs<TASK>(t, e, i, io.tick, STREAM_NOISE, obs);
+    } else {  // env03_v1.py:124-201
+      float time = (float)e.elapsed * t.dt_env;
+      float f = fminf(time / t.ramp, 1.0f);
+      float smin[3], smax[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        smin[k] = t.space_s[0][k] + f * (t.space_e[0][k] - t.space_s[0][k]);
+        smax[k] = t.space_s[1][k] + f * (t.space_e[1][k] - t.space_s[1][k]);
+      }
+      float speed = f <= 0.05f ? t.speed_min : t.speed_min + (f - 0.05f) * (t.speed_max - t.speed_min) / (1.0f - 0.05f);
+      float dx = e.aux[12] - e.blk[0], dy = e.aux[13] - e.blk[1], dz = e.aux[14] - e.blk[2];
+      float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+      if (!((float)(e.elapsed - e.t0step) * t.dt_env < e.aux[15] && dist > 0.02f)) {  // :77-93
+        uint4 r = draw(t, i, io.tick, STREAM_TASK);
+        e.aux[12] = smin[0] + (smax[0] - smin[0]) * u01(r.x);
+        e.aux[13] = smin[1] + (smax[1] - smin[1]) * u01(r.y);
+        e.aux[14] = smin[2] + (smax[2] - smin[2]) * u01(r.z);
+        e.aux[15] = 1.2f + (5.1f - 1.2f) * u01(r.w);
+        e.t0step = e.elapsed;
+      }
+      dx = e.aux[12] - e.blk[0]; dy = e.aux[13] - e.blk[1]; dz = e.aux[14] - e.blk[2];  // :95-122
+      dist = sqrtf(dx * dx + dy * dy + dz * dz);
+      if (dist > 0.0f) {
+        float sd = fminf(speed * t.h, dist) / dist;
+        e.blk[0] += dx * sd; e.blk[1] += dy * sd; e.blk[2] += dz * sd;
+      }
+      float newcmd[SO_NJ];
+#pragma unroll
+      for (int j = 0; j < SO_NJ; j++) { newcmd[j] = e.aux[j] + a[j] * t.step_scale; ctrl[j] = newcmd[j]; }  // open loop (Q6)
+      physics<TASK>(C, B, e, ctrl);
+      write_obs<TASK>(t, e, i, io.tick, STREAM_NOISE, obs);
+      if (obs[6] == -1.0f && obs[7] == -1.0f) {  // :152-164
+        if (e.miss > t.lost_limit) term = true;
+        e.miss += 1;
+      } else { e.aux[16] = obs[6]; e.aux[17] = obs[7]; e.flags |= F_CENTRE_VALID; e.miss = 0; }
+      rew = 0.5f;
+      if (e.flags & F_CENTRE_VALID) {
+        float ex = 0.5f - e.aux[16], ey = 0.5f - e.aux[17];
+        rew -= sqrtf(ex * ex + ey * ey);
+      }
+      rew += joint_penalty(t, e.aux);  // on the commanded (old) angles, Q7
+      float pen = 0.0f;
+#pragma unroll
+      for (int j = 0; j < SO_NJ; j++) {  // env_base_01.py:165-178 with timestep 0.002 (Q8)
+        float av = (newcmd[j] - e.aux[j]) / t.h;
+        if (e.flags & F_ANGVEL_VALID) pen += fabsf(av - e.aux[6 + j]) * 0.0025f;
+        e.aux[6 + j] = av;
+      }
+      e.flags |= F_ANGVEL_VALID;
+      rew += -pen * f;
+      obs[6] *= 5.0f; obs[7] *= 5.0f;
+#pragma unroll
+      for (int j = 0; j < SO_NJ; j++) e.aux[j] = newcmd[j];
+    }
+    // MuJoCo's mj_checkPos/Vel analogue: a non-finite state forces a reset (counted, never trapped)
+    float chk = 0.0f;
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) chk += e.q[j] + e.v[j];
+    bool bad = !isfinite(chk);
+    if (bad) atomicAdd(&B.stats[1], 1ULL);
+    e.elapsed += 1;
+    e.ep_ret += rew;
+    bool trunc = e.elapsed >= t.max_steps;  // gymnasium TimeLimit
+    io.reward[i] = rew;
+    io.terminated[i] = term ? 1 : 0;
+    io.truncated[i] = (trunc && !term) ? 1 : 0;
+    if (term || trunc || bad) {
+      if (io.terminal_obs) {
+#pragma unroll
+        for (int k = 0; k < OD; k++) io.terminal_obs[(size_t)i * OD + k] = obs[k];
+      }
+      if (io.ep_return_out) io.ep_return_out[i] = e.ep_ret;
+      if (io.ep_len_out) io.ep_len_out[i] = e.elapsed;
+      if (bad) io.truncated[i] = term ? 0 : 1;
+      reset_env<TASK>(C, B, e, i, io.tick, STREAM_RESET, obs);
+    }
+    store_env<TASK>(B, n, i, e);
+#pragma unroll
+    for (int k = 0; k < OD; k++) sh[threadIdx.x * OD + k] = obs[k];
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < kBlock * OD; k += kBlock) {
+    size_t g = (size_t)base * OD + k;
+    if (g < (size_t)n * OD) io.obs[g] = sh[k];
+  }
+}
+
+template <int TASK>
+__global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ Consts C, const Bufs B, const uint8_t* mask, float* obs_out, unsigned tick) {
+  constexpr int OD = TASK == 5 ? 8 : 15;
+  const int n = C.t.n, i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n || (mask && !mask[i])) return;
+  EnvRegs e;
+  load_env<TASK>(B, n, i, e);
+  float obs[OD];
+  reset_env<TASK>(C, B, e, i, tick, STREAM_API_RESET, obs);
+  store_env<TASK>(B, n, i, e);
+#pragma unroll
+  for (int k = 0; k < OD; k++) obs_out[(size_t)i * OD + k] = obs[k];
+}
+
+// debug / parity: one cold-start forward-dynamics evaluation per sample
+__global__ void __launch_bounds__(kBlock) forward_kernel(const __grid_constant__ Consts C, int n, const float* qpos, const float* qvel, const float* ctrl,
+                                                          float* M_out, float* bias_out, float* qacc_out, float* kin_out) {
+  int i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const TaskC& t = C.t;
+  float q[SO_NJ], v[SO_NJ], s[SO_NJ], c[SO_NJ], bias[SO_NJ], M[21], b[SO_NJ], a[SO_NJ];
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) { q[j] = qpos[j * n + i]; v[j] = qvel[j * n + i]; sincosf(q[j], &s[j], &c[j]); a[j] = 0.0f; }
+  dyn_bias_mass<float>(C.dyn, s, c, v, bias, M);
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) {
+    float f = t.kp[j] * clampf(ctrl[j * n + i], t.ctrl_lo[j], t.ctrl_hi[j]) - t.kp[j] * q[j] - t.kv[j] * v[j];
+    b[j] = clampf(f, t.frc_lo[j], t.frc_hi[j]) - bias[j];
+  }
+  solve_qacc<float, 12>(C.con, M, b, q, v, a);
+  if (M_out)
+#pragma unroll
+    for (int k = 0; k < 21; k++) M_out[k * n + i] = M[k];
+  if (bias_out)
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) bias_out[j * n + i] = bias[j];
+  if (qacc_out)
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) qacc_out[j * n + i] = a[j];
+  if (kin_out) {
+    KinOut<float> ko;
+    task_kinematics<float, true>(C.dyn, C.kin, s, c, ko);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { kin_out[k * n + i] = ko.end_pos[k]; kin_out[(3 + k) * n + i] = ko.wrist[k]; kin_out[(6 + k) * n + i] = ko.cam_pos[k]; }
+#pragma unroll
+    for (int k = 0; k < 9; k++) kin_out[(9 + k) * n + i] = ko.cam_R[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host: model -> constants
+namespace {
+
+struct V3 { double v[3]; };
+void qnorm(const double* q, double* o) {
+  double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; i++) o[i] = q[i] / n;
+}
+void q2m(const double* q, double* R) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0] = w * w + x * x - y * y - z * z; R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
+}
+void mmul(const double* A, const double* B, double* o) {
+  double r[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) r[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+  memcpy(o, r, sizeof r);
+}
+void mtrans(const double* A, double* o) {
+  double r[9];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r[3 * i + j] = A[3 * j + i];
+  memcpy(o, r, sizeof r);
+}
+void mvec(const double* A, const double* v, double* o) {
+  double r[3];
+  for (int i = 0; i < 3; i++) r[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
+  memcpy(o, r, sizeof r);
+}
+// proper rotation P with P e_z = axis (columns a, b, axis)
+bool axis_frame(const double* ax_in, double* P) {
+  double n = std::sqrt(ax_in[0] * ax_in[0] + ax_in[1] * ax_in[1] + ax_in[2] * ax_in[2]);
+  if (!(n > 1e-12)) return false;
+  double u[3] = {ax_in[0] / n, ax_in[1] / n, ax_in[2] / n};
+  // exact cyclic permutations for coordinate axes keep the constants free of rounding noise
+  if (u[0] == 1 && u[1] == 0 && u[2] == 0) { double Q[9] = {0, 0, 1, 1, 0, 0, 0, 1, 0}; memcpy(P, Q, sizeof Q); return true; }
+  if (u[0] == 0 && u[1] == 1 && u[2] == 0) { double Q[9] = {0, 1, 0, 0, 0, 1, 1, 0, 0}; memcpy(P, Q, sizeof Q); return true; }
+  if (u[0] == 0 && u[1] == 0 && u[2] == 1) { double Q[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; memcpy(P, Q, sizeof Q); return true; }
+  double t[3] = {1, 0, 0};
+  if (std::fabs(u[0]) > 0.9) { t[0] = 0; t[1] = 1; }
+  double d = t[0] * u[0] + t[1] * u[1] + t[2] * u[2];
+  double a[3] = {t[0] - d * u[0], t[1] - d * u[1], t[2] - d * u[2]};
+  double an = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+  for (int k = 0; k < 3; k++) a[k] /= an;
+  double b[3] = {u[1] * a[2] - u[2] * a[1], u[2] * a[0] - u[0] * a[2], u[0] * a[1] - u[1] * a[0]};
+  for (int r = 0; r < 3; r++) { P[3 * r] = a[r]; P[3 * r + 1] = b[r]; P[3 * r + 2] = u[r]; }
+  return true;
+}
+
+struct HostModel {
+  DynC<double> dyn;
+  ConC<double> con;
+  KinC<double> kin;
+  double dof_M0[SO_NJ], kv[SO_NJ], invw[SO_NJ];
+};
+
+template <typename A, typename B>
+void cast_arr(const A* a, B* b, int n) { for (int i = 0; i < n; i++) b[i] = (B)a[i]; }
+
+int build_host_model(const so100_model& m, HostModel& H) {
+  double Pprev[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  double Pall[SO_NJ][9];
+  for (int i = 0; i < SO_NJ; i++) {
+    double P[9], Pt[9], bq[4], Rfix[9], T[9];
+    if (!axis_frame(m.jnt_axis[i], P)) return fail(SO100_ERR_MODEL, "joint axis of zero length");
+    memcpy(Pall[i], P, sizeof P);
+    qnorm(m.body_quat[i], bq);
+    q2m(bq, Rfix);
+    mtrans(Pprev, Pt);
+    mmul(Pt, Rfix, T);
+    mmul(T, P, H.dyn.L[i].R);              // R' = P_{i-1}^T Rfix P_i
+    mvec(Pt, m.body_pos[i], H.dyn.L[i].p);  // p' = P_{i-1}^T p
+    // inertia about the COM in the re-based child frame, then about the joint origin
+    double iq[4], Riq[9], A[9], At[9], Ic[9], D[9] = {0}, com[3];
+    qnorm(m.body_iquat[i], iq);
+    q2m(iq, Riq);
+    mtrans(P, Pt);
+    mmul(Pt, Riq, A);
+    D[0] = m.body_inertia[i][0]; D[4] = m.body_inertia[i][1]; D[8] = m.body_inertia[i][2];
+    mmul(A, D, T);
+    mtrans(A, At);
+    mmul(T, At, Ic);
+    mvec(Pt, m.body_ipos[i], com);
+    double mass = m.body_mass[i], c2 = com[0] * com[0] + com[1] * com[1] + com[2] * com[2];
+    if (!(mass > 0)) return fail(SO100_ERR_MODEL, "body mass must be positive");
+    LinkC<double>& L = H.dyn.L[i];
+    L.m = mass;
+    for (int k = 0; k < 3; k++) L.h[k] = mass * com[k];
+    L.I[0] = Ic[0] + mass * (c2 - com[0] * com[0]);
+    L.I[1] = Ic[4] + mass * (c2 - com[1] * com[1]);
+    L.I[2] = Ic[8] + mass * (c2 - com[2] * com[2]);
+    L.I[3] = Ic[1] - mass * com[0] * com[1];
+    L.I[4] = Ic[2] - mass * com[0] * com[2];
+    L.I[5] = Ic[5] - mass * com[1] * com[2];
+    L.arm = m.jnt_armature[i];
+    memcpy(Pprev, P, sizeof P);
+  }
+  double bq[4], Rb[9], Rbt[9], g[3] = {-m.gravity[0], -m.gravity[1], -m.gravity[2]};
+  qnorm(m.base_quat, bq);
+  q2m(bq, Rb);
+  mtrans(Rb, Rbt);
+  mvec(Rbt, g, H.dyn.a0);
+  memcpy(H.kin.base_R, Rb, sizeof Rb);
+  memcpy(H.kin.base_p, m.base_pos, sizeof(double) * 3);
+  if (m.ee_body < 0 || m.ee_body >= SO_NJ || m.wrist_body < 0 || m.wrist_body >= SO_NJ || m.cam_body < 0 || m.cam_body >= SO_NJ)
+    return fail(SO100_ERR_MODEL, "ee_body / wrist_body / cam_body out of range");
+  H.kin.ee_body = m.ee_body; H.kin.wrist_body = m.wrist_body; H.kin.cam_body = m.cam_body;
+  double Pt[9], cq[4], Rc[9];
+  mtrans(Pall[m.ee_body], Pt);
+  mvec(Pt, m.ee_offset, H.kin.ee_off);
+  mtrans(Pall[m.cam_body], Pt);
+  mvec(Pt, m.cam_pos, H.kin.cam_pos);
+  qnorm(m.cam_quat, cq);
+  q2m(cq, Rc);
+  mmul(Pt, Rc, H.kin.cam_R);
+
+  // mj_setConst analogue at qpos0 = 0: dof_M0, dof_invweight0 (diag of M^-1), kv from dampratio
+  double s0[SO_NJ] = {0}, c0[SO_NJ] = {1, 1, 1, 1, 1, 1}, v0[SO_NJ] = {0}, bias[SO_NJ], Mp[21], Mf[36], Lc[36] = {0};
+  dyn_bias_mass<double>(H.dyn, s0, c0, v0, bias, Mp);
+  for (int i = 0; i < SO_NJ; i++) for (int j = 0; j <= i; j++) Mf[i * 6 + j] = Mf[j * 6 + i] = Mp[midx(i, j)];
+  for (int j = 0; j < SO_NJ; j++) {
+    double d = Mf[j * 6 + j];
+    for (int k = 0; k < j; k++) d -= Lc[j * 6 + k] * Lc[j * 6 + k];
+    if (!(d > 0)) return fail(SO100_ERR_MODEL, "mass matrix at qpos0 is not positive definite");
+    Lc[j * 6 + j] = std::sqrt(d);
+    for (int i = j + 1; i < SO_NJ; i++) {
+      double sv = Mf[i * 6 + j];
+      for (int k = 0; k < j; k++) sv -= Lc[i * 6 + k] * Lc[j * 6 + k];
+      Lc[i * 6 + j] = sv / Lc[j * 6 + j];
+    }
+  }
+  for (int j = 0; j < SO_NJ; j++) {
+    double y[SO_NJ], x[SO_NJ];
+    for (int i = 0; i < SO_NJ; i++) {
+      double sv = (i == j) ? 1.0 : 0.0;
+      for (int k = 0; k < i; k++) sv -= Lc[i * 6 + k] * y[k];
+      y[i] = sv / Lc[i * 6 + i];
+    }
+    for (int i = SO_NJ - 1; i >= 0; i--) {
+      double sv = y[i];
+      for (int k = i + 1; k < SO_NJ; k++) sv -= Lc[k * 6 + i] * x[k];
+      x[i] = sv / Lc[i * 6 + i];
+    }
+    H.invw[j] = x[j];
+    H.dof_M0[j] = Mf[j * 6 + j];
+    H.kv[j] = m.act_dampratio[j] > 0 ? m.act_dampratio[j] * 2 * std::sqrt(m.act_kp[j] * H.dof_M0[j]) : m.act_kv[j];
+  }
+  // constraint constants
+  for (int j = 0; j < SO_NJ; j++) {
+    auto kb = [&](const double* solref, const double* solimp, double& K, double& Bv) {
+      double tc = solref[0], dr = solref[1], dmax = solimp[1];
+      if (tc > 0) {
+        if (tc < 2 * m.timestep) tc = 2 * m.timestep;  // refsafe
+        K = 1.0 / std::fmax(1e-15, dmax * dmax * tc * tc * dr * dr);
+        Bv = 2.0 / std::fmax(1e-15, dmax * tc);
+      } else { K = -solref[0] / (dmax * dmax); Bv = -solref[1] / dmax; }
+    };
+    double K, Bv;
+    kb(m.dof_solref_friction[j], m.dof_solimp_friction[j], K, Bv);
+    const double* si = m.dof_solimp_friction[j];
+    double imp = (si[0] == si[1] || si[2] <= 1e-15) ? 0.5 * (si[0] + si[1]) : si[0];  // impedance at pos = 0
+    double Rf = std::fmax(1e-15, (1 - imp) / imp * H.invw[j]);
+    H.con.fr_D[j] = 1.0 / Rf; H.con.fr_B[j] = Bv; H.con.fr_loss[j] = m.jnt_frictionloss[j] > 0 ? m.jnt_frictionloss[j] : 0.0;
+    kb(m.jnt_solref_limit[j], m.jnt_solimp_limit[j], K, Bv);
+    H.con.lim_B[j] = Bv; H.con.lim_K[j] = K; H.con.invw[j] = H.invw[j];
+    H.con.lo[j] = m.jnt_range[j][0]; H.con.hi[j] = m.jnt_range[j][1];
+    if (!(H.con.hi[j] > H.con.lo[j])) return fail(SO100_ERR_MODEL, "joint range must have hi > lo");
+    const double* sl = m.jnt_solimp_limit[j];
+    H.con.imp0[j] = sl[0]; H.con.imp1[j] = sl[1]; H.con.imp_w[j] = sl[2]; H.con.imp_mid[j] = sl[3]; H.con.imp_pow[j] = sl[4];
+  }
+  return SO100_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ ctx
+struct so100_ctx {
+  int device = 0, n = 0, task = 0, obs_dim = 0;
+  Consts C;
+  HostModel H;
+  Bufs B{};
+  float* start_tab = nullptr;
+  int64_t tick = 0, launches = 0;
+  // staging for the *_host entry points
+  float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_tobs = nullptr, *h_epr = nullptr;
+  uint8_t *h_term = nullptr, *h_trunc = nullptr;
+  int* h_epl = nullptr;
+};
+
+static void free_ctx(so100_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  void* ptrs[] = {c->B.qpos, c->B.qvel, c->B.warm, c->B.block, c->B.snap, c->B.aux, c->B.ep_return, c->B.cnt, c->B.stats,
+                  c->start_tab, c->h_act, c->h_obs, c->h_rew, c->h_tobs, c->h_epr, c->h_term, c->h_trunc, c->h_epl};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete c;
+}
+
+extern "C" {
+
+int so100_abi_version(void) { return SO100_ABI_VERSION; }
+const char* so100_last_error(void) { return g_err.c_str(); }
+int so100_obs_dim(int task) {
+  if (task == SO100_TASK_ENV01 || task == SO100_TASK_ENV02) return 15;
+  if (task == SO100_TASK_ENV05) return 8;
+  return fail(SO100_ERR_ARG, "unknown task");
+}
+int so100_act_dim(int task) { return so100_obs_dim(task) < 0 ? SO100_ERR_ARG : SO_NJ; }
+
+int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so100_ctx** out) {
+  if (!m || !cfg || !out) return fail(SO100_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (m->struct_size != (int)sizeof(so100_model)) return fail(SO100_ERR_ARG, "so100_model.struct_size mismatch");
+  if (cfg->struct_size != (int)sizeof(so100_task_cfg)) return fail(SO100_ERR_ARG, "so100_task_cfg.struct_size mismatch");
+  if (so100_obs_dim(cfg->task) < 0) return SO100_ERR_ARG;
+  if (cfg->num_envs <= 0) return fail(SO100_ERR_ARG, "num_envs must be positive");
+  if (cfg->max_episode_steps <= 0) return fail(SO100_ERR_ARG, "max_episode_steps must be positive");
+  if (cfg->task == SO100_TASK_ENV01 && (cfg->n_start <= 0 || cfg->n_start > kMaxStart)) return fail(SO100_ERR_ARG, "n_start out of range");
+  if (m->nsubstep <= 0 || !(m->timestep > 0)) return fail(SO100_ERR_MODEL, "nsubstep / timestep must be positive");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(SO100_ERR_ARG, "no such CUDA device");
+  CU(cudaSetDevice(device));
+  so100_ctx* c = new (std::nothrow) so100_ctx();
+  if (!c) return fail(SO100_ERR_CUDA, "out of host memory");
+  c->device = device; c->n = cfg->num_envs; c->task = cfg->task; c->obs_dim = so100_obs_dim(cfg->task);
+  int rc = build_host_model(*m, c->H);
+  if (rc != SO100_OK) { delete c; return rc; }
+  // fp64 -> fp32 constants
+  Consts& C = c->C;
+  memset(&C, 0, sizeof C);
+  for (int i = 0; i < SO_NJ; i++) {
+    const LinkC<double>& s = c->H.dyn.L[i];
+    LinkC<float>& d = C.dyn.L[i];
+    cast_arr(s.R, d.R, 9); cast_arr(s.p, d.p, 3); cast_arr(s.h, d.h, 3); cast_arr(s.I, d.I, 6);
+    d.m = (float)s.m; d.arm = (float)s.arm;
+  }
+  cast_arr(c->H.dyn.a0, C.dyn.a0, 3);
+#define CASTF(f) cast_arr(c->H.con.f, C.con.f, SO_NJ)
+  CASTF(fr_D); CASTF(fr_B); CASTF(fr_loss); CASTF(lo); CASTF(hi); CASTF(lim_B); CASTF(lim_K); CASTF(invw);
+  CASTF(imp0); CASTF(imp1); CASTF(imp_w); CASTF(imp_mid); CASTF(imp_pow);
+#undef CASTF
+  cast_arr(c->H.kin.base_R, C.kin.base_R, 9); cast_arr(c->H.kin.base_p, C.kin.base_p, 3);
+  cast_arr(c->H.kin.ee_off, C.kin.ee_off, 3); cast_arr(c->H.kin.cam_pos, C.kin.cam_pos, 3); cast_arr(c->H.kin.cam_R, C.kin.cam_R, 9);
+  C.kin.ee_body = c->H.kin.ee_body; C.kin.wrist_body = c->H.kin.wrist_body; C.kin.cam_body = c->H.kin.cam_body;
+  TaskC& t = C.t;
+  t.task = cfg->task; t.n = cfg->num_envs; t.max_steps = cfg->max_episode_steps; t.n_start = cfg->n_start;
+  t.lost_limit = cfg->lost_limit; t.nsub = m->nsubstep; t.flags = cfg->flags;
+  t.seed_lo = (unsigned)(cfg->seed & 0xFFFFFFFFull); t.seed_hi = (unsigned)(cfg->seed >> 32);
+  t.env_offset = cfg->env_offset;
+  t.h = (float)m->timestep; t.dt_env = (float)(m->timestep * m->nsubstep); t.step_scale = (float)cfg->joint_step_scale;
+  for (int j = 0; j < SO_NJ; j++) {
+    t.kp[j] = (float)m->act_kp[j]; t.kv[j] = (float)c->H.kv[j];
+    t.ctrl_lo[j] = (float)m->act_ctrlrange[j][0]; t.ctrl_hi[j] = (float)m->act_ctrlrange[j][1];
+    t.frc_lo[j] = (float)m->act_forcerange[j][0]; t.frc_hi[j] = (float)m->act_forcerange[j][1];
+    double lo = m->jnt_range[j][0], hi = m->jnt_range[j][1];
+    t.pen_lo[j] = (float)(lo + 0.05 * (hi - lo)); t.pen_hi[j] = (float)(hi - 0.05 * (hi - lo));
+    t.rest[j] = (float)cfg->rest_position[j]; t.start05[j] = (float)cfg->start_position05[j];
+  }
+  t.dist_lo = (float)cfg->block_dist_range[0]; t.dist_hi = (float)cfg->block_dist_range[1];
+  t.theta_half = (float)cfg->block_theta_half; t.reach = (float)cfg->reach_threshold;
+  for (int a = 0; a < 2; a++) for (int k = 0; k < 3; k++) { t.space_s[a][k] = (float)cfg->block_space_start[a][k]; t.space_e[a][k] = (float)cfg->block_space_end[a][k]; }
+  t.speed_min = (float)cfg->block_speed_min; t.speed_max = (float)cfg->block_speed_max; t.ramp = (float)cfg->ramp_seconds;
+  t.res_w = (float)cfg->cam_res_w; t.res_h = (float)cfg->cam_res_h; t.noise = (float)cfg->obs_noise;
+  t.fy = (float)(0.5 * cfg->cam_res_h / std::tan(m->cam_fovy_deg * 3.14159265358979323846 / 180.0 / 2));  // env_base_02.py:100
+
+  const size_t n = (size_t)c->n;
+  auto alloc = [&](void** p, size_t bytes) -> bool {
+    if (cudaMalloc(p, bytes) != cudaSuccess) return false;
+    return cudaMemset(*p, 0, bytes) == cudaSuccess;
+  };
+  bool ok = alloc((void**)&c->B.qpos, 6 * n * 4) && alloc((void**)&c->B.qvel, 6 * n * 4) && alloc((void**)&c->B.warm, 6 * n * 4) &&
+            alloc((void**)&c->B.block, 3 * n * 4) && alloc((void**)&c->B.snap, kSnap * n * 4) && alloc((void**)&c->B.aux, kAux * n * 4) &&
+            alloc((void**)&c->B.ep_return, n * 4) && alloc((void**)&c->B.cnt, kCnt * n * 4) && alloc((void**)&c->B.stats, 2 * 8) &&
+            alloc((void**)&c->start_tab, kMaxStart * SO_NJ * 4);
+  if (!ok) { std::string e = cudaGetErrorString(cudaGetLastError()); free_ctx(c); return fail(SO100_ERR_CUDA, "cudaMalloc: " + e); }
+  float tab[kMaxStart * SO_NJ];
+  for (int i = 0; i < kMaxStart; i++) for (int j = 0; j < SO_NJ; j++) tab[i * SO_NJ + j] = (float)cfg->start_positions[i][j];
+  if (cudaMemcpy(c->start_tab, tab, sizeof tab, cudaMemcpyHostToDevice) != cudaSuccess) { free_ctx(c); return fail(SO100_ERR_CUDA, "cudaMemcpy(start table)"); }
+  c->B.start_tab = c->start_tab;
+  *out = c;
+  return SO100_OK;
+}
+
+void so100_destroy(so100_ctx* ctx) { free_ctx(ctx); }
+
+static inline int grid_for(int n) { return (n + kBlock - 1) / kBlock; }
+
+int so100_reset(so100_ctx* c, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+  if (!c || !obs_dev) return fail(SO100_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned tick = (unsigned)c->tick;
+  switch (c->task) {
+    case 1: reset_kernel<1><<<grid_for(c->n), kBlock, 0, st>>>(c->C, c->B, mask_dev, obs_dev, tick); break;
+    case 2: reset_kernel<2><<<grid_for(c->n), kBlock, 0, st>>>(c->C, c->B, mask_dev, obs_dev, tick); break;
+    default: reset_kernel<5><<<grid_for(c->n), kBlock, 0, st>>>(c->C, c->B, mask_dev, obs_dev, tick); break;
+  }
+  c->launches++;
+  CU(cudaGetLastError());
+  return SO100_OK;
+}
+
+int so100_step(so100_ctx* c, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* terminated_dev,
+               uint8_t* truncated_dev, float* terminal_obs_dev, float* ep_return_dev, int32_t* ep_len_dev, void* stream) {
+  if (!c || !actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail(SO100_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  c->tick += 1;
+  StepIO io{actions_dev, obs_dev, reward_dev, terminal_obs_dev, ep_return_dev, terminated_dev, truncated_dev, ep_len_dev, (unsigned)c->tick};
+  switch (c->task) {
+    case 1: step_kernel<1><<<grid_for(c->n), kBlock, 0, st>>>(c->C, c->B, io); break;
+    case 2: step_kernel<2><<<grid_for(c->n), kBlock, 0, st>>>(c->C, c->B, io); break;
+    default: step_kernel<5><<<grid_for(c->n), kBlock, 0, st>>>(c->C, c->B, io); break;
+  }
+  c->launches++;
+  CU(cudaGetLastError());
+  return SO100_OK;
+}
+
+static int ensure_staging(so100_ctx* c) {
+  if (c->h_act) return SO100_OK;
+  size_t n = (size_t)c->n, od = (size_t)c->obs_dim;
+  CU(cudaMalloc((void**)&c->h_act, n * SO_NJ * 4));
+  CU(cudaMalloc((void**)&c->h_obs, n * od * 4));
+  CU(cudaMalloc((void**)&c->h_tobs, n * od * 4));
+  CU(cudaMalloc((void**)&c->h_rew, n * 4));
+  CU(cudaMalloc((void**)&c->h_epr, n * 4));
+  CU(cudaMalloc((void**)&c->h_epl, n * 4));
+  CU(cudaMalloc((void**)&c->h_term, n));
+  CU(cudaMalloc((void**)&c->h_trunc, n));
+  return SO100_OK;
+}
+
+int so100_reset_host(so100_ctx* c, float* obs_host, void* stream) {
+  if (!c || !obs_host) return fail(SO100_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  int rc = ensure_staging(c);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = so100_reset(c, nullptr, c->h_obs, stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(obs_host, c->h_obs, (size_t)c->n * c->obs_dim * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SO100_OK;
+}
+
+int so100_step_host(so100_ctx* c, const float* actions_host, float* obs_host, float* reward_host, uint8_t* terminated_host,
+                    uint8_t* truncated_host, float* terminal_obs_host, float* ep_return_host, int32_t* ep_len_host, void* stream) {
+  if (!c || !actions_host || !obs_host || !reward_host || !terminated_host || !truncated_host) return fail(SO100_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  int rc = ensure_staging(c);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t n = (size_t)c->n, od = (size_t)c->obs_dim;
+  CU(cudaMemcpyAsync(c->h_act, actions_host, n * SO_NJ * 4, cudaMemcpyHostToDevice, st));
+  rc = so100_step(c, c->h_act, c->h_obs, c->h_rew, c->h_term, c->h_trunc, terminal_obs_host ? c->h_tobs : nullptr,
+                  ep_return_host ? c->h_epr : nullptr, ep_len_host ? c->h_epl : nullptr, stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(obs_host, c->h_obs, n * od * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(reward_host, c->h_rew, n * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(terminated_host, c->h_term, n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(truncated_host, c->h_trunc, n, cudaMemcpyDeviceToHost, st));
+  if (terminal_obs_host) CU(cudaMemcpyAsync(terminal_obs_host, c->h_tobs, n * od * 4, cudaMemcpyDeviceToHost, st));
+  if (ep_return_host) CU(cudaMemcpyAsync(ep_return_host, c->h_epr, n * 4, cudaMemcpyDeviceToHost, st));
+  if (ep_len_host) CU(cudaMemcpyAsync(ep_len_host, c->h_epl, n * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SO100_OK;
+}
+
+static int copy_state(so100_ctx* c, const so100_state_view* v, void* stream, bool get) {
+  if (!c || !v) return fail(SO100_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t n = (size_t)c->n;
+  struct { void* ext; void* in; size_t bytes; } f[] = {
+      {v->qpos, c->B.qpos, 6 * n * 4}, {v->qvel, c->B.qvel, 6 * n * 4}, {v->qacc_warm, c->B.warm, 6 * n * 4},
+      {v->block, c->B.block, 3 * n * 4}, {v->snap, c->B.snap, kSnap * n * 4}, {v->aux, c->B.aux, kAux * n * 4},
+      {v->counters, c->B.cnt, kCnt * n * 4}, {v->ep_return, c->B.ep_return, n * 4}};
+  for (auto& x : f) {
+    if (!x.ext) continue;
+    if (get) CU(cudaMemcpyAsync(x.ext, x.in, x.bytes, cudaMemcpyDeviceToDevice, st));
+    else CU(cudaMemcpyAsync(x.in, x.ext, x.bytes, cudaMemcpyDeviceToDevice, st));
+  }
+  return SO100_OK;
+}
+int so100_get_state(so100_ctx* c, const so100_state_view* v, void* stream) { return copy_state(c, v, stream, true); }
+int so100_set_state(so100_ctx* c, const so100_state_view* v, void* stream) { return copy_state(c, v, stream, false); }
+
+int so100_get_tick(so100_ctx* c, int64_t* tick) {
+  if (!c || !tick) return fail(SO100_ERR_ARG, "null argument");
+  *tick = c->tick;
+  return SO100_OK;
+}
+int so100_set_tick(so100_ctx* c, int64_t tick) {
+  if (!c || tick < 0) return fail(SO100_ERR_ARG, "bad argument");
+  c->tick = tick;
+  return SO100_OK;
+}
+
+int so100_forward_dynamics(so100_ctx* c, int n, const float* qpos_dev, const float* qvel_dev, const float* ctrl_dev,
+                           float* M_dev, float* bias_dev, float* qacc_dev, float* kin_dev, void* stream) {
+  if (!c || n <= 0 || !qpos_dev || !qvel_dev || !ctrl_dev) return fail(SO100_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  forward_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(c->C, n, qpos_dev, qvel_dev, ctrl_dev, M_dev, bias_dev, qacc_dev, kin_dev);
+  c->launches++;
+  CU(cudaGetLastError());
+  return SO100_OK;
+}
+
+int so100_host_forward(const so100_model* m, int n, const double* qpos, const double* qvel, const double* ctrl, double* M_out,
+                       double* bias_out, double* qacc_out, double* kin_out, int sweeps) {
+  if (!m || n <= 0 || !qpos || !qvel || !ctrl) return fail(SO100_ERR_ARG, "bad argument");
+  if (m->struct_size != (int)sizeof(so100_model)) return fail(SO100_ERR_ARG, "so100_model.struct_size mismatch");
+  HostModel H;
+  int rc = build_host_model(*m, H);
+  if (rc) return rc;
+  for (int i = 0; i < n; i++) {
+    const double *q = qpos + 6 * i, *v = qvel + 6 * i, *u = ctrl + 6 * i;
+    double s[SO_NJ], c[SO_NJ], bias[SO_NJ], M[21], b[SO_NJ], a[SO_NJ] = {0};
+    for (int j = 0; j < SO_NJ; j++) { s[j] = std::sin(q[j]); c[j] = std::cos(q[j]); }
+    dyn_bias_mass<double>(H.dyn, s, c, v, bias, M);
+    for (int j = 0; j < SO_NJ; j++) {
+      double cc = std::fmin(std::fmax(u[j], m->act_ctrlrange[j][0]), m->act_ctrlrange[j][1]);
+      double f = m->act_kp[j] * cc - m->act_kp[j] * q[j] - H.kv[j] * v[j];
+      b[j] = std::fmin(std::fmax(f, m->act_forcerange[j][0]), m->act_forcerange[j][1]) - bias[j];
+    }
+    for (int k = 0; k < (sweeps > 0 ? sweeps : 1); k++) solve_qacc<double, 1>(H.con, M, b, q, v, a);
+    if (M_out) memcpy(M_out + 21 * i, M, sizeof M);
+    if (bias_out) memcpy(bias_out + 6 * i, bias, sizeof bias);
+    if (qacc_out) memcpy(qacc_out + 6 * i, a, sizeof a);
+    if (kin_out) {
+      KinOut<double> ko;
+      task_kinematics<double, true>(H.dyn, H.kin, s, c, ko);
+      memcpy(kin_out + 18 * i, ko.end_pos, 24); memcpy(kin_out + 18 * i + 3, ko.wrist, 24);
+      memcpy(kin_out + 18 * i + 6, ko.cam_pos, 24); memcpy(kin_out + 18 * i + 9, ko.cam_R, 72);
+    }
+  }
+  return SO100_OK;
+}
+
+int so100_get_derived(so100_ctx* c, double* dof_M0, double* kv, double* invweight0) {
+  if (!c) return fail(SO100_ERR_ARG, "null argument");
+  for (int j = 0; j < SO_NJ; j++) {
+    if (dof_M0) dof_M0[j] = c->H.dof_M0[j];
+    if (kv) kv[j] = c->H.kv[j];
+    if (invweight0) invweight0[j] = c->H.invw[j];
+  }
+  return SO100_OK;
+}
+
+int so100_get_stats(so100_ctx* c, int64_t* launches, int64_t* solver_fallbacks, int64_t* nan_resets) {
+  if (!c) return fail(SO100_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  unsigned long long s[2];
+  CU(cudaMemcpy(s, c->B.stats, sizeof s, cudaMemcpyDeviceToHost));
+  if (launches) *launches = c->launches;
+  if (solver_fallbacks) *solver_fallbacks = (int64_t)s[0];
+  if (nan_resets) *nan_resets = (int64_t)s[1];
+  return SO100_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,340 @@
+// so100_dyn.cuh — arm dynamics of the so100 chain as straight-line recursions in LINK-LOCAL frames.
+//
+// This is the B200 restatement of what MuJoCo's mj_fwdPosition / mj_fwdVelocity compute for this model
+// (mj_kinematics, mj_crb, mj_rne; reference call site: mujoco.mj_step at
+// src/so100_mujoco_rl/envs/env01_v1.py:26, env02_v1.py:39, env03_v1.py:142).  It is NOT MuJoCo's formulation:
+//   * every link frame is re-based on the host so that its hinge turns about the local +z axis; crossing a joint is
+//     then a constant 3x3 times a planar (c,s) rotation, and no world-frame kinematics is needed in the substep loop;
+//   * bias forces: recursive Newton-Euler with the spatial inertia (m, h = m*com, I about the joint origin);
+//   * joint-space inertia: composite rigid bodies accumulated tip -> base in the same backward sweep;
+//   * everything lives in registers of ONE thread per environment; loops are fully unrolled.
+// The same templates run on the host in double (T = double) to derive MuJoCo's compile-time constants
+// (dof_M0, dof_invweight0, actuator kv) and on the device in float.
+#pragma once
+
+#include <cmath>
+
+#ifdef __CUDACC__
+#define SO_HD __host__ __device__ __forceinline__
+#else
+#define SO_HD inline
+#endif
+
+#define SO_NJ 6
+
+template <typename T>
+struct LinkC {
+  T R[9];  // parent <- child constant rotation (row-major), before the joint rotation
+  T p[3];  // child origin in the parent frame
+  T m;     // mass
+  T h[3];  // m * com (child frame)
+  T I[6];  // inertia about the joint origin, child frame: xx yy zz xy xz yz
+  T arm;   // armature
+};
+
+template <typename T>
+struct DynC {
+  LinkC<T> L[SO_NJ];
+  T a0[3];  // acceleration of the base frame = -gravity, in base coordinates
+};
+
+// packed lower triangle, i >= j
+SO_HD constexpr int midx(int i, int j) { return i * (i + 1) / 2 + j; }
+
+template <typename T>
+SO_HD void cross3(const T* a, const T* b, T* o) {
+  T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+// o += a x b
+template <typename T>
+SO_HD void cross3_acc(const T* a, const T* b, T* o) {
+  T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] += x; o[1] += y; o[2] += z;
+}
+// child -> parent:  o = R * Rz(c,s) * v
+template <typename T>
+SO_HD void to_parent(const T* R, T s, T c, const T* v, T* o) {
+  T x = c * v[0] - s * v[1], y = s * v[0] + c * v[1], z = v[2];
+  T o0 = R[0] * x + R[1] * y + R[2] * z, o1 = R[3] * x + R[4] * y + R[5] * z, o2 = R[6] * x + R[7] * y + R[8] * z;
+  o[0] = o0; o[1] = o1; o[2] = o2;
+}
+// parent -> child:  o = Rz(c,s)^T * R^T * v
+template <typename T>
+SO_HD void to_child(const T* R, T s, T c, const T* v, T* o) {
+  T x = R[0] * v[0] + R[3] * v[1] + R[6] * v[2], y = R[1] * v[0] + R[4] * v[1] + R[7] * v[2],
+    z = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+  o[0] = c * x + s * y; o[1] = c * y - s * x; o[2] = z;
+}
+template <typename T>
+SO_HD void sym_mv(const T* I, const T* v, T* o) {  // I: xx yy zz xy xz yz
+  T x = I[0] * v[0] + I[3] * v[1] + I[4] * v[2], y = I[3] * v[0] + I[1] * v[1] + I[5] * v[2],
+    z = I[4] * v[0] + I[5] * v[1] + I[2] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+
+// Move a composite spatial inertia (m, h, I about the child origin, child frame) into the parent frame about the
+// parent origin and ADD it to (pm, ph, pI).
+template <typename T>
+SO_HD void add_composite(const LinkC<T>& L, T s, T c, T m, const T* h, const T* I, T& pm, T* ph, T* pI) {
+  // 1) planar rotation Rz(q) of the symmetric tensor (double-angle form)
+  T c2 = c * c - s * s, s2 = T(2) * c * s;
+  T av = T(0.5) * (I[0] + I[1]), bv = T(0.5) * (I[0] - I[1]);
+  T xx = av + bv * c2 - I[3] * s2, yy = av - bv * c2 + I[3] * s2, xy = bv * s2 + I[3] * c2;
+  T xz = c * I[4] - s * I[5], yz = s * I[4] + c * I[5], zz = I[2];
+  // 2) constant rotation: J = R * I1 * R^T
+  const T* R = L.R;
+  T t0[3], t1[3], t2[3];  // rows of R*I1
+  for (int r = 0; r < 3; r++) {
+    T a = R[3 * r], b = R[3 * r + 1], d = R[3 * r + 2];
+    T u0 = a * xx + b * xy + d * xz, u1 = a * xy + b * yy + d * yz, u2 = a * xz + b * yz + d * zz;
+    if (r == 0) { t0[0] = u0; t0[1] = u1; t0[2] = u2; }
+    else if (r == 1) { t1[0] = u0; t1[1] = u1; t1[2] = u2; }
+    else { t2[0] = u0; t2[1] = u1; t2[2] = u2; }
+  }
+  T Jxx = t0[0] * R[0] + t0[1] * R[1] + t0[2] * R[2];
+  T Jyy = t1[0] * R[3] + t1[1] * R[4] + t1[2] * R[5];
+  T Jzz = t2[0] * R[6] + t2[1] * R[7] + t2[2] * R[8];
+  T Jxy = t0[0] * R[3] + t0[1] * R[4] + t0[2] * R[5];
+  T Jxz = t0[0] * R[6] + t0[1] * R[7] + t0[2] * R[8];
+  T Jyz = t1[0] * R[6] + t1[1] * R[7] + t1[2] * R[8];
+  // 3) first moment, then the shift of the reference point by p (parallel-axis with a non-central first moment):
+  //    I' = J + (p.t) 1 - (p t^T + t p^T)/2,   t = 2 h_r + m p
+  T hr[3];
+  to_parent(R, s, c, h, hr);
+  const T* p = L.p;
+  T tx = T(2) * hr[0] + m * p[0], ty = T(2) * hr[1] + m * p[1], tz = T(2) * hr[2] + m * p[2];
+  T pt = p[0] * tx + p[1] * ty + p[2] * tz;
+  pI[0] += Jxx + pt - p[0] * tx;
+  pI[1] += Jyy + pt - p[1] * ty;
+  pI[2] += Jzz + pt - p[2] * tz;
+  pI[3] += Jxy - T(0.5) * (p[0] * ty + p[1] * tx);
+  pI[4] += Jxz - T(0.5) * (p[0] * tz + p[2] * tx);
+  pI[5] += Jyz - T(0.5) * (p[1] * tz + p[2] * ty);
+  ph[0] += hr[0] + m * p[0]; ph[1] += hr[1] + m * p[1]; ph[2] += hr[2] + m * p[2];
+  pm += m;
+}
+
+// bias[6] = RNE(q, qd, qdd = 0) incl. gravity;  M[21] = joint-space inertia incl. armature (packed lower triangle).
+template <typename T>
+SO_HD void dyn_bias_mass(const DynC<T>& C, const T* s, const T* c, const T* qd, T* bias, T* M) {
+  T f[SO_NJ][3], n[SO_NJ][3];
+  {
+    T w[3] = {T(0), T(0), T(0)}, wd[3] = {T(0), T(0), T(0)}, a[3] = {C.a0[0], C.a0[1], C.a0[2]};
+#pragma unroll
+    for (int i = 0; i < SO_NJ; i++) {
+      const LinkC<T>& L = C.L[i];
+      T ap[3] = {a[0], a[1], a[2]};
+      if (i > 0) {  // origin of link i rides on link i-1 at offset p
+        T t[3];
+        cross3_acc(wd, L.p, ap);
+        cross3(w, L.p, t);
+        cross3_acc(w, t, ap);
+      }
+      T wl[3], wdl[3], al[3];
+      to_child(L.R, s[i], c[i], w, wl);
+      to_child(L.R, s[i], c[i], wd, wdl);
+      to_child(L.R, s[i], c[i], ap, al);
+      wdl[0] += qd[i] * wl[1];  // (E^T w_parent) x (e_z qd)
+      wdl[1] -= qd[i] * wl[0];
+      wl[2] += qd[i];
+      // f = m a + wd x h + w x (w x h);   n = I wd + w x (I w) + h x a     (about the joint origin)
+      T t[3], Iw[3];
+      f[i][0] = L.m * al[0]; f[i][1] = L.m * al[1]; f[i][2] = L.m * al[2];
+      cross3_acc(wdl, L.h, f[i]);
+      cross3(wl, L.h, t);
+      cross3_acc(wl, t, f[i]);
+      sym_mv(L.I, wdl, n[i]);
+      sym_mv(L.I, wl, Iw);
+      cross3_acc(wl, Iw, n[i]);
+      cross3_acc(L.h, al, n[i]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { w[k] = wl[k]; wd[k] = wdl[k]; a[k] = al[k]; }
+    }
+  }
+  // backward sweep: wrench accumulation (bias) + composite inertia and its columns (M)
+  T cm = C.L[SO_NJ - 1].m, ch[3], cI[6];
+#pragma unroll
+  for (int k = 0; k < 3; k++) ch[k] = C.L[SO_NJ - 1].h[k];
+#pragma unroll
+  for (int k = 0; k < 6; k++) cI[k] = C.L[SO_NJ - 1].I[k];
+#pragma unroll
+  for (int i = SO_NJ - 1; i >= 0; i--) {
+    bias[i] = n[i][2];
+    M[midx(i, i)] = cI[2] + C.L[i].arm;
+    // unit acceleration about local z of the composite body: force (e_z x h), moment I e_z
+    T cf[3] = {-ch[1], ch[0], T(0)}, cn[3] = {cI[4], cI[5], cI[2]};
+#pragma unroll
+    for (int j = i - 1; j >= 0; j--) {
+      const LinkC<T>& Lc = C.L[j + 1];
+      to_parent(Lc.R, s[j + 1], c[j + 1], cf, cf);
+      to_parent(Lc.R, s[j + 1], c[j + 1], cn, cn);
+      cross3_acc(Lc.p, cf, cn);
+      M[midx(i, j)] = cn[2];
+    }
+    if (i > 0) {
+      const LinkC<T>& L = C.L[i];
+      T fp[3], np[3];
+      to_parent(L.R, s[i], c[i], f[i], fp);
+      to_parent(L.R, s[i], c[i], n[i], np);
+      cross3_acc(L.p, fp, np);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { f[i - 1][k] += fp[k]; n[i - 1][k] += np[k]; }
+      T pm = C.L[i - 1].m, ph[3], pI[6];
+#pragma unroll
+      for (int k = 0; k < 3; k++) ph[k] = C.L[i - 1].h[k];
+#pragma unroll
+      for (int k = 0; k < 6; k++) pI[k] = C.L[i - 1].I[k];
+      add_composite(L, s[i], c[i], cm, ch, cI, pm, ph, pI);
+      cm = pm;
+#pragma unroll
+      for (int k = 0; k < 3; k++) ch[k] = ph[k];
+#pragma unroll
+      for (int k = 0; k < 6; k++) cI[k] = pI[k];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Soft constraints (MuJoCo friction-loss + joint-limit rows) and their solve.
+template <typename T>
+struct ConC {
+  T fr_D[SO_NJ], fr_B[SO_NJ], fr_loss[SO_NJ];  // friction-loss row: D = 1/R, aref = -B*qd, |force| <= loss
+  T lo[SO_NJ], hi[SO_NJ];                      // joint range
+  T lim_B[SO_NJ], lim_K[SO_NJ], invw[SO_NJ];   // limit row: aref = -B*(J qd) - K*imp*dist, R = (1-imp)/imp*invw
+  T imp0[SO_NJ], imp1[SO_NJ], imp_w[SO_NJ], imp_mid[SO_NJ], imp_pow[SO_NJ];
+};
+
+template <typename T>
+SO_HD T so_pow(T x, T p) {
+#ifdef __CUDA_ARCH__
+  return (sizeof(T) == 4) ? (T)powf((float)x, (float)p) : (T)pow((double)x, (double)p);
+#else
+  return (T)std::pow((double)x, (double)p);
+#endif
+}
+
+template <typename T>
+SO_HD T impedance(const ConC<T>& K, int j, T dist) {  // MuJoCo getimpedance with margin 0
+  if (K.imp0[j] == K.imp1[j] || K.imp_w[j] <= T(1e-15)) return T(0.5) * (K.imp0[j] + K.imp1[j]);
+  T x = (dist < 0 ? -dist : dist) / K.imp_w[j];
+  if (x >= T(1)) return K.imp1[j];
+  if (x <= T(0)) return K.imp0[j];
+  T y, p = K.imp_pow[j], mid = K.imp_mid[j];
+  if (p == T(1)) y = x;
+  else if (p == T(2)) y = (x <= mid) ? x * x / mid : T(1) - (T(1) - x) * (T(1) - x) / (T(1) - mid);
+  else if (x <= mid) y = so_pow(x, p) / so_pow(mid, p - T(1));
+  else y = T(1) - so_pow(T(1) - x, p) / so_pow(T(1) - mid, p - T(1));
+  return K.imp0[j] + y * (K.imp1[j] - K.imp0[j]);
+}
+
+// Exact minimiser over x of  m x^2/2 - c x + huber_f(x - af)   (friction-loss row only), closed form:
+//   t = c - m af;  F = clamp(t * D/(m+D), -loss, loss);  x = af + (t - F)/m
+template <typename T>
+SO_HD T solve1(T m, T c, T af, T D, T loss) {
+  T t = c - m * af;
+  T F = t * (D / (m + D));
+  F = F > loss ? loss : (F < -loss ? -loss : F);
+  return af + (t - F) / m;
+}
+
+// Projected Gauss-Seidel on   min_a  a^T M a / 2 - b^T a + sum_j [ friction_j(a_j) + limit_j(a_j) ]:
+// every constraint row touches ONE dof, so each coordinate update is the exact 1-D minimiser.  M ~ armature-dominated
+// (cond < 1.3) => contraction ~1e-2 per sweep (measured against the fp64 Newton oracle).
+// a[] holds the warm start on entry and the solution on exit; returns the largest update of the LAST sweep.
+template <typename T, int SWEEPS>
+SO_HD T solve_qacc(const ConC<T>& K, const T* M, const T* b, const T* q, const T* qd, T* a) {
+  T af[SO_NJ], xl[SO_NJ], Dl[SO_NJ], sg[SO_NJ];
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) {
+    af[j] = -K.fr_B[j] * qd[j];
+    sg[j] = T(0); xl[j] = T(0); Dl[j] = T(0);
+    T dlo = q[j] - K.lo[j], dhi = K.hi[j] - q[j];
+    if (dlo < T(0) || dhi < T(0)) {  // rare: joint outside its range -> one unilateral row
+      T side = dlo < T(0) ? T(1) : T(-1), dist = dlo < T(0) ? dlo : dhi;
+      T imp = impedance(K, j, dist);
+      T R = (T(1) - imp) / imp * K.invw[j];
+      R = R < T(1e-15) ? T(1e-15) : R;
+      T aref = -K.lim_B[j] * (side * qd[j]) - K.lim_K[j] * imp * dist;
+      sg[j] = side; Dl[j] = T(1) / R; xl[j] = side * aref;  // row active while side*(x - xl) < 0
+    }
+  }
+  T last = T(0);
+#pragma unroll
+  for (int sw = 0; sw < SWEEPS; sw++) {
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) {
+      T m = M[midx(j, j)], cc = b[j];
+#pragma unroll
+      for (int k = 0; k < SO_NJ; k++)
+        if (k != j) cc -= (k < j ? M[midx(j, k)] : M[midx(k, j)]) * a[k];
+      T x = solve1(m, cc, af[j], K.fr_D[j], K.fr_loss[j]);
+      if (sg[j] != T(0) && sg[j] * (x - xl[j]) < T(0)) x = solve1(m + Dl[j], cc + Dl[j] * xl[j], af[j], K.fr_D[j], K.fr_loss[j]);
+      if (sw == SWEEPS - 1) { T d = x - a[j]; d = d < 0 ? -d : d; last = d > last ? d : last; }
+      a[j] = x;
+    }
+  }
+  return last;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// World kinematics of the points the tasks look at (done once per env step, in the last substep: SURVEY Q3).
+template <typename T>
+struct KinC {
+  T base_R[9], base_p[3];
+  int ee_body, wrist_body, cam_body;
+  T ee_off[3], cam_pos[3], cam_R[9];
+};
+template <typename T>
+struct KinOut { T end_pos[3], wrist[3], cam_pos[3], cam_R[9]; };
+
+template <typename T>
+SO_HD void mat_vec(const T* R, const T* v, T* o) {
+  T x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2], y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2],
+    z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+template <typename T>
+SO_HD void mat_mul(const T* A, const T* B, T* o) {
+  T r[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) r[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+#pragma unroll
+  for (int i = 0; i < 9; i++) o[i] = r[i];
+}
+
+template <typename T, bool WANT_CAM>
+SO_HD void task_kinematics(const DynC<T>& C, const KinC<T>& Kc, const T* s, const T* c, KinOut<T>& out) {
+  T R[9], o[3];
+#pragma unroll
+  for (int k = 0; k < 9; k++) R[k] = Kc.base_R[k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) o[k] = Kc.base_p[k];
+#pragma unroll
+  for (int i = 0; i < SO_NJ; i++) {
+    const LinkC<T>& L = C.L[i];
+    if (i > Kc.ee_body && i > Kc.wrist_body && (!WANT_CAM || i > Kc.cam_body)) break;
+    T t[3];
+    mat_vec(R, L.p, t);
+    o[0] += t[0]; o[1] += t[1]; o[2] += t[2];
+    mat_mul(R, L.R, R);
+#pragma unroll
+    for (int r = 0; r < 3; r++) {  // R <- R * Rz(q_i)
+      T x = R[3 * r], y = R[3 * r + 1];
+      R[3 * r] = c[i] * x + s[i] * y;
+      R[3 * r + 1] = c[i] * y - s[i] * x;
+    }
+    if (i == Kc.wrist_body) { out.wrist[0] = o[0]; out.wrist[1] = o[1]; out.wrist[2] = o[2]; }
+    if (i == Kc.ee_body) {
+      mat_vec(R, Kc.ee_off, t);
+      out.end_pos[0] = o[0] + t[0]; out.end_pos[1] = o[1] + t[1]; out.end_pos[2] = o[2] + t[2];
+    }
+    if (WANT_CAM && i == Kc.cam_body) {
+      mat_vec(R, Kc.cam_pos, t);
+      out.cam_pos[0] = o[0] + t[0]; out.cam_pos[1] = o[1] + t[1]; out.cam_pos[2] = o[2] + t[2];
+      mat_mul(R, Kc.cam_R, out.cam_R);
+    }
+  }
+}
