@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py — so100 env-steps/s at 65 536 envs/GPU (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--task Env01] [--envs-per-gpu 65536]
+
+A "step" is one `so100_step` launch over every env of this rank: pre-step task logic, 16 physics substeps,
+obs / reward / termination / TimeLimit and in-kernel auto-reset.  Inputs (actions) are resident in HBM when the timed
+region starts; `e2e` repeats the measurement through the host-buffer C-ABI call (pinned host actions in, host
+obs / reward / done out, copies inside the timed region).  Rank 0 prints ONE JSON line.
+
+`--impl reference`: the reference's CPU path.  MuJoCo is not installable in this image (no wheel, no network), so the
+timed engine is the repo's fp64 C oracle (kind "port") on all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# Algorithmic work per env step (DESIGN.md "Roofline arithmetic"; tools/count_flops.cpp for the FLOPs)
+FLOP_PER_ENV_STEP = {1: 60400.0, 2: 60400.0, 5: 60700.0}
+BYTES_PER_ENV_STEP = {1: 338.0, 2: 362.0, 5: 420.0}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--task", default="Env01")
+    ap.add_argument("--envs-per-gpu", type=int, default=65536)
+    ap.add_argument("--cpu-envs", type=int, default=0, help="envs in the CPU sample (default: 256 per host thread)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons with nvidia-smi WHILE the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for k, name in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(task: int, n_envs: int, seconds: float, threads: int):
+    """env-steps/s of the fp64 C oracle on `threads` host threads (bounded sample)."""
+    import numpy as np
+    from oracle.pyoracle import Oracle
+    from so100_mujoco_rl_b200.model import load_model
+    from so100_mujoco_rl_b200.tasks import make_task_cfg
+    o = Oracle(load_model().to_ctypes(), make_task_cfg(task, n_envs, seed=0))
+    o.reset(nthreads=threads)
+    rng = np.random.default_rng(0)
+    acts = [rng.uniform(-1, 1, (n_envs, 6)).astype(np.float32) for _ in range(8)]
+    o.step(acts[0], nthreads=threads)  # warm-up
+    t0, k = time.perf_counter(), 0
+    while True:
+        o.step(acts[k % 8], nthreads=threads)
+        k += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            break
+    return n_envs * k / dt, k, dt
+
+
+def run_reference(args, rank: int):
+    """Reference arm: the CPU path on the host's cores (oracle port; see module docstring)."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle.pyoracle import Oracle, lib
+    from so100_mujoco_rl_b200.model import load_model
+    from so100_mujoco_rl_b200.tasks import make_task_cfg, task_id
+    task = task_id(args.task)
+    threads = lib().orc_hw_threads()
+    n = args.cpu_envs or 256 * threads
+    o = Oracle(load_model().to_ctypes(), make_task_cfg(task, n, seed=0))
+    o.reset(nthreads=threads)
+    rng = np.random.default_rng(0)
+    acts = [rng.uniform(-1, 1, (n, 6)).astype(np.float32) for _ in range(8)]
+    for w in range(args.warmup):
+        o.step(acts[w % 8], nthreads=threads)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        o.step(acts[k % 8], nthreads=threads)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"{n} envs x {args.steps} steps of the {args.envs_per_gpu}-env workload, fp64 C oracle (MuJoCo not installable here), {threads} threads"
+    line = {
+        "impl": "reference", "metric": "so100 env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.task} reach, {args.envs_per_gpu} envs/GPU, U(-1,1) random actions (CPU sample: {n} envs)"},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from so100_mujoco_rl_b200 import _native
+    from so100_mujoco_rl_b200.batched_env import BatchedSo100Env
+    from so100_mujoco_rl_b200.tasks import OBS_DIM, task_id
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    task = task_id(args.task)
+    n = args.envs_per_gpu
+    env = BatchedSo100Env(task, n, device=local_rank, seed=0, env_offset=rank * n)  # env-sharded, no collective on the step path
+    env.reset()
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    ring = [torch.rand((n, 6), device=dev, generator=g) * 2 - 1 for _ in range(64)]  # U(-1,1) actions, resident in HBM
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for w in range(max(args.warmup, 3)):
+        env.step(ring[w % 64])
+    launches0 = env.stats()["launches"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()  # evict the env state from L2 between timed iterations
+        ev[k][0].record()
+        env.step(ring[k % 64])
+        ev[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    launches = env.stats()["launches"] - launches0
+    stats = env.stats()
+
+    # end to end through the host-buffer C-ABI call (what the VecEnv adapter uses)
+    e2e = None
+    if not args.no_e2e:
+        host = env.alloc_host()
+        host_ring = [r.cpu().pin_memory() for r in ring[:8]]
+        for w in range(3):
+            host["actions"].copy_(host_ring[w % 8])
+            env.step_host(host)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            host["actions"].copy_(host_ring[k % 8])
+            env.step_host(host)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        od = OBS_DIM[task]
+        e2e = {"seconds": e2e_s, "h2d": n * 6 * 4, "d2h": n * (2 * od * 4 + 4 + 1 + 1 + 4 + 4)}
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, e2e["seconds"] if e2e else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_max = float(t[0]), float(t[1])
+    else:
+        e2e_max = e2e["seconds"] if e2e else 0.0
+
+    if rank == 0:
+        import ctypes
+        total_envs = n * world
+        value = total_envs * args.steps / (total_ms * 1e-3)
+        per_gpu = value / world
+        tf = ctypes.c_double(0.0)
+        _native.check(_native.lib().so100_bench_fp32_peak(local_rank, 4096, ctypes.byref(tf)))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak, hbm_src = (peaks["hbm_gbs"], "of measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "of fallback")
+        ach_tf = per_gpu * FLOP_PER_ENV_STEP[task] / 1e12
+        ach_gb = per_gpu * BYTES_PER_ENV_STEP[task] / 1e9
+        line = {
+            "metric": "so100 env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.task}, {n} envs/GPU, U(-1,1) random actions, 16 substeps/step, in-kernel auto-reset",
+                       "envs_per_gpu": n, "task": args.task, "l2": "flushed between timed steps (256 MiB memset)",
+                       "parallelism": f"env-sharded x{world}, no collective on the step path"},
+            "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s",
+                         "frac": ach_tf / tf.value if tf.value else None, "traffic": None,
+                         "peak_source": "FFMA probe measured in this run (so100_bench_fp32_peak); nominal 74.5",
+                         "flop_per_env_step": FLOP_PER_ENV_STEP[task]},
+            "roofline_hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
+                             "peak_source": hbm_src, "bytes_per_env_step": BYTES_PER_ENV_STEP[task]},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "wall_s_timed_region": t_wall,
+            "solver_unconverged": stats["solver_unconverged"], "nan_resets": stats["nan_resets"],
+        }
+        if e2e:
+            line["e2e"] = {"value": total_envs * args.steps / e2e_max, "unit": "env-steps/s",
+                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            ncpu = args.cpu_envs or 256 * threads
+            rate, k, dt = cpu_oracle_rate(task, ncpu, 12.0, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                                    "sample": f"{ncpu} envs x {k} steps ({dt:.1f} s) of the same workload on the fp64 C oracle"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

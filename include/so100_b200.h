@@ -134,6 +134,7 @@ typedef struct so100_state_view {
   float *qpos;          /* [6][N] */
   float *qvel;          /* [6][N] */
   float *qacc_warm;     /* [6][N]  previous substep's qacc (solver warm start, mjData.qacc_warmstart) */
+  float *qpos_comp;     /* [6][N]  compensation term of the fp32 qpos integration: qpos_exact ~ qpos - qpos_comp */
   float *block;         /* [3][N]  block position (qpos[6:9] of the reference) */
   float *snap;          /* [12][N] stale kinematics snapshot: Env01/02 end_pos(0..2), wrist_z(3), block_xpos(4..6);
                                     Env05 cam_xpos(0..2), cam_xmat(3..11 row-major) */
@@ -211,6 +212,13 @@ int so100_get_derived(so100_ctx *ctx, double *dof_M0, double *kv, double *invwei
 /* Kernel launches issued by this ctx so far; env steps whose Gauss-Seidel solve had not converged to 1e-4
    (relative) in its last sweep; envs force-reset because their state went non-finite (device counters, syncs). */
 int so100_get_stats(so100_ctx *ctx, int64_t *launches, int64_t *solver_fallbacks, int64_t *nan_resets);
+
+/*
+ * Bench utility (not part of the env API): measures this GPU's achievable FP32 FMA rate with a register-resident
+ * FFMA loop (8 independent chains per thread, every SM filled) and returns TFLOP/s (FMA = 2 FLOP).  It is the
+ * denominator of the FP32 roofline in bench.py, because MEASURED_PEAKS.json carries no CUDA-core figure.
+ */
+int so100_bench_fp32_peak(int device, int iters, double *tflops_out);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ EXPORTS = [
     "so100_abi_version", "so100_last_error", "so100_obs_dim", "so100_act_dim", "so100_create", "so100_destroy",
     "so100_reset", "so100_step", "so100_reset_host", "so100_step_host", "so100_get_state", "so100_set_state",
     "so100_get_tick", "so100_set_tick", "so100_forward_dynamics", "so100_host_forward", "so100_get_derived",
-    "so100_get_stats",
+    "so100_get_stats", "so100_bench_fp32_peak",
 ]
 
 
@@ -32,7 +32,7 @@ class So100Error(RuntimeError):
 class StateView(ctypes.Structure):
     """ctypes mirror of `so100_state_view`."""
     _fields_ = [(n, ctypes.c_void_p) for n in
-                ("qpos", "qvel", "qacc_warm", "block", "snap", "aux", "counters", "ep_return")]
+                ("qpos", "qvel", "qacc_warm", "qpos_comp", "block", "snap", "aux", "counters", "ep_return")]
 
 
 _lib = None
@@ -69,6 +69,7 @@ def lib() -> ctypes.CDLL:
     L.so100_host_forward.argtypes = [ctypes.POINTER(So100Model), ci, dp, dp, dp, dp, dp, dp, dp, ci]
     L.so100_get_derived.argtypes = [vp, dp, dp, dp]
     L.so100_get_stats.argtypes = [vp, i64p, i64p, i64p]
+    L.so100_bench_fp32_peak.argtypes = [ci, ci, dp]
     for name in EXPORTS:
         if name not in ("so100_last_error", "so100_destroy"):
             getattr(L, name).restype = ci

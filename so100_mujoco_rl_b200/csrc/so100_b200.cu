@@ -59,7 +59,7 @@ struct Consts {
 };
 
 struct Bufs {
-  float *qpos, *qvel, *warm, *block, *snap, *aux, *ep_return;
+  float *qpos, *qvel, *warm, *qcomp, *block, *snap, *aux, *ep_return;
   int* cnt;
   const float* start_tab;  // [n_start][6]
   unsigned long long* stats;  // [0] solver non-converged, [1] nan resets
@@ -93,6 +93,7 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 
 struct EnvRegs {  // everything one env carries through a step, in registers
   float q[SO_NJ], v[SO_NJ], w[SO_NJ];
+  float qc[SO_NJ];  // Kahan compensation of the qpos integration (qpos = q - qc to ~2^-48)
   float blk[3];
   float snap[kSnap];
   float aux[kAux];
@@ -103,7 +104,7 @@ struct EnvRegs {  // everything one env carries through a step, in registers
 template <int TASK>
 __device__ __forceinline__ void load_env(const Bufs& B, int n, int i, EnvRegs& e) {
 #pragma unroll
-  for (int j = 0; j < SO_NJ; j++) { e.q[j] = B.qpos[j * n + i]; e.v[j] = B.qvel[j * n + i]; e.w[j] = B.warm[j * n + i]; }
+  for (int j = 0; j < SO_NJ; j++) { e.q[j] = B.qpos[j * n + i]; e.v[j] = B.qvel[j * n + i]; e.w[j] = B.warm[j * n + i]; e.qc[j] = B.qcomp[j * n + i]; }
 #pragma unroll
   for (int k = 0; k < 3; k++) e.blk[k] = B.block[k * n + i];
   constexpr int ns = TASK == 5 ? 12 : 7, na = TASK == 5 ? 18 : (TASK == 2 ? 6 : 0);
@@ -118,7 +119,7 @@ __device__ __forceinline__ void load_env(const Bufs& B, int n, int i, EnvRegs& e
 template <int TASK>
 __device__ __forceinline__ void store_env(const Bufs& B, int n, int i, const EnvRegs& e) {
 #pragma unroll
-  for (int j = 0; j < SO_NJ; j++) { B.qpos[j * n + i] = e.q[j]; B.qvel[j * n + i] = e.v[j]; B.warm[j * n + i] = e.w[j]; }
+  for (int j = 0; j < SO_NJ; j++) { B.qpos[j * n + i] = e.q[j]; B.qvel[j * n + i] = e.v[j]; B.warm[j * n + i] = e.w[j]; B.qcomp[j * n + i] = e.qc[j]; }
 #pragma unroll
   for (int k = 0; k < 3; k++) B.block[k * n + i] = e.blk[k];
   constexpr int ns = TASK == 5 ? 12 : 7, na = TASK == 5 ? 18 : (TASK == 2 ? 6 : 0);
@@ -198,7 +199,7 @@ template <int TASK>
 __device__ __forceinline__ void reset_env(const Consts& C, const Bufs& B, EnvRegs& e, int env, unsigned tick, unsigned stream, float* obs) {
   const TaskC& t = C.t;
 #pragma unroll
-  for (int j = 0; j < SO_NJ; j++) { e.q[j] = 0.0f; e.v[j] = 0.0f; e.w[j] = 0.0f; }
+  for (int j = 0; j < SO_NJ; j++) { e.q[j] = 0.0f; e.v[j] = 0.0f; e.w[j] = 0.0f; e.qc[j] = 0.0f; }
 #pragma unroll
   for (int k = 0; k < kSnap; k++) e.snap[k] = 0.0f;
   e.elapsed = 0; e.ep_ret = 0.0f;
@@ -262,12 +263,19 @@ __device__ __forceinline__ float reward_reach(const TaskC& t, EnvRegs& e) {
 }
 
 // 16 x mj_step on the arm.  ctrl is constant over the env step, so kp*clip(ctrl) is hoisted.
+// ctrl is carried as an unevaluated sum ctrl_hi + ctrl_lo so that Env01/02's closed loop ctrl = qpos + a*0.075 does not
+// round the 0.075-rad increment to the ulp of a 3-rad angle (that rounding random-walks qpos in a neutrally stable loop).
 template <int TASK>
-__device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs& e, const float* ctrl) {
+__device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs& e, const float* ctrl_hi, const float* ctrl_lo) {
   const TaskC& t = C.t;
-  float kc[SO_NJ];
+  float cc[SO_NJ], cl[SO_NJ];
 #pragma unroll
-  for (int j = 0; j < SO_NJ; j++) kc[j] = t.kp[j] * clampf(ctrl[j], t.ctrl_lo[j], t.ctrl_hi[j]);
+  for (int j = 0; j < SO_NJ; j++) {
+    float sum = ctrl_hi[j] + ctrl_lo[j];
+    bool in = sum >= t.ctrl_lo[j] && sum <= t.ctrl_hi[j];
+    cc[j] = in ? ctrl_hi[j] : clampf(sum, t.ctrl_lo[j], t.ctrl_hi[j]);
+    cl[j] = in ? ctrl_lo[j] : 0.0f;
+  }
   float worst = 0.0f;
 #pragma unroll 1
   for (int sub = 0; sub < t.nsub; sub++) {
@@ -278,16 +286,19 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
     dyn_bias_mass<float>(C.dyn, s, c, e.v, bias, M);
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {
-      float f = kc[j] - t.kp[j] * e.q[j] - t.kv[j] * e.v[j];
+      float f = t.kp[j] * ((cc[j] - e.q[j]) + (cl[j] + e.qc[j])) - t.kv[j] * e.v[j];  // differences first: no cancellation
       b[j] = clampf(f, t.frc_lo[j], t.frc_hi[j]) - bias[j];
     }
-    float d = solve_qacc<float, 5>(C.con, M, b, e.q, e.v, e.w);
+    float d = solve_qacc<float, 5>(C.con, M, b, e.q, e.qc, e.v, e.w);
     float amax = 1.0f;
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {
       amax = fmaxf(amax, fabsf(e.w[j]));
       e.v[j] += t.h * e.w[j];   // mj_Euler (semi-implicit; no joint damping in this model)
-      e.q[j] += t.h * e.v[j];
+      float y = __fsub_rn(__fmul_rn(t.h, e.v[j]), e.qc[j]);  // compensated sum: 16 000 substeps of 1e-5 rad increments on |q| ~ 3
+      float s1 = __fadd_rn(e.q[j], y);
+      e.qc[j] = __fsub_rn(__fsub_rn(s1, e.q[j]), y);
+      e.q[j] = s1;
     }
     worst = fmaxf(worst, d / amax);
   }
@@ -319,12 +330,12 @@ __global__ void __launch_bounds__(kBlock, 7) step_kernel(const __grid_constant__
   if (live) {
     EnvRegs e;
     load_env<TASK>(B, n, i, e);
-    float rew, ctrl[SO_NJ];
+    float rew, ctrl[SO_NJ], ctrl_lo[SO_NJ];
     bool term = false;
     if (TASK == 1 || TASK == 2) {
       rew = reward_reach(t, e);
 #pragma unroll
-      for (int j = 0; j < SO_NJ; j++) ctrl[j] = e.q[j] + a[j] * t.step_scale;  // closed loop on qpos (Q6)
+      for (int j = 0; j < SO_NJ; j++) { ctrl[j] = e.q[j]; ctrl_lo[j] = a[j] * t.step_scale - e.qc[j]; }  // closed loop on qpos (Q6)
       if (TASK == 2) {  // env02_v1.py:29-37, reach test on stale kinematics
         float dx = e.snap[4] - e.snap[0], dy = e.snap[5] - e.snap[1], dz = e.snap[6] - e.snap[2];
         if (sqrtf(dx * dx + dy * dy + dz * dz) < t.reach) {
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(kBlock, 7) step_kernel(const __grid_constant__
           for (int k = 0; k < 3; k++) e.aux[k] = e.blk[k];
         }
       }
-      physics<TASK>(C, B, e, ctrl);
+      physics<TASK>(C, B, e, ctrl, ctrl_lo);
       write_obs<TASK>(t, e, i, io.tick, STREAM_NOISE, obs);
     } else {  // env03_v1.py:124-201
       float time = (float)e.elapsed * t.dt_env;
@@ -368,8 +379,8 @@ __global__ void __launch_bounds__(kBlock, 7) step_kernel(const __grid_constant__
       }
       float newcmd[SO_NJ];
 #pragma unroll
-      for (int j = 0; j < SO_NJ; j++) { newcmd[j] = e.aux[j] + a[j] * t.step_scale; ctrl[j] = newcmd[j]; }  // open loop (Q6)
-      physics<TASK>(C, B, e, ctrl);
+      for (int j = 0; j < SO_NJ; j++) { newcmd[j] = e.aux[j] + a[j] * t.step_scale; ctrl[j] = newcmd[j]; ctrl_lo[j] = 0.0f; }  // open loop (Q6)
+      physics<TASK>(C, B, e, ctrl, ctrl_lo);
       write_obs<TASK>(t, e, i, io.tick, STREAM_NOISE, obs);
       if (obs[6] == -1.0f && obs[7] == -1.0f) {  // :152-164
         if (e.miss > t.lost_limit) term = true;
@@ -456,7 +467,8 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const __grid_constant__
     float f = t.kp[j] * clampf(ctrl[j * n + i], t.ctrl_lo[j], t.ctrl_hi[j]) - t.kp[j] * q[j] - t.kv[j] * v[j];
     b[j] = clampf(f, t.frc_lo[j], t.frc_hi[j]) - bias[j];
   }
-  solve_qacc<float, 12>(C.con, M, b, q, v, a);
+  float zc[SO_NJ] = {0, 0, 0, 0, 0, 0};
+  solve_qacc<float, 12>(C.con, M, b, q, zc, v, a);
   if (M_out)
 #pragma unroll
     for (int k = 0; k < 21; k++) M_out[k * n + i] = M[k];
@@ -474,6 +486,20 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const __grid_constant__
 #pragma unroll
     for (int k = 0; k < 9; k++) kin_out[(9 + k) * n + i] = ko.cam_R[k];
   }
+}
+
+// FP32 peak probe: 8 independent FFMA chains per thread, operands in registers
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.678f) out[0] = s;  // never true in practice; keeps the chains alive
 }
 
 // ------------------------------------------------------------------------------------------------ host: model -> constants
@@ -669,7 +695,7 @@ struct so100_ctx {
 static void free_ctx(so100_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  void* ptrs[] = {c->B.qpos, c->B.qvel, c->B.warm, c->B.block, c->B.snap, c->B.aux, c->B.ep_return, c->B.cnt, c->B.stats,
+  void* ptrs[] = {c->B.qpos, c->B.qvel, c->B.warm, c->B.qcomp, c->B.block, c->B.snap, c->B.aux, c->B.ep_return, c->B.cnt, c->B.stats,
                   c->start_tab, c->h_act, c->h_obs, c->h_rew, c->h_tobs, c->h_epr, c->h_term, c->h_trunc, c->h_epl};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete c;
@@ -748,7 +774,7 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
     if (cudaMalloc(p, bytes) != cudaSuccess) return false;
     return cudaMemset(*p, 0, bytes) == cudaSuccess;
   };
-  bool ok = alloc((void**)&c->B.qpos, 6 * n * 4) && alloc((void**)&c->B.qvel, 6 * n * 4) && alloc((void**)&c->B.warm, 6 * n * 4) &&
+  bool ok = alloc((void**)&c->B.qpos, 6 * n * 4) && alloc((void**)&c->B.qvel, 6 * n * 4) && alloc((void**)&c->B.warm, 6 * n * 4) && alloc((void**)&c->B.qcomp, 6 * n * 4) &&
             alloc((void**)&c->B.block, 3 * n * 4) && alloc((void**)&c->B.snap, kSnap * n * 4) && alloc((void**)&c->B.aux, kAux * n * 4) &&
             alloc((void**)&c->B.ep_return, n * 4) && alloc((void**)&c->B.cnt, kCnt * n * 4) && alloc((void**)&c->B.stats, 2 * 8) &&
             alloc((void**)&c->start_tab, kMaxStart * SO_NJ * 4);
@@ -853,7 +879,7 @@ static int copy_state(so100_ctx* c, const so100_state_view* v, void* stream, boo
   cudaStream_t st = (cudaStream_t)stream;
   size_t n = (size_t)c->n;
   struct { void* ext; void* in; size_t bytes; } f[] = {
-      {v->qpos, c->B.qpos, 6 * n * 4}, {v->qvel, c->B.qvel, 6 * n * 4}, {v->qacc_warm, c->B.warm, 6 * n * 4},
+      {v->qpos, c->B.qpos, 6 * n * 4}, {v->qvel, c->B.qvel, 6 * n * 4}, {v->qacc_warm, c->B.warm, 6 * n * 4}, {v->qpos_comp, c->B.qcomp, 6 * n * 4},
       {v->block, c->B.block, 3 * n * 4}, {v->snap, c->B.snap, kSnap * n * 4}, {v->aux, c->B.aux, kAux * n * 4},
       {v->counters, c->B.cnt, kCnt * n * 4}, {v->ep_return, c->B.ep_return, n * 4}};
   for (auto& x : f) {
@@ -904,7 +930,8 @@ int so100_host_forward(const so100_model* m, int n, const double* qpos, const do
       double f = m->act_kp[j] * cc - m->act_kp[j] * q[j] - H.kv[j] * v[j];
       b[j] = std::fmin(std::fmax(f, m->act_forcerange[j][0]), m->act_forcerange[j][1]) - bias[j];
     }
-    for (int k = 0; k < (sweeps > 0 ? sweeps : 1); k++) solve_qacc<double, 1>(H.con, M, b, q, v, a);
+    const double zc[SO_NJ] = {0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < (sweeps > 0 ? sweeps : 1); k++) solve_qacc<double, 1>(H.con, M, b, q, zc, v, a);
     if (M_out) memcpy(M_out + 21 * i, M, sizeof M);
     if (bias_out) memcpy(bias_out + 6 * i, bias, sizeof bias);
     if (qacc_out) memcpy(qacc_out + 6 * i, a, sizeof a);
@@ -936,6 +963,33 @@ int so100_get_stats(so100_ctx* c, int64_t* launches, int64_t* solver_fallbacks, 
   if (launches) *launches = c->launches;
   if (solver_fallbacks) *solver_fallbacks = (int64_t)s[0];
   if (nan_resets) *nan_resets = (int64_t)s[1];
+  return SO100_OK;
+}
+
+int so100_bench_fp32_peak(int device, int iters, double* tflops_out) {
+  if (!tflops_out || iters <= 0) return fail(SO100_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  float* d = nullptr;
+  CU(cudaMalloc((void**)&d, 4));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    CU(cudaEventRecord(e0));
+    ffma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999f, 0.001f);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    double fl = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    if (rep > 0 && ms > 0) best = std::fmax(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *tflops_out = best;
   return SO100_OK;
 }
 

@@ -242,14 +242,15 @@ SO_HD T solve1(T m, T c, T af, T D, T loss) {
 // every constraint row touches ONE dof, so each coordinate update is the exact 1-D minimiser.  M ~ armature-dominated
 // (cond < 1.3) => contraction ~1e-2 per sweep (measured against the fp64 Newton oracle).
 // a[] holds the warm start on entry and the solution on exit; returns the largest update of the LAST sweep.
+// qc[] is the compensation term of the fp32 position integration (zeros when T = double).
 template <typename T, int SWEEPS>
-SO_HD T solve_qacc(const ConC<T>& K, const T* M, const T* b, const T* q, const T* qd, T* a) {
+SO_HD T solve_qacc(const ConC<T>& K, const T* M, const T* b, const T* q, const T* qc, const T* qd, T* a) {
   T af[SO_NJ], xl[SO_NJ], Dl[SO_NJ], sg[SO_NJ];
 #pragma unroll
   for (int j = 0; j < SO_NJ; j++) {
     af[j] = -K.fr_B[j] * qd[j];
     sg[j] = T(0); xl[j] = T(0); Dl[j] = T(0);
-    T dlo = q[j] - K.lo[j], dhi = K.hi[j] - q[j];
+    T dlo = (q[j] - K.lo[j]) - qc[j], dhi = (K.hi[j] - q[j]) + qc[j];  // true qpos = q - qc (compensated sum)
     if (dlo < T(0) || dhi < T(0)) {  // rare: joint outside its range -> one unilateral row
       T side = dlo < T(0) ? T(1) : T(-1), dist = dlo < T(0) ? dlo : dhi;
       T imp = impedance(K, j, dist);

@@ -137,7 +137,8 @@ class ModelSpec:
     ee_body: int = 4  # Fixed_Jaw
     wrist_body: int = 3  # Wrist_Pitch_Roll
     cam_body: int = 4
-    ee_offset: np.ndarray = field(default_factory=lambda: np.array([0.0, -0.1, 0.0]))  # env_base_01.py:125
+    # env_base_01.py:125 builds the offset as a float32 array, so the reference's -0.1 is float32(-0.1) = -0.10000000149
+    ee_offset: np.ndarray = field(default_factory=lambda: np.array([0.0, -0.1, 0.0], dtype=np.float32).astype(np.float64))
     cam_pos: np.ndarray = field(default_factory=lambda: np.zeros(3))
     cam_quat: np.ndarray = field(default_factory=lambda: np.array([1.0, 0, 0, 0]))
     cam_fovy_deg: float = 45.0

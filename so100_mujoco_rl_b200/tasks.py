@@ -72,7 +72,7 @@ ENV_IDS = {"Env01": TASK_ENV01, "Env01-v1": TASK_ENV01, "Env02": TASK_ENV02, "En
 
 
 class So100TaskCfg(ctypes.Structure):
-    """ctypes mirror of `so100_task_cfg` (include/so100_b200.h) and `orc_task_cfg` (oracle/so100_oracle.h)."""
+    """ctypes mirror of `so100_task_cfg` (include/so100_b200.h); the test oracle declares the same layout."""
     _fields_ = [
         ("struct_size", ctypes.c_int32),
         ("task", ctypes.c_int32),

@@ -1,0 +1,55 @@
+"""The oracle's TASK LOGIC against fixtures produced by the reference's own, unmodified Python env classes
+(tools/gen_golden_from_reference.py: Env01 / Env02 / Env05 imported from the reference checkout, with `mujoco`
+stubbed by the oracle's physics and np.random patched to the shared Philox stream).  This pins reward, observation,
+reset, block scripting, re-projection, lost-cube termination, TimeLimit and auto-reset bit-for-bit in behaviour.
+The GPU tests replay the same fixtures through the CUDA path (tests/test_gpu_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, make_oracle
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def load(task):
+    return np.load(os.path.join(GOLD, f"ref_env0{task}.npz"))
+
+
+@pytest.mark.parametrize("task", [1, 2, 5])
+def test_oracle_reproduces_reference_task_logic(task):
+    g = load(task)
+    steps, n = g["reward"].shape
+    o = make_oracle(task, n, seed=int(g["seed"]), max_episode_steps=int(g["max_episode_steps"]))
+    assert np.array_equal(o.reset(), g["obs0"])
+    nd = 0
+    for t in range(steps):
+        obs, rew, term, trunc, tobs, epr, epl = o.step(g["actions"][t])
+        assert np.array_equal(term, g["terminated"][t]) and np.array_equal(trunc, g["truncated"][t]), f"step {t}"
+        # the reference computes Env05's reward partly in float32 (numpy scalar promotion); everything else is fp64
+        assert np.abs(rew - g["reward"][t]).max() < (2e-6 if task == 5 else 1e-12), f"step {t}"
+        assert np.abs(obs - g["obs"][t]).max() <= (1e-6 if task == 5 else 0), f"step {t}"
+        done = (term | trunc).astype(bool)
+        nd += int(done.sum())
+        if done.any():
+            assert np.abs(tobs[done] - g["terminal_obs"][t][done]).max() <= (1e-6 if task == 5 else 0)
+    assert nd >= n  # every fixture exercises auto-reset
+    if task == 5:
+        assert g["terminated"].sum() >= 1  # ... and the lost-cube termination
+
+
+def test_fixtures_cover_the_quirks():
+    g1, g2, g5 = load(1), load(2), load(5)
+    # Q2: reset observations carry zero kinematics; Env05 reset obs is (START_POSITION, -1, -1) un-scaled
+    assert (g1["obs0"][:, 6:] == 0).all() and (g2["obs0"][:, 6:] == 0).all()
+    assert (g5["obs0"][:, 6:] == -1).all()
+    # Q5: Env01 leaves the Jaw at qpos0 on reset, Env02 resets to REST_POSITION
+    assert (g1["obs0"][:, 5] == 0).all()
+    assert np.allclose(g2["obs0"][:, :6], [0.0, -3.141, 3.117, 1.0, 0.0, 0.0])
+    # Q12: the first Env02 step after a reset sees distance 0 < 0.03 (zero kinematics) and relocates the block
+    assert (np.abs(g2["obs"][0][:, 9:11]).sum(axis=1) > 0.2).all()
+    # Q10 / Q13: a miss is reported as -5 after the x5 scaling, outside the declared [0, 5] bounds
+    assert (g5["obs"][:, :, 6:] == -5).any()
+    # Env01's reward is a sum of non-positive terms
+    assert (g1["reward"] <= 0).all()

@@ -1,0 +1,155 @@
+"""Pins the fp64 oracle (oracle/so100_oracle.c) with analytic invariants and the survey's hand-derived anchors
+(SURVEY.md Appendix A.4).  The reference holds no golden vectors for mj_step (its arithmetic is the MuJoCo wheel),
+so these are the strongest pins available offline: PARITY WITH REAL MUJOCO REMAINS UNPINNED."""
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import make_oracle
+from oracle.pyoracle import philox
+from so100_mujoco_rl_b200.tasks import REST_POSITION, START_POSITION_05, VALID_START_POSITIONS
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return make_oracle(1, 1)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10: counter 0 / key 0
+    assert [hex(x) for x in philox(0, 0, 0, 0)] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+
+
+def test_survey_anchors(orc):
+    m0, kv, iw = orc.derived()
+    assert np.allclose(m0, [0.131490, 0.125088, 0.108872, 0.101160, 0.100043, 0.100028], atol=1e-6)
+    assert np.allclose(kv, [5.12815, 5.00176, 4.66631, 4.49799, 4.47311, 4.47276], atol=1e-5)
+    assert np.allclose(iw, [7.605165, 8.126401, 9.329947, 9.905365, 9.995670, 9.997296], atol=1e-6)
+    k = orc.fk([0] * 6)
+    assert np.allclose(k["end_pos"], [0, -0.4834, 0.0962], atol=1e-4) and np.allclose(k["wrist_pos"], [0, -0.3233, 0.0962], atol=1e-4)
+    k = orc.fk(REST_POSITION)
+    assert np.allclose(k["end_pos"], [0, -0.1877, 0.0229], atol=1e-4) and np.allclose(k["wrist_pos"], [0, -0.0980, 0.1555], atol=1e-4)
+    k = orc.fk(START_POSITION_05)
+    assert np.allclose(k["end_pos"], [0, -0.2625, 0.2400], atol=1e-4) and np.allclose(k["cam_xpos"], [-0.0015, -0.2368, 0.3320], atol=1e-4)
+    assert np.allclose(orc.fk(VALID_START_POSITIONS[0])["end_pos"], [0.0180, -0.1999, 0.2650], atol=1e-4)
+    M = orc.mass_matrix([0] * 6)
+    assert np.isclose(M[1, 2], 0.014293, atol=1e-6) and np.isclose(M[1, 3], 0.004342, atol=1e-6) and np.isclose(M[2, 3], 0.002892, atol=1e-6)
+    z = [0] * 6
+    assert np.allclose(-orc.bias(z, z), [0, 0.948174, 0.474886, 0.126042, 0.000352, -0.006027], atol=1e-6)
+    assert np.allclose(-orc.bias(REST_POSITION, z), [0, -0.055260, 0.417972, 0.069496, 0.000197, -0.003111], atol=1e-6)
+    assert np.allclose(-orc.bias(START_POSITION_05, z), [0, 0.192522, 0.321925, 0.100069, -0.001261, -0.001538], atol=1e-6)
+
+
+def test_env05_start_projection_anchor():
+    o = make_oracle(5, 1)
+    k = o.fk(START_POSITION_05)
+    p = k["cam_xmat"].reshape(3, 3).T @ (np.array([0, -0.35, 0.01]) - k["cam_xpos"])
+    assert np.allclose(p, [0.0002, -0.1077, -0.3239], atol=2e-4)
+    f = 0.5 * 1920 / np.tan(np.deg2rad(120) / 2)
+    u, v = f * p[0] / p[2] + 540, f * p[1] / p[2] + 960
+    assert abs((1080 - int(u)) / 1080 - 0.5009) < 2e-3 and abs((1920 - int(v)) / 1920 - 0.4042) < 2e-3
+
+
+def test_mass_matrix_symmetric_positive_definite(orc, spec):
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        q = rng.uniform(spec.jnt_range[:, 0], spec.jnt_range[:, 1])
+        M = orc.mass_matrix(q)
+        assert np.abs(M - M.T).max() < 1e-16
+        w = np.linalg.eigvalsh(M)
+        assert w.min() > 0.09 and w.max() / w.min() < 1.5  # armature-dominated
+
+
+def test_bias_equals_lagrangian_terms(orc, spec):
+    """qfrc_bias = C(q,qd) qd + dV/dq, with C from the Christoffel symbols of M(q) (central differences)."""
+    rng = np.random.default_rng(1)
+    eps = 1e-6
+    for _ in range(10):
+        q = rng.uniform(spec.jnt_range[:, 0], spec.jnt_range[:, 1]); qd = rng.normal(0, 2, 6)
+        dM = np.zeros((6, 6, 6)); dV = np.zeros(6)
+        for k in range(6):
+            e = np.zeros(6); e[k] = eps
+            dM[:, :, k] = (orc.mass_matrix(q + e) - orc.mass_matrix(q - e)) / (2 * eps)
+            dV[k] = (orc.energy(q + e, qd)[1] - orc.energy(q - e, qd)[1]) / (2 * eps)
+        c = np.zeros(6)
+        for i in range(6):
+            for j in range(6):
+                for k in range(6):
+                    c[i] += 0.5 * (dM[i, j, k] + dM[i, k, j] - dM[j, k, i]) * qd[j] * qd[k]
+        assert np.abs(orc.bias(q, qd) - (c + dV)).max() < 2e-8
+
+
+def _variant(spec, **over):
+    s = copy.deepcopy(spec)
+    for k, v in over.items():
+        setattr(s, k, np.asarray(v, dtype=float) if not np.isscalar(v) else v)
+    return s
+
+
+def test_energy_is_conserved_without_actuation_and_friction(spec):
+    """kp = 0, kv = 0, no friction-loss: the arm is a frictionless compound pendulum; semi-implicit Euler keeps the
+    total energy within O(h) of its initial value while it swings well away from the limits."""
+    s = _variant(spec, act_kp=np.zeros(6), act_dampratio=np.zeros(6), act_kv=np.zeros(6), jnt_frictionloss=np.zeros(6),
+                 jnt_armature=np.full(6, 0.1))
+    o = make_oracle(1, 1, spec=s)
+    q = np.array([0.3, -1.6, 1.5, 0.2, 0.1, 0.5]); v = np.zeros(6); w = np.zeros(6)
+    T0, V0 = o.energy(q, v)
+    drift = 0
+    for _ in range(40):
+        q, v, w = o.substeps(q, v, w, np.zeros(6), 5)
+        T, V = o.energy(q, v)
+        drift = max(drift, abs(T + V - T0 - V0))
+        assert (q > s.jnt_range[:, 0]).all() and (q < s.jnt_range[:, 1]).all()
+    assert T > 1e-4          # it actually moved
+    assert drift < 2e-3 * abs(V0) + 2e-4
+
+
+def test_friction_holds_small_torques(orc, spec):
+    """|gravity + servo torque| < frictionloss on a joint at rest => (almost) no acceleration: the Huber row sticks."""
+    q = np.array(REST_POSITION, dtype=float); v = np.zeros(6)
+    g = -orc.bias(q, v)
+    ctrl = q - g / 50.0            # servo cancels gravity exactly
+    ctrl[0] += 0.05 / 50.0         # +0.05 N m on Rotation, below the 0.1 N m friction loss
+    a = orc.forward(q, v, ctrl)[0]
+    m00 = orc.mass_matrix(q)[0, 0]
+    assert abs(a[0]) < 0.05 / m00 * 0.2    # far below the free response 0.05/M00
+    ctrl[0] += 0.25 / 50.0         # 0.30 N m: slips, net 0.2 N m over M00
+    a = orc.forward(q, v, ctrl)[0]
+    assert 0.95 * 0.2 / m00 < a[0] < 1.05 * 0.2 / m00
+
+
+def test_servo_settles_to_target_within_friction_deadband(orc):
+    q = np.array(START_POSITION_05); v = np.zeros(6); w = np.zeros(6)
+    ctrl = q + np.array([0.05, -0.05, 0.05, -0.05, 0.05, -0.05])
+    q, v, w = orc.substeps(q, v, w, ctrl, 1500)
+    g = -orc.bias(q, np.zeros(6))
+    # steady state: |kp (ctrl - q) + gravity| <= frictionloss (+ a little slack for the soft constraint)
+    assert np.abs(50 * (ctrl - q) + g).max() < 0.1 + 5e-3
+    assert np.abs(v).max() < 1e-3
+
+
+def test_joint_limit_pushes_back(orc, spec):
+    q = np.array(REST_POSITION, dtype=float); q[2] = spec.jnt_range[2, 1] + 0.01  # Elbow 0.01 rad beyond its upper limit
+    v = np.zeros(6)
+    a_in = orc.forward(q, v, q.copy())[0]
+    q2 = q.copy(); q2[2] = spec.jnt_range[2, 1] - 0.01
+    a_free = orc.forward(q2, v, q2.copy())[0]
+    assert a_in[2] < a_free[2] - 5.0  # K*imp*dist = 2770*0.95*0.01 ~ 26 rad/s^2 of reference acceleration
+    q, v, w = orc.substeps(q, v, np.zeros(6), q.copy() + 0.0, 400)
+    assert q[2] < spec.jnt_range[2, 1] + 0.004
+
+
+def test_newton_reaches_the_unique_minimiser(orc, spec):
+    """KKT check of the oracle's solve: M(a - a_smooth) = J^T f with f inside the Huber / unilateral laws."""
+    rng = np.random.default_rng(4)
+    m0, kv, iw = orc.derived()
+    for _ in range(100):
+        q = rng.uniform(spec.jnt_range[:, 0] - 0.03, spec.jnt_range[:, 1] + 0.03); v = rng.normal(0, 1, 6)
+        u = q + rng.uniform(-1, 1, 6) * 0.075
+        a, a_s, fc, it = orc.forward(q, v, u)
+        assert it < 30
+        M = orc.mass_matrix(q)
+        assert np.abs(M @ (a - a_s) - fc).max() < 1e-10 * (1 + np.abs(M @ a_s).max())
+        inside = (q >= spec.jnt_range[:, 0]) & (q <= spec.jnt_range[:, 1])
+        assert (np.abs(fc[inside]) <= 0.1 + 1e-12).all()   # friction-loss bound where no limit row is active
