@@ -57,6 +57,7 @@ extern "C" {
 /* quirk flags (task_cfg.flags). Default 0 reproduces the reference bit for bit in behaviour. */
 #define SO100_FLAG_FRESH_FK_ON_RESET 1u /* run kinematics in reset (the reference does not: SURVEY Q2) */
 #define SO100_FLAG_CLIP_ACTIONS 2u      /* clip actions to [-1,1] on device (the reference env does not) */
+#define SO100_FLAG_GENERIC_KERNEL 4u    /* never use the model-specialised kernel (tests: generic vs specialised) */
 
 /*
  * Model constants as they stand in the MJCF (so_arm100_camera.xml + env01.xml), nothing derived.
@@ -201,16 +202,29 @@ int so100_forward_dynamics(so100_ctx *ctx, int n, const float *qpos_dev, const f
  * needs no GPU.  It exists so that the kernel mathematics can be checked against the oracle on a CPU-only machine
  * and is how so100_create derives dof_M0 / kv / invweight0.  Row-major host arrays: qpos/qvel/ctrl [n][6],
  * M [n][21] (packed lower triangle), bias [n][6], qacc [n][6] (cold start, `sweeps` Gauss-Seidel sweeps),
- * kin [n][18] (end_pos 3, wrist 3, cam_xpos 3, cam_xmat 9).  Outputs may be NULL.
+ * kin [n][18] (end_pos 3, wrist 3, cam_xpos 3, cam_xmat 9).  Outputs may be NULL.  variant 0 = generic recursion,
+ * 1 = the generated model-specialised code (error if `model` is not the one it was generated from).
  */
 int so100_host_forward(const so100_model *model, int n, const double *qpos, const double *qvel, const double *ctrl,
-                       double *M, double *bias, double *qacc, double *kin, int sweeps);
+                       double *M, double *bias, double *qacc, double *kin, int sweeps, int variant);
+
+/*
+ * The link constants the kernels consume, as the library derives them from the MJCF numbers (fp64, host only):
+ * for each link i = 0..5: R[9] p[3] m h[3] I[6] armature (23 doubles), then the base acceleration a0[3] = 141 doubles.
+ * Frames are re-based so that every hinge turns about local +z (csrc/so100_dyn.cuh).  tools/gen_so100_dyn.py reads
+ * these to emit the model-specialised straight-line dynamics (csrc/so100_dyn_gen.cuh).
+ */
+#define SO100_N_DYN_CONSTANTS 141
+int so100_host_constants(const so100_model *model, double *out /*[141]*/);
+
+/* Which step kernel this ctx launches: 0 = generic (constants at run time), 1 = specialised to the baked so100 model. */
+int so100_kernel_variant(so100_ctx *ctx);
 
 /* Derived constants as the library computed them (host, fp64): dof_M0[6], kv[6], invweight0[6]. */
 int so100_get_derived(so100_ctx *ctx, double *dof_M0, double *kv, double *invweight0);
 
-/* Kernel launches issued by this ctx so far; env steps whose Gauss-Seidel solve had not converged to 1e-4
-   (relative) in its last sweep; envs force-reset because their state went non-finite (device counters, syncs). */
+/* Kernel launches issued by this ctx so far; env steps in which the last Gauss-Seidel sweep of some substep still
+   moved qacc by more than 2e-3 (relative; the sweep itself contracts the error ~100x further); envs force-reset because their state went non-finite (device counters, syncs). */
 int so100_get_stats(so100_ctx *ctx, int64_t *launches, int64_t *solver_fallbacks, int64_t *nan_resets);
 
 /*

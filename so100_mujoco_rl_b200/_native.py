@@ -12,14 +12,14 @@ from .model import So100Model
 from .tasks import So100TaskCfg
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libso100_b200.so")
+LIB_PATH = os.environ.get("SO100_B200_LIB") or os.path.join(PKG_DIR, "libso100_b200.so")  # override: kernel experiments only
 
 # every symbol include/so100_b200.h declares (tests/test_abi.py checks the two lists against each other)
 EXPORTS = [
     "so100_abi_version", "so100_last_error", "so100_obs_dim", "so100_act_dim", "so100_create", "so100_destroy",
     "so100_reset", "so100_step", "so100_reset_host", "so100_step_host", "so100_get_state", "so100_set_state",
     "so100_get_tick", "so100_set_tick", "so100_forward_dynamics", "so100_host_forward", "so100_get_derived",
-    "so100_get_stats", "so100_bench_fp32_peak",
+    "so100_get_stats", "so100_bench_fp32_peak", "so100_host_constants", "so100_kernel_variant",
 ]
 
 
@@ -66,7 +66,9 @@ def lib() -> ctypes.CDLL:
     L.so100_get_tick.argtypes = [vp, i64p]
     L.so100_set_tick.argtypes = [vp, ctypes.c_int64]
     L.so100_forward_dynamics.argtypes = [vp, ci] + [vp] * 7 + [vp]
-    L.so100_host_forward.argtypes = [ctypes.POINTER(So100Model), ci, dp, dp, dp, dp, dp, dp, dp, ci]
+    L.so100_host_forward.argtypes = [ctypes.POINTER(So100Model), ci, dp, dp, dp, dp, dp, dp, dp, ci, ci]
+    L.so100_host_constants.argtypes = [ctypes.POINTER(So100Model), dp]
+    L.so100_kernel_variant.argtypes = [vp]
     L.so100_get_derived.argtypes = [vp, dp, dp, dp]
     L.so100_get_stats.argtypes = [vp, i64p, i64p, i64p]
     L.so100_bench_fp32_peak.argtypes = [ci, ci, dp]

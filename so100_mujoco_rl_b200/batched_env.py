@@ -174,6 +174,10 @@ class BatchedSo100Env:
         _native.check(self._L.so100_get_derived(self._h, dp(a), dp(b), dp(c)))
         return a, b, c
 
+    @property
+    def kernel_variant(self) -> str:
+        return "specialised" if _native.check(self._L.so100_kernel_variant(self._h)) == 1 else "generic"
+
     def stats(self) -> dict:
         a, b, c = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
         _native.check(self._L.so100_get_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))

@@ -20,6 +20,8 @@
 
 #include "../../include/so100_b200.h"
 #include "so100_dyn.cuh"
+#define SO100_GEN_N SO100_N_DYN_CONSTANTS
+#include "so100_dyn_gen.cuh"  // model-specialised straight-line dynamics (tools/gen_so100_dyn.py)
 
 // ------------------------------------------------------------------------------------------------ error plumbing
 static thread_local std::string g_err;
@@ -32,7 +34,17 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 // ------------------------------------------------------------------------------------------------ device constants
-constexpr int kBlock = 64;          // threads per CTA (one env each); 7 CTAs/SM keep 65 536 envs in one wave on 148 SMs
+// Launch shape (tunable at build time for experiments; defaults are the measured best, see profiles/).
+#ifndef SO100_BLOCK
+#define SO100_BLOCK 256
+#endif
+#ifndef SO100_MINBLOCKS
+#define SO100_MINBLOCKS 2
+#endif
+#ifndef SO100_SYNC
+#define SO100_SYNC 1   // __syncthreads() per substep: keeps a CTA's warps on the same stretch of straight-line code (i-cache)
+#endif
+constexpr int kBlock = SO100_BLOCK;  // threads per CTA, one env each
 constexpr int kMaxStart = SO100_MAX_START;
 constexpr int kSnap = 12, kAux = 24, kCnt = 4;
 enum { F_EVER_STEPPED = 1, F_HAS_LAST_BLOCK = 2, F_ANGVEL_VALID = 4, F_CENTRE_VALID = 8 };
@@ -265,8 +277,8 @@ __device__ __forceinline__ float reward_reach(const TaskC& t, EnvRegs& e) {
 // 16 x mj_step on the arm.  ctrl is constant over the env step, so kp*clip(ctrl) is hoisted.
 // ctrl is carried as an unevaluated sum ctrl_hi + ctrl_lo so that Env01/02's closed loop ctrl = qpos + a*0.075 does not
 // round the 0.075-rad increment to the ulp of a 3-rad angle (that rounding random-walks qpos in a neutrally stable loop).
-template <int TASK>
-__device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs& e, const float* ctrl_hi, const float* ctrl_lo) {
+template <int TASK, bool SPEC>
+__device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs& e, const float* ctrl_hi, const float* ctrl_lo, bool live) {
   const TaskC& t = C.t;
   float cc[SO_NJ], cl[SO_NJ];
 #pragma unroll
@@ -279,17 +291,23 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
   float worst = 0.0f;
 #pragma unroll 1
   for (int sub = 0; sub < t.nsub; sub++) {
+#if SO100_SYNC
+    __syncthreads();
+#endif
     float s[SO_NJ], c[SO_NJ], bias[SO_NJ], M[21], b[SO_NJ];
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) sincosf(e.q[j], &s[j], &c[j]);
     if (sub == t.nsub - 1) take_snapshot<TASK>(C, s, c, e);  // kinematics of the LAST substep's start state (Q3)
-    dyn_bias_mass<float>(C.dyn, s, c, e.v, bias, M);
+    if (SPEC) dyn_bias_mass_so100<float>(s, c, e.v, bias, M);  // constants folded at build time (so100 MJCF)
+    else dyn_bias_mass<float>(C.dyn, s, c, e.v, bias, M);       // any other model: constants from the ctx
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {
       float f = t.kp[j] * ((cc[j] - e.q[j]) + (cl[j] + e.qc[j])) - t.kv[j] * e.v[j];  // differences first: no cancellation
       b[j] = clampf(f, t.frc_lo[j], t.frc_hi[j]) - bias[j];
     }
-    float d = solve_qacc<float, 5>(C.con, M, b, e.q, e.qc, e.v, e.w);
+    // ctrl changes once per env step: the first substep's warm start is far (5 sweeps), later ones are within a few %
+    // of the solution and every sweep contracts the error ~100x (3 sweeps)
+    float d = solve_qacc<float>(C.con, M, b, e.q, e.qc, e.v, e.w, sub == 0 ? 5 : 3);
     float amax = 1.0f;
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {
@@ -302,17 +320,19 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
     }
     worst = fmaxf(worst, d / amax);
   }
-  if (worst > 1e-4f) atomicAdd(&B.stats[0], 1ULL);
+  // the last sweep's largest update bounds the error BEFORE that sweep; the sweep itself contracts it ~100x more
+  if (worst > 2e-3f && live) atomicAdd(&B.stats[0], 1ULL);
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
-template <int TASK>
-__global__ void __launch_bounds__(kBlock, 7) step_kernel(const __grid_constant__ Consts C, const Bufs B, const StepIO io) {
+template <int TASK, bool SPEC>
+__global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __grid_constant__ Consts C, const Bufs B, const StepIO io) {
   constexpr int OD = TASK == 5 ? 8 : 15;
   __shared__ float sh[kBlock * OD];
   const TaskC& t = C.t;
-  const int n = t.n, base = blockIdx.x * kBlock, i = base + threadIdx.x;
-  const bool live = i < n;
+  const int n = t.n, base = blockIdx.x * kBlock;
+  const bool live = base + (int)threadIdx.x < n;
+  const int i = live ? base + (int)threadIdx.x : n - 1;  // tail threads shadow the last env (they must reach every barrier); nothing they compute is stored
   // coalesced load of the CTA's action rows through shared memory
   for (int k = threadIdx.x; k < kBlock * SO_NJ; k += kBlock) {
     int g = base * SO_NJ + k;
@@ -327,7 +347,7 @@ __global__ void __launch_bounds__(kBlock, 7) step_kernel(const __grid_constant__
   }
   __syncthreads();
   float obs[OD];
-  if (live) {
+  {
     EnvRegs e;
     load_env<TASK>(B, n, i, e);
     float rew, ctrl[SO_NJ], ctrl_lo[SO_NJ];
@@ -349,7 +369,7 @@ __global__ void __launch_bounds__(kBlock, 7) step_kernel(const __grid_constant__
           for (int k = 0; k < 3; k++) e.aux[k] = e.blk[k];
         }
       }
-      physics<TASK>(C, B, e, ctrl, ctrl_lo);
+      physics<TASK, SPEC>(C, B, e, ctrl, ctrl_lo, live);
       write_obs<TASK>(t, e, i, io.tick, STREAM_NOISE, obs);
     } else {  // env03_v1.py:124-201
       float time = (float)e.elapsed * t.dt_env;
@@ -380,7 +400,7 @@ __global__ void __launch_bounds__(kBlock, 7) step_kernel(const __grid_constant__
       float newcmd[SO_NJ];
 #pragma unroll
       for (int j = 0; j < SO_NJ; j++) { newcmd[j] = e.aux[j] + a[j] * t.step_scale; ctrl[j] = newcmd[j]; ctrl_lo[j] = 0.0f; }  // open loop (Q6)
-      physics<TASK>(C, B, e, ctrl, ctrl_lo);
+      physics<TASK, SPEC>(C, B, e, ctrl, ctrl_lo, live);
       write_obs<TASK>(t, e, i, io.tick, STREAM_NOISE, obs);
       if (obs[6] == -1.0f && obs[7] == -1.0f) {  // :152-164
         if (e.miss > t.lost_limit) term = true;
@@ -410,24 +430,26 @@ __global__ void __launch_bounds__(kBlock, 7) step_kernel(const __grid_constant__
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) chk += e.q[j] + e.v[j];
     bool bad = !isfinite(chk);
-    if (bad) atomicAdd(&B.stats[1], 1ULL);
+    if (bad && live) atomicAdd(&B.stats[1], 1ULL);
     e.elapsed += 1;
     e.ep_ret += rew;
     bool trunc = e.elapsed >= t.max_steps;  // gymnasium TimeLimit
-    io.reward[i] = rew;
-    io.terminated[i] = term ? 1 : 0;
-    io.truncated[i] = (trunc && !term) ? 1 : 0;
+    if (live) {
+      io.reward[i] = rew;
+      io.terminated[i] = term ? 1 : 0;
+      io.truncated[i] = (trunc && !term) ? 1 : 0;
+    }
     if (term || trunc || bad) {
-      if (io.terminal_obs) {
+      if (live && io.terminal_obs) {
 #pragma unroll
         for (int k = 0; k < OD; k++) io.terminal_obs[(size_t)i * OD + k] = obs[k];
       }
-      if (io.ep_return_out) io.ep_return_out[i] = e.ep_ret;
-      if (io.ep_len_out) io.ep_len_out[i] = e.elapsed;
-      if (bad) io.truncated[i] = term ? 0 : 1;
+      if (live && io.ep_return_out) io.ep_return_out[i] = e.ep_ret;
+      if (live && io.ep_len_out) io.ep_len_out[i] = e.elapsed;
+      if (live && bad) io.truncated[i] = term ? 0 : 1;
       reset_env<TASK>(C, B, e, i, io.tick, STREAM_RESET, obs);
     }
-    store_env<TASK>(B, n, i, e);
+    if (live) store_env<TASK>(B, n, i, e);
 #pragma unroll
     for (int k = 0; k < OD; k++) sh[threadIdx.x * OD + k] = obs[k];
   }
@@ -468,7 +490,7 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const __grid_constant__
     b[j] = clampf(f, t.frc_lo[j], t.frc_hi[j]) - bias[j];
   }
   float zc[SO_NJ] = {0, 0, 0, 0, 0, 0};
-  solve_qacc<float, 12>(C.con, M, b, q, zc, v, a);
+  solve_qacc<float>(C.con, M, b, q, zc, v, a, 12);
   if (M_out)
 #pragma unroll
     for (int k = 0; k < 21; k++) M_out[k * n + i] = M[k];
@@ -679,6 +701,20 @@ int build_host_model(const so100_model& m, HostModel& H) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ ctx
+static void flatten_dyn(const DynC<double>& D, double* out) {
+  int k = 0;
+  for (int i = 0; i < SO_NJ; i++) {
+    const LinkC<double>& L = D.L[i];
+    for (int a = 0; a < 9; a++) out[k++] = L.R[a];
+    for (int a = 0; a < 3; a++) out[k++] = L.p[a];
+    out[k++] = L.m;
+    for (int a = 0; a < 3; a++) out[k++] = L.h[a];
+    for (int a = 0; a < 6; a++) out[k++] = L.I[a];
+    out[k++] = L.arm;
+  }
+  for (int a = 0; a < 3; a++) out[k++] = D.a0[a];
+}
+
 struct so100_ctx {
   int device = 0, n = 0, task = 0, obs_dim = 0;
   Consts C;
@@ -686,6 +722,7 @@ struct so100_ctx {
   Bufs B{};
   float* start_tab = nullptr;
   int64_t tick = 0, launches = 0;
+  bool specialised = false;  // model == the constants baked into so100_dyn_gen.cuh
   // staging for the *_host entry points
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_tobs = nullptr, *h_epr = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
@@ -731,6 +768,11 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
   c->device = device; c->n = cfg->num_envs; c->task = cfg->task; c->obs_dim = so100_obs_dim(cfg->task);
   int rc = build_host_model(*m, c->H);
   if (rc != SO100_OK) { delete c; return rc; }
+  {
+    double flat[SO100_N_DYN_CONSTANTS];
+    flatten_dyn(c->H.dyn, flat);
+    c->specialised = memcmp(flat, kGenDynConstants, sizeof flat) == 0 && !(cfg->flags & SO100_FLAG_GENERIC_KERNEL);
+  }
   // fp64 -> fp32 constants
   Consts& C = c->C;
   memset(&C, 0, sizeof C);
@@ -813,10 +855,19 @@ int so100_step(so100_ctx* c, const float* actions_dev, float* obs_dev, float* re
   cudaStream_t st = (cudaStream_t)stream;
   c->tick += 1;
   StepIO io{actions_dev, obs_dev, reward_dev, terminal_obs_dev, ep_return_dev, terminated_dev, truncated_dev, ep_len_dev, (unsigned)c->tick};
-  switch (c->task) {
-    case 1: step_kernel<1><<<grid_for(c->n), kBlock, 0, st>>>(c->C, c->B, io); break;
-    case 2: step_kernel<2><<<grid_for(c->n), kBlock, 0, st>>>(c->C, c->B, io); break;
-    default: step_kernel<5><<<grid_for(c->n), kBlock, 0, st>>>(c->C, c->B, io); break;
+  const int g = grid_for(c->n);
+  if (c->specialised) {
+    switch (c->task) {
+      case 1: step_kernel<1, true><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
+      case 2: step_kernel<2, true><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
+      default: step_kernel<5, true><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
+    }
+  } else {
+    switch (c->task) {
+      case 1: step_kernel<1, false><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
+      case 2: step_kernel<2, false><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
+      default: step_kernel<5, false><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
+    }
   }
   c->launches++;
   CU(cudaGetLastError());
@@ -913,25 +964,41 @@ int so100_forward_dynamics(so100_ctx* c, int n, const float* qpos_dev, const flo
   return SO100_OK;
 }
 
+int so100_host_constants(const so100_model* m, double* out) {
+  if (!m || !out) return fail(SO100_ERR_ARG, "null argument");
+  if (m->struct_size != (int)sizeof(so100_model)) return fail(SO100_ERR_ARG, "so100_model.struct_size mismatch");
+  HostModel H;
+  int rc = build_host_model(*m, H);
+  if (rc) return rc;
+  flatten_dyn(H.dyn, out);
+  return SO100_OK;
+}
+
 int so100_host_forward(const so100_model* m, int n, const double* qpos, const double* qvel, const double* ctrl, double* M_out,
-                       double* bias_out, double* qacc_out, double* kin_out, int sweeps) {
+                       double* bias_out, double* qacc_out, double* kin_out, int sweeps, int variant) {
   if (!m || n <= 0 || !qpos || !qvel || !ctrl) return fail(SO100_ERR_ARG, "bad argument");
   if (m->struct_size != (int)sizeof(so100_model)) return fail(SO100_ERR_ARG, "so100_model.struct_size mismatch");
   HostModel H;
   int rc = build_host_model(*m, H);
   if (rc) return rc;
+  if (variant == 1) {
+    double flat[SO100_N_DYN_CONSTANTS];
+    flatten_dyn(H.dyn, flat);
+    if (memcmp(flat, kGenDynConstants, sizeof flat) != 0) return fail(SO100_ERR_MODEL, "model differs from the constants baked into so100_dyn_gen.cuh");
+  } else if (variant != 0) return fail(SO100_ERR_ARG, "variant must be 0 (generic) or 1 (specialised)");
   for (int i = 0; i < n; i++) {
     const double *q = qpos + 6 * i, *v = qvel + 6 * i, *u = ctrl + 6 * i;
     double s[SO_NJ], c[SO_NJ], bias[SO_NJ], M[21], b[SO_NJ], a[SO_NJ] = {0};
     for (int j = 0; j < SO_NJ; j++) { s[j] = std::sin(q[j]); c[j] = std::cos(q[j]); }
-    dyn_bias_mass<double>(H.dyn, s, c, v, bias, M);
+    if (variant == 1) dyn_bias_mass_so100<double>(s, c, v, bias, M);
+    else dyn_bias_mass<double>(H.dyn, s, c, v, bias, M);
     for (int j = 0; j < SO_NJ; j++) {
       double cc = std::fmin(std::fmax(u[j], m->act_ctrlrange[j][0]), m->act_ctrlrange[j][1]);
       double f = m->act_kp[j] * cc - m->act_kp[j] * q[j] - H.kv[j] * v[j];
       b[j] = std::fmin(std::fmax(f, m->act_forcerange[j][0]), m->act_forcerange[j][1]) - bias[j];
     }
     const double zc[SO_NJ] = {0, 0, 0, 0, 0, 0};
-    for (int k = 0; k < (sweeps > 0 ? sweeps : 1); k++) solve_qacc<double, 1>(H.con, M, b, q, zc, v, a);
+    solve_qacc<double>(H.con, M, b, q, zc, v, a, sweeps > 0 ? sweeps : 1);
     if (M_out) memcpy(M_out + 21 * i, M, sizeof M);
     if (bias_out) memcpy(bias_out + 6 * i, bias, sizeof bias);
     if (qacc_out) memcpy(qacc_out + 6 * i, a, sizeof a);
@@ -953,6 +1020,11 @@ int so100_get_derived(so100_ctx* c, double* dof_M0, double* kv, double* invweigh
     if (invweight0) invweight0[j] = c->H.invw[j];
   }
   return SO100_OK;
+}
+
+int so100_kernel_variant(so100_ctx* c) {
+  if (!c) return fail(SO100_ERR_ARG, "null argument");
+  return c->specialised ? 1 : 0;
 }
 
 int so100_get_stats(so100_ctx* c, int64_t* launches, int64_t* solver_fallbacks, int64_t* nan_resets) {

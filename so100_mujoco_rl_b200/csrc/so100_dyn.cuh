@@ -22,6 +22,11 @@
 
 #define SO_NJ 6
 
+SO_HD float so_fma(float a, float b, float c) { return fmaf(a, b, c); }
+SO_HD double so_fma(double a, double b, double c) { return a * b + c; }
+template <typename T>
+SO_HD T so_fma(T a, T b, T c) { return a * b + c; }
+
 template <typename T>
 struct LinkC {
   T R[9];  // parent <- child constant rotation (row-major), before the joint rotation
@@ -228,14 +233,60 @@ SO_HD T impedance(const ConC<T>& K, int j, T dist) {  // MuJoCo getimpedance wit
   return K.imp0[j] + y * (K.imp1[j] - K.imp0[j]);
 }
 
-// Exact minimiser over x of  m x^2/2 - c x + huber_f(x - af)   (friction-loss row only), closed form:
-//   t = c - m af;  F = clamp(t * D/(m+D), -loss, loss);  x = af + (t - F)/m
+#ifdef __CUDACC__
+#define SO_NOINLINE __host__ __device__ __noinline__
+#else
+#define SO_NOINLINE
+#endif
+SO_HD float so_clamp(float x, float lo, float hi) {
+#ifdef __CUDA_ARCH__
+  return fminf(fmaxf(x, lo), hi);
+#else
+  return x < lo ? lo : (x > hi ? hi : x);
+#endif
+}
+SO_HD double so_clamp(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 template <typename T>
-SO_HD T solve1(T m, T c, T af, T D, T loss) {
+SO_HD T so_clamp(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+// 1/x for the solver's preconditioners (1/M_jj, 1/(M_jj + D)): MUFU.RCP, <= 1 ulp.  A relative error eps here moves the
+// Gauss-Seidel fixed point by eps relative, i.e. by the same amount as one fp32 rounding of the result.
+SO_HD float so_rcp(float x) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+template <typename T>
+SO_HD T so_rcp(T x) { return T(1) / x; }
+
+// Exact minimiser over x of  m x^2/2 - c x + huber_f(x - af)   (friction-loss row only), closed form:
+//   t = c - m af;  F = clamp(t * D/(m+D), -loss, loss);  x = af + (t - F)/m          (rm = 1/m, kap = D/(m+D))
+template <typename T>
+SO_HD T solve1(T m, T rm, T kap, T c, T af, T loss) {
   T t = c - m * af;
-  T F = t * (D / (m + D));
-  F = F > loss ? loss : (F < -loss ? -loss : F);
-  return af + (t - F) / m;
+  T F = so_clamp(t * kap, -loss, loss);
+  return af + (t - F) * rm;
+}
+
+// Joint j is outside its range: one unilateral limit row (MuJoCo mj_instantiateLimit) joins the friction row on this
+// dof.  Evaluated ONCE per substep; the sweeps only see (xl, sDl, rm2, kap2).  With random actions the arm sits on
+// its limits often (several start poses are on them), so this is not a cold path.
+template <typename T>
+SO_HD void limit_row(const ConC<T>& K, int j, T m, T q, T qc, T qd, T& xl, T& sDl, T& rm2, T& kap2) {
+  T dlo = (q - K.lo[j]) - qc, dhi = (K.hi[j] - q) + qc;  // true qpos = q - qc (compensated sum)
+  T side = dlo < T(0) ? T(1) : T(-1), dist = dlo < T(0) ? dlo : dhi;
+  T imp = impedance(K, j, dist);
+  T R = (T(1) - imp) * K.invw[j] * so_rcp(imp);
+  R = R < T(1e-15) ? T(1e-15) : R;
+  T Dl = so_rcp(R);
+  xl = side * (-K.lim_B[j] * (side * qd) - K.lim_K[j] * imp * dist);  // row active while side*(x - xl) < 0
+  sDl = side * Dl;
+  T m2 = m + Dl;
+  rm2 = so_rcp(m2);
+  kap2 = K.fr_D[j] * so_rcp(m2 + K.fr_D[j]);
 }
 
 // Projected Gauss-Seidel on   min_a  a^T M a / 2 - b^T a + sum_j [ friction_j(a_j) + limit_j(a_j) ]:
@@ -243,35 +294,44 @@ SO_HD T solve1(T m, T c, T af, T D, T loss) {
 // (cond < 1.3) => contraction ~1e-2 per sweep (measured against the fp64 Newton oracle).
 // a[] holds the warm start on entry and the solution on exit; returns the largest update of the LAST sweep.
 // qc[] is the compensation term of the fp32 position integration (zeros when T = double).
-template <typename T, int SWEEPS>
-SO_HD T solve_qacc(const ConC<T>& K, const T* M, const T* b, const T* q, const T* qc, const T* qd, T* a) {
-  T af[SO_NJ], xl[SO_NJ], Dl[SO_NJ], sg[SO_NJ];
+template <typename T>
+SO_HD T solve_qacc(const ConC<T>& K, const T* M, const T* b, const T* q, const T* qc, const T* qd, T* a, int sweeps) {
+  T af[SO_NJ], rm[SO_NJ], kap[SO_NJ], xl[SO_NJ], sDl[SO_NJ], rm2[SO_NJ], kap2[SO_NJ];
 #pragma unroll
   for (int j = 0; j < SO_NJ; j++) {
+    T m = M[midx(j, j)];
     af[j] = -K.fr_B[j] * qd[j];
-    sg[j] = T(0); xl[j] = T(0); Dl[j] = T(0);
-    T dlo = (q[j] - K.lo[j]) - qc[j], dhi = (K.hi[j] - q[j]) + qc[j];  // true qpos = q - qc (compensated sum)
-    if (dlo < T(0) || dhi < T(0)) {  // rare: joint outside its range -> one unilateral row
-      T side = dlo < T(0) ? T(1) : T(-1), dist = dlo < T(0) ? dlo : dhi;
-      T imp = impedance(K, j, dist);
-      T R = (T(1) - imp) / imp * K.invw[j];
-      R = R < T(1e-15) ? T(1e-15) : R;
-      T aref = -K.lim_B[j] * (side * qd[j]) - K.lim_K[j] * imp * dist;
-      sg[j] = side; Dl[j] = T(1) / R; xl[j] = side * aref;  // row active while side*(x - xl) < 0
-    }
+    rm[j] = so_rcp(m);
+    kap[j] = K.fr_D[j] * so_rcp(m + K.fr_D[j]);
+    xl[j] = T(0); sDl[j] = T(0); rm2[j] = T(0); kap2[j] = T(0);
+    if ((q[j] - K.lo[j]) - qc[j] < T(0) || (K.hi[j] - q[j]) + qc[j] < T(0))
+      limit_row(K, j, m, q[j], qc[j], qd[j], xl[j], sDl[j], rm2[j], kap2[j]);
   }
   T last = T(0);
-#pragma unroll
-  for (int sw = 0; sw < SWEEPS; sw++) {
+#pragma unroll 1
+  for (int sw = 0; sw < sweeps; sw++) {
+    last = T(0);
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {
-      T m = M[midx(j, j)], cc = b[j];
+      // c_j = b_j - sum_{k != j} M_jk a_k, as two independent chains
+      T m = M[midx(j, j)], c0 = b[j], c1 = T(0);
 #pragma unroll
-      for (int k = 0; k < SO_NJ; k++)
-        if (k != j) cc -= (k < j ? M[midx(j, k)] : M[midx(k, j)]) * a[k];
-      T x = solve1(m, cc, af[j], K.fr_D[j], K.fr_loss[j]);
-      if (sg[j] != T(0) && sg[j] * (x - xl[j]) < T(0)) x = solve1(m + Dl[j], cc + Dl[j] * xl[j], af[j], K.fr_D[j], K.fr_loss[j]);
-      if (sw == SWEEPS - 1) { T d = x - a[j]; d = d < 0 ? -d : d; last = d > last ? d : last; }
+      for (int k = 0; k < SO_NJ; k++) {
+        if (k == j) continue;
+        T mjk = k < j ? M[midx(j, k)] : M[midx(k, j)];
+        if (k & 1) c1 -= mjk * a[k];
+        else c0 -= mjk * a[k];
+      }
+      T cc = c0 + c1;
+      T x = solve1(m, rm[j], kap[j], cc, af[j], K.fr_loss[j]);
+      if (sDl[j] != T(0)) {  // limit row present: active iff the limit-free minimiser violates it
+        T Dl = sDl[j] < T(0) ? -sDl[j] : sDl[j];
+        T x2 = solve1(m + Dl, rm2[j], kap2[j], cc + Dl * xl[j], af[j], K.fr_loss[j]);
+        x = sDl[j] * (x - xl[j]) < T(0) ? x2 : x;
+      }
+      T d = x - a[j];
+      d = d < T(0) ? -d : d;
+      last = d > last ? d : last;
       a[j] = x;
     }
   }

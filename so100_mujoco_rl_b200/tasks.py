@@ -14,6 +14,7 @@ MAX_START = 64
 TASK_ENV01, TASK_ENV02, TASK_ENV05 = 1, 2, 5
 FLAG_FRESH_FK_ON_RESET = 1
 FLAG_CLIP_ACTIONS = 2
+FLAG_GENERIC_KERNEL = 4
 
 JOINT_STEP_SCALE = 0.075  # envs/utils.py:9
 REST_POSITION = [0.0, -3.141, 3.117, 1.0, 0.0, 0.0]  # envs/utils.py:11

@@ -23,7 +23,7 @@ def test_host_forward_matches_oracle(native_lib, spec):
     v = rng.normal(0, 1.5, (n, 6))
     u = q + rng.uniform(-1, 1, (n, 6)) * 0.3
     M, b, a, k = np.zeros((n, 21)), np.zeros((n, 6)), np.zeros((n, 6)), np.zeros((n, 18))
-    _native.check(native_lib.so100_host_forward(ctypes.byref(m), n, _dp(q), _dp(v), _dp(u), _dp(M), _dp(b), _dp(a), _dp(k), 12))
+    _native.check(native_lib.so100_host_forward(ctypes.byref(m), n, _dp(q), _dp(v), _dp(u), _dp(M), _dp(b), _dp(a), _dp(k), 12, 0))
     for i in range(n):
         Mo = o.mass_matrix(q[i])
         assert np.abs(np.array([Mo[r, c] for r in range(6) for c in range(r + 1)]) - M[i]).max() < 1e-14
@@ -46,6 +46,43 @@ def test_gauss_seidel_contraction(native_lib, spec):
     errs = {}
     for sweeps in (2, 5):
         a = np.zeros((n, 6))
-        _native.check(native_lib.so100_host_forward(ctypes.byref(m), n, _dp(q), _dp(v), _dp(u), None, None, _dp(a), None, sweeps))
+        _native.check(native_lib.so100_host_forward(ctypes.byref(m), n, _dp(q), _dp(v), _dp(u), None, None, _dp(a), None, sweeps, 0))
         errs[sweeps] = max(np.abs(o.forward(q[i], v[i], u[i])[0] - a[i]).max() / (1 + np.abs(a[i]).max()) for i in range(n))
     assert errs[5] < 1e-7 and errs[5] < errs[2] * 1e-3
+
+
+def test_specialised_dynamics_match_oracle(native_lib, spec):
+    """The generated, model-specialised straight-line code (csrc/so100_dyn_gen.cuh) in fp64 against the oracle.
+    Its constants are the fp32-rounded ones the kernels use, so agreement is to fp32 rounding of the constants."""
+    from so100_mujoco_rl_b200 import _native
+    m = spec.to_ctypes()
+    o = make_oracle(1, 1)
+    rng = np.random.default_rng(7)
+    n = 200
+    lo, hi = spec.jnt_range[:, 0], spec.jnt_range[:, 1]
+    q = rng.uniform(lo, hi, (n, 6)); v = rng.normal(0, 1.5, (n, 6)); u = q.copy()
+    Mg, bg, Ms, bs = np.zeros((n, 21)), np.zeros((n, 6)), np.zeros((n, 21)), np.zeros((n, 6))
+    _native.check(native_lib.so100_host_forward(ctypes.byref(m), n, _dp(q), _dp(v), _dp(u), _dp(Mg), _dp(bg), None, None, 1, 0))
+    _native.check(native_lib.so100_host_forward(ctypes.byref(m), n, _dp(q), _dp(v), _dp(u), _dp(Ms), _dp(bs), None, None, 1, 1))
+    assert np.abs(Ms - Mg).max() < 2e-8      # M entries ~0.1: relative 2e-7 = fp32 rounding of the baked constants
+    assert np.abs(bs - bg).max() < 5e-7      # bias ~1 N m
+    for i in range(0, n, 10):
+        assert np.abs(o.bias(q[i], v[i]) - bs[i]).max() < 5e-7
+
+
+def test_specialised_variant_rejects_other_models(native_lib, spec):
+    import copy
+    from so100_mujoco_rl_b200 import _native
+    s2 = copy.deepcopy(spec)
+    s2.body_mass = s2.body_mass * 1.01
+    m = s2.to_ctypes()
+    q = np.zeros((1, 6)); M = np.zeros((1, 21))
+    assert native_lib.so100_host_forward(ctypes.byref(m), 1, _dp(q), _dp(q), _dp(q), _dp(M), None, None, None, 1, 1) == -3
+    assert native_lib.so100_host_forward(ctypes.byref(m), 1, _dp(q), _dp(q), _dp(q), _dp(M), None, None, None, 1, 0) == 0
+
+
+def test_generated_header_is_current():
+    import subprocess, sys, os
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_so100_dyn.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr

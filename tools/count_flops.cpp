@@ -53,7 +53,7 @@ int main() {
   C::n = 0;
   C zc[6]; for (int j = 0; j < 6; j++) zc[j] = 0;
   C::n = 0;
-  solve_qacc<C, 5>(K, M, b, q, zc, qd, a);
+  solve_qacc<C>(K, M, b, q, zc, qd, a, 5);
   long solve = C::n;
   C::n = 0;
   for (int j = 0; j < 6; j++) { qd[j] += C(0.002) * a[j]; q[j] += C(0.002) * qd[j]; }
