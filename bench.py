@@ -215,7 +215,9 @@ def main():
         barrier()
         e2e_s = time.perf_counter() - t0
         od = OBS_DIM[task]
-        e2e = {"seconds": e2e_s, "h2d": n * 6 * 4, "d2h": n * (2 * od * 4 + 4 + 1 + 1 + 4 + 4)}
+        # obs + reward + terminated + truncated + the 4-byte any-done flag; terminal_obs / ep_return / ep_len (another
+        # n*(od*4+8) bytes) cross only on steps where some episode ended (none inside this window: 4000-step episodes)
+        e2e = {"seconds": e2e_s, "h2d": n * 6 * 4, "d2h": n * (od * 4 + 4 + 1 + 1) + 4}
 
     # max over ranks
     if world > 1:

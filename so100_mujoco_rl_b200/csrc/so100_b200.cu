@@ -83,6 +83,8 @@ struct StepIO {
   uint8_t *terminated, *truncated;
   int* ep_len_out;
   unsigned tick;
+  int env_lo, env_hi;   // this launch covers envs [env_lo, env_hi) (the host path pipelines chunks)
+  int* any_done;        // optional: set to 1 if any env of the launch finished an episode
 };
 
 // ------------------------------------------------------------------------------------------------ device helpers
@@ -330,13 +332,13 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
   constexpr int OD = TASK == 5 ? 8 : 15;
   __shared__ float sh[kBlock * OD];
   const TaskC& t = C.t;
-  const int n = t.n, base = blockIdx.x * kBlock;
-  const bool live = base + (int)threadIdx.x < n;
-  const int i = live ? base + (int)threadIdx.x : n - 1;  // tail threads shadow the last env (they must reach every barrier); nothing they compute is stored
+  const int n = t.n, base = io.env_lo + blockIdx.x * kBlock, hi = io.env_hi;
+  const bool live = base + (int)threadIdx.x < hi;
+  const int i = live ? base + (int)threadIdx.x : hi - 1;  // tail threads shadow the last env (they must reach every barrier); nothing they compute is stored
   // coalesced load of the CTA's action rows through shared memory
   for (int k = threadIdx.x; k < kBlock * SO_NJ; k += kBlock) {
     int g = base * SO_NJ + k;
-    sh[k] = g < n * SO_NJ ? io.actions[g] : 0.0f;
+    sh[k] = g < hi * SO_NJ ? io.actions[g] : 0.0f;
   }
   __syncthreads();
   float a[SO_NJ];
@@ -447,6 +449,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
       if (live && io.ep_return_out) io.ep_return_out[i] = e.ep_ret;
       if (live && io.ep_len_out) io.ep_len_out[i] = e.elapsed;
       if (live && bad) io.truncated[i] = term ? 0 : 1;
+      if (live && io.any_done) *io.any_done = 1;
       reset_env<TASK>(C, B, e, i, io.tick, STREAM_RESET, obs);
     }
     if (live) store_env<TASK>(B, n, i, e);
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
   __syncthreads();
   for (int k = threadIdx.x; k < kBlock * OD; k += kBlock) {
     size_t g = (size_t)base * OD + k;
-    if (g < (size_t)n * OD) io.obs[g] = sh[k];
+    if (g < (size_t)hi * OD) io.obs[g] = sh[k];
   }
 }
 
@@ -727,6 +730,11 @@ struct so100_ctx {
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_tobs = nullptr, *h_epr = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
   int* h_epl = nullptr;
+  // host path pipeline: chunks of envs on helper streams so that H2D, kernel and D2H overlap
+  static constexpr int kMaxChunks = 4;
+  cudaStream_t hs[kMaxChunks] = {};
+  cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {};
+  int *d_any_done = nullptr, *p_any_done = nullptr;  // device flag + pinned host copy
 };
 
 static void free_ctx(so100_ctx* c) {
@@ -735,6 +743,13 @@ static void free_ctx(so100_ctx* c) {
   void* ptrs[] = {c->B.qpos, c->B.qvel, c->B.warm, c->B.qcomp, c->B.block, c->B.snap, c->B.aux, c->B.ep_return, c->B.cnt, c->B.stats,
                   c->start_tab, c->h_act, c->h_obs, c->h_rew, c->h_tobs, c->h_epr, c->h_term, c->h_trunc, c->h_epl};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (c->d_any_done) cudaFree(c->d_any_done);
+  if (c->p_any_done) cudaFreeHost(c->p_any_done);
+  for (int k = 0; k < so100_ctx::kMaxChunks; k++) {
+    if (c->hs[k]) cudaStreamDestroy(c->hs[k]);
+    if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
+  }
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
   delete c;
 }
 
@@ -848,14 +863,8 @@ int so100_reset(so100_ctx* c, const uint8_t* mask_dev, float* obs_dev, void* str
   return SO100_OK;
 }
 
-int so100_step(so100_ctx* c, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* terminated_dev,
-               uint8_t* truncated_dev, float* terminal_obs_dev, float* ep_return_dev, int32_t* ep_len_dev, void* stream) {
-  if (!c || !actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail(SO100_ERR_ARG, "null argument");
-  CU(cudaSetDevice(c->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  c->tick += 1;
-  StepIO io{actions_dev, obs_dev, reward_dev, terminal_obs_dev, ep_return_dev, terminated_dev, truncated_dev, ep_len_dev, (unsigned)c->tick};
-  const int g = grid_for(c->n);
+static int launch_step(so100_ctx* c, const StepIO& io, cudaStream_t st) {
+  const int g = grid_for(io.env_hi - io.env_lo);
   if (c->specialised) {
     switch (c->task) {
       case 1: step_kernel<1, true><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
@@ -874,6 +883,16 @@ int so100_step(so100_ctx* c, const float* actions_dev, float* obs_dev, float* re
   return SO100_OK;
 }
 
+int so100_step(so100_ctx* c, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* terminated_dev,
+               uint8_t* truncated_dev, float* terminal_obs_dev, float* ep_return_dev, int32_t* ep_len_dev, void* stream) {
+  if (!c || !actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail(SO100_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  c->tick += 1;
+  StepIO io{actions_dev, obs_dev, reward_dev, terminal_obs_dev, ep_return_dev, terminated_dev, truncated_dev, ep_len_dev, (unsigned)c->tick, 0, c->n, nullptr};
+  return launch_step(c, io, st);
+}
+
 static int ensure_staging(so100_ctx* c) {
   if (c->h_act) return SO100_OK;
   size_t n = (size_t)c->n, od = (size_t)c->obs_dim;
@@ -885,6 +904,13 @@ static int ensure_staging(so100_ctx* c) {
   CU(cudaMalloc((void**)&c->h_epl, n * 4));
   CU(cudaMalloc((void**)&c->h_term, n));
   CU(cudaMalloc((void**)&c->h_trunc, n));
+  CU(cudaMalloc((void**)&c->d_any_done, sizeof(int)));
+  CU(cudaMallocHost((void**)&c->p_any_done, sizeof(int)));
+  for (int k = 0; k < so100_ctx::kMaxChunks; k++) {
+    CU(cudaStreamCreateWithFlags(&c->hs[k], cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+  }
+  CU(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
   return SO100_OK;
 }
 
@@ -908,19 +934,41 @@ int so100_step_host(so100_ctx* c, const float* actions_host, float* obs_host, fl
   int rc = ensure_staging(c);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  size_t n = (size_t)c->n, od = (size_t)c->obs_dim;
-  CU(cudaMemcpyAsync(c->h_act, actions_host, n * SO_NJ * 4, cudaMemcpyHostToDevice, st));
-  rc = so100_step(c, c->h_act, c->h_obs, c->h_rew, c->h_term, c->h_trunc, terminal_obs_host ? c->h_tobs : nullptr,
-                  ep_return_host ? c->h_epr : nullptr, ep_len_host ? c->h_epl : nullptr, stream);
-  if (rc) return rc;
-  CU(cudaMemcpyAsync(obs_host, c->h_obs, n * od * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(reward_host, c->h_rew, n * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(terminated_host, c->h_term, n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(truncated_host, c->h_trunc, n, cudaMemcpyDeviceToHost, st));
-  if (terminal_obs_host) CU(cudaMemcpyAsync(terminal_obs_host, c->h_tobs, n * od * 4, cudaMemcpyDeviceToHost, st));
-  if (ep_return_host) CU(cudaMemcpyAsync(ep_return_host, c->h_epr, n * 4, cudaMemcpyDeviceToHost, st));
-  if (ep_len_host) CU(cudaMemcpyAsync(ep_len_host, c->h_epl, n * 4, cudaMemcpyDeviceToHost, st));
+  const size_t od = (size_t)c->obs_dim;
+  const bool want_term = terminal_obs_host || ep_return_host || ep_len_host;
+  // chunks are multiples of the CTA size; small batches are not worth splitting
+  int nchunk = c->n >= 4 * 4096 ? so100_ctx::kMaxChunks : 1;
+  int per = ((c->n + nchunk - 1) / nchunk + kBlock - 1) / kBlock * kBlock;
+  c->tick += 1;
+  CU(cudaMemsetAsync(c->d_any_done, 0, sizeof(int), st));
+  CU(cudaEventRecord(c->ev_start, st));
+  for (int k = 0; k < nchunk; k++) {
+    int lo = k * per, hi = lo + per < c->n ? lo + per : c->n;
+    if (lo >= hi) { nchunk = k; break; }
+    cudaStream_t hs = c->hs[k];
+    size_t cnt = (size_t)(hi - lo);
+    CU(cudaStreamWaitEvent(hs, c->ev_start, 0));
+    CU(cudaMemcpyAsync(c->h_act + (size_t)lo * SO_NJ, actions_host + (size_t)lo * SO_NJ, cnt * SO_NJ * 4, cudaMemcpyHostToDevice, hs));
+    StepIO io{c->h_act, c->h_obs, c->h_rew, want_term ? c->h_tobs : nullptr, want_term ? c->h_epr : nullptr, c->h_term, c->h_trunc,
+              want_term ? c->h_epl : nullptr, (unsigned)c->tick, lo, hi, c->d_any_done};
+    rc = launch_step(c, io, hs);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(obs_host + (size_t)lo * od, c->h_obs + (size_t)lo * od, cnt * od * 4, cudaMemcpyDeviceToHost, hs));
+    CU(cudaMemcpyAsync(reward_host + lo, c->h_rew + lo, cnt * 4, cudaMemcpyDeviceToHost, hs));
+    CU(cudaMemcpyAsync(terminated_host + lo, c->h_term + lo, cnt, cudaMemcpyDeviceToHost, hs));
+    CU(cudaMemcpyAsync(truncated_host + lo, c->h_trunc + lo, cnt, cudaMemcpyDeviceToHost, hs));
+    CU(cudaEventRecord(c->ev_done[k], hs));
+  }
+  for (int k = 0; k < nchunk; k++) CU(cudaStreamWaitEvent(st, c->ev_done[k], 0));
+  CU(cudaMemcpyAsync(c->p_any_done, c->d_any_done, sizeof(int), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if (want_term && *c->p_any_done) {  // the terminal rows are only meaningful for envs that finished: copy them only then
+    size_t n = (size_t)c->n;
+    if (terminal_obs_host) CU(cudaMemcpyAsync(terminal_obs_host, c->h_tobs, n * od * 4, cudaMemcpyDeviceToHost, st));
+    if (ep_return_host) CU(cudaMemcpyAsync(ep_return_host, c->h_epr, n * 4, cudaMemcpyDeviceToHost, st));
+    if (ep_len_host) CU(cudaMemcpyAsync(ep_len_host, c->h_epl, n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
   return SO100_OK;
 }
 

@@ -307,9 +307,14 @@ SO_HD T solve_qacc(const ConC<T>& K, const T* M, const T* b, const T* q, const T
     if ((q[j] - K.lo[j]) - qc[j] < T(0) || (K.hi[j] - q[j]) + qc[j] < T(0))
       limit_row(K, j, m, q[j], qc[j], qd[j], xl[j], sDl[j], rm2[j], kap2[j]);
   }
-  T last = T(0);
+  T last = T(0), amax = T(1);
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) { T ax = a[j] < T(0) ? -a[j] : a[j]; amax = ax > amax ? ax : amax; }
+  const T tol = T(1e-3) * amax;  // scale from the warm start
 #pragma unroll 1
-  for (int sw = 0; sw < sweeps; sw++) {
+  for (int sw = 0; sw < sweeps + 6; sw++) {
+    // fixed schedule, then (rare, per-lane) extra sweeps while the last one still moved qacc by > 1e-3 relative
+    if (sw >= sweeps && !(last > tol)) break;
     last = T(0);
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {
