@@ -35,7 +35,8 @@ def test_host_forward_matches_oracle(native_lib, spec):
 
 
 def test_gauss_seidel_contraction(native_lib, spec):
-    """5 sweeps from a cold start are already within fp32 resolution of the exact minimiser."""
+    """5 sweeps from a cold start are within fp32 resolution of the exact minimiser; with fewer scheduled sweeps the
+    solver keeps sweeping (per env) while the last sweep still moved qacc by more than 1e-3 relative."""
     from so100_mujoco_rl_b200 import _native
     m = spec.to_ctypes()
     o = make_oracle(1, 1)
@@ -48,7 +49,7 @@ def test_gauss_seidel_contraction(native_lib, spec):
         a = np.zeros((n, 6))
         _native.check(native_lib.so100_host_forward(ctypes.byref(m), n, _dp(q), _dp(v), _dp(u), None, None, _dp(a), None, sweeps, 0))
         errs[sweeps] = max(np.abs(o.forward(q[i], v[i], u[i])[0] - a[i]).max() / (1 + np.abs(a[i]).max()) for i in range(n))
-    assert errs[5] < 1e-7 and errs[5] < errs[2] * 1e-3
+    assert errs[5] < 1e-7 and errs[5] < errs[2] and errs[2] < 1e-5
 
 
 def test_specialised_dynamics_match_oracle(native_lib, spec):
