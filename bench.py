@@ -137,7 +137,17 @@ def run_reference(args, rank: int):
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line: dict):
+    """The contract is ONE JSON line on stdout; everything else (NCCL banner, torchrun notices) goes to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# libraries (NCCL prints its version banner) write to fd 1: keep the real stdout aside and point fd 1 at stderr
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -269,7 +279,7 @@ def main():
             rate, k, dt = cpu_oracle_rate(task, ncpu, 12.0, threads)
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
                                     "sample": f"{ncpu} envs x {k} steps ({dt:.1f} s) of the same workload on the fp64 C oracle"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

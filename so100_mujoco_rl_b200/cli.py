@@ -1,0 +1,111 @@
+"""Command surface of the reference's `main.py` for the batched backend:  `-a PPO [-m MODEL] train -e EnvXX`.
+
+Reference: src/so100_mujoco_rl/main.py:241-284 (`cli` group with -a/--algorithm and -m/--model, sub-commands
+train | test | record, each with -e/--environment).  Here `train` builds the batched simulator instead of `gym.make`:
+  * `--trainer native` (default): the GPU-resident PPO of so100_mujoco_rl_b200/ppo.py (SB3-default hyper-parameters);
+  * `--trainer sb3`: hands a `So100VecEnv` to stable_baselines3 exactly as main.py:56-64 does (needs SB3 installed).
+`test` and `record` drive an interactive viewer / a video encoder in the reference (main.py:78-171); rendering is outside
+the hot path, so they only evaluate the policy head-less and report returns.
+
+    python -m so100_mujoco_rl_b200.cli -a PPO train -e Env01 --num-envs 4096 --total-timesteps 20000000
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import click
+
+
+@click.group()
+@click.option("-a", "--algorithm", default="PPO", show_default=True, help="RL algorithm (main.py:242-249); the native trainer implements PPO")
+@click.option("-m", "--model", "model_path", default=None, help="path of a saved policy to continue from / evaluate (main.py:250-256)")
+@click.pass_context
+def cli(ctx, algorithm, model_path):
+    ctx.ensure_object(dict)
+    ctx.obj["ALGORITHM_NAME"], ctx.obj["MODEL_PATH"] = algorithm, model_path
+
+
+@cli.command()
+@click.option("-e", "--environment", required=True, help="Env01 | Env02 | Env05 (or the -v1 ids)")
+@click.option("--num-envs", default=4096, show_default=True)
+@click.option("--device", default=0, show_default=True)
+@click.option("--trainer", type=click.Choice(["native", "sb3"]), default="native", show_default=True)
+@click.option("--total-timesteps", default=20_000_000, show_default=True)
+@click.option("--n-steps", default=32, show_default=True)
+@click.option("--seed", default=0, show_default=True)
+@click.option("--out", default="models", show_default=True, help="output folder (reference: models/<Env>_<Algo>/)")
+@click.pass_context
+def train(ctx, environment, num_envs, device, trainer, total_timesteps, n_steps, seed, out):
+    algo = ctx.obj["ALGORITHM_NAME"]
+    folder = os.path.join(out, f"{environment}_{algo}")
+    os.makedirs(folder, exist_ok=True)
+    if trainer == "sb3":
+        import stable_baselines3  # noqa: F401  (as main.py:258-262 validates the algorithm name)
+        from .vec_env import So100VecEnv
+        env = So100VecEnv(environment, num_envs, device=device, seed=seed)
+        cls = getattr(stable_baselines3, algo)
+        model = cls("MlpPolicy", env, device="cpu", n_steps=n_steps, verbose=1) if not ctx.obj["MODEL_PATH"] else cls.load(ctx.obj["MODEL_PATH"], env=env)
+        model.learn(total_timesteps=total_timesteps)
+        model.save(os.path.join(folder, "final_model"))
+        return
+    if algo != "PPO":
+        raise click.UsageError("the native trainer implements PPO; use --trainer sb3 for other algorithms")
+    import torch
+    from .batched_env import BatchedSo100Env
+    from .ppo import PPO, PPOConfig
+    env = BatchedSo100Env(environment, num_envs, device=device, seed=seed)
+    learner = PPO(env, PPOConfig(n_steps=n_steps, seed=seed))
+    if ctx.obj["MODEL_PATH"]:
+        learner.policy.load_state_dict(torch.load(ctx.obj["MODEL_PATH"], map_location=env.device)["policy"])
+    t0 = time.time()
+    stats = learner.learn(total_timesteps, log_every=10)
+    torch.save({"policy": learner.policy.state_dict(), "sb3_policy_state_dict": learner.policy.state_dict_sb3(),
+                "env": environment, "history": stats.history}, os.path.join(folder, "final_model.pt"))
+    click.echo(json.dumps({"samples": stats.samples, "wall_s": time.time() - t0, "rollout_s": stats.rollout_s,
+                           "update_s": stats.update_s, "last": stats.history[-1] if stats.history else None}))
+
+
+def _evaluate(ctx, environment, num_envs, device, steps):
+    import torch
+    from .batched_env import BatchedSo100Env
+    from .ppo import MlpPolicy
+    if not ctx.obj["MODEL_PATH"]:
+        raise click.UsageError("-m/--model is required")
+    env = BatchedSo100Env(environment, num_envs, device=device, seed=123)
+    policy = MlpPolicy(env.obs_dim, env.act_dim).to(env.device)
+    policy.load_state_dict(torch.load(ctx.obj["MODEL_PATH"], map_location=env.device)["policy"])
+    obs, total = env.reset(), torch.zeros(num_envs, device=env.device)
+    with torch.no_grad():
+        for _ in range(steps):
+            a, _, _ = policy.act(obs, deterministic=True)
+            r = env.step(torch.clamp(a, -1, 1))
+            obs = r.obs
+            total += r.reward
+    click.echo(json.dumps({"env": environment, "steps": steps, "mean_return": float(total.mean()), "mean_step_reward": float(total.mean()) / steps}))
+
+
+@cli.command()
+@click.option("-e", "--environment", required=True)
+@click.option("--num-envs", default=256, show_default=True)
+@click.option("--device", default=0, show_default=True)
+@click.option("--steps", default=3000, show_default=True)
+@click.pass_context
+def test(ctx, environment, num_envs, device, steps):
+    """Head-less stand-in for main.py:78-124 (the reference opens a MuJoCo viewer): deterministic policy, mean return."""
+    _evaluate(ctx, environment, num_envs, device, steps)
+
+
+@cli.command()
+@click.option("-e", "--environment", required=True)
+@click.option("--num-envs", default=256, show_default=True)
+@click.option("--device", default=0, show_default=True)
+@click.pass_context
+def record(ctx, environment, num_envs, device):
+    """main.py:127-171 renders 3000 steps to video; rendering is out of scope, so this reports the same 3000 steps' returns."""
+    _evaluate(ctx, environment, num_envs, device, 3000)
+
+
+if __name__ == "__main__":
+    cli(obj={})

@@ -1,0 +1,229 @@
+"""GPU-resident PPO for the batched so100 envs — the caller side of the seam at scale.
+
+The reference trains with `stable_baselines3.PPO("MlpPolicy", env, device='cpu')` on ONE env
+(src/so100_mujoco_rl/main.py:56-64, 234-238).  SB3's rollout loop is per-env Python and its buffers are numpy, which caps
+a 65 536-env simulator at a few 10^5 samples/s; this learner keeps observations, actions, the rollout buffer, GAE and
+the updates on the GPU and drives `BatchedSo100Env` tensors directly.  Hyper-parameters and network are SB3 2.6.0's
+PPO/MlpPolicy defaults (2x64 tanh, separate policy/value towers, state-independent log_std initialised at 0,
+orthogonal init, Adam 3e-4 eps 1e-5, gamma 0.99, lambda 0.95, clip 0.2, vf_coef 0.5, ent_coef 0, max_grad_norm 0.5,
+10 epochs, per-minibatch advantage normalisation, bootstrap of TimeLimit truncations with V(terminal_obs)); only the
+batch geometry differs (n_steps x num_envs samples per rollout, large minibatches).  `state_dict_sb3()` exports the
+weights under SB3's parameter names so that `PPO.load`-style tooling can consume them.
+
+Data parallel: one process per GPU, each with its own env shard; gradients are averaged with ONE flat all-reduce per
+minibatch (NCCL over NVLink; ~10 k fp32 values, latency bound).  The env step path itself has no collective.
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass, field
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+def _ortho(layer: nn.Linear, gain: float) -> nn.Linear:
+    nn.init.orthogonal_(layer.weight, gain=gain)
+    nn.init.zeros_(layer.bias)
+    return layer
+
+
+class MlpPolicy(nn.Module):
+    """SB3 ActorCriticPolicy with net_arch dict(pi=[64, 64], vf=[64, 64]), tanh, DiagGaussian head."""
+
+    def __init__(self, obs_dim: int, act_dim: int, hidden: int = 64, log_std_init: float = 0.0):
+        super().__init__()
+        g = math.sqrt(2.0)
+        self.pi = nn.Sequential(_ortho(nn.Linear(obs_dim, hidden), g), nn.Tanh(), _ortho(nn.Linear(hidden, hidden), g), nn.Tanh())
+        self.vf = nn.Sequential(_ortho(nn.Linear(obs_dim, hidden), g), nn.Tanh(), _ortho(nn.Linear(hidden, hidden), g), nn.Tanh())
+        self.action_net = _ortho(nn.Linear(hidden, act_dim), 0.01)
+        self.value_net = _ortho(nn.Linear(hidden, 1), 1.0)
+        self.log_std = nn.Parameter(torch.full((act_dim,), float(log_std_init)))
+
+    def value(self, obs: torch.Tensor) -> torch.Tensor:
+        return self.value_net(self.vf(obs)).squeeze(-1)
+
+    def dist_params(self, obs: torch.Tensor):
+        return self.action_net(self.pi(obs)), self.log_std
+
+    @staticmethod
+    def log_prob(mean, log_std, actions):
+        var = torch.exp(2 * log_std)
+        return (-((actions - mean) ** 2) / (2 * var) - log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+
+    def act(self, obs: torch.Tensor, deterministic: bool = False):
+        mean, log_std = self.dist_params(obs)
+        a = mean if deterministic else mean + torch.exp(log_std) * torch.randn_like(mean)
+        return a, self.log_prob(mean, log_std, a), self.value(obs)
+
+    def evaluate(self, obs, actions):
+        mean, log_std = self.dist_params(obs)
+        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + log_std).sum(-1).expand(obs.shape[0])
+        return self.value(obs), self.log_prob(mean, log_std, actions), entropy
+
+    def state_dict_sb3(self) -> dict:
+        """Weights under stable_baselines3.common.policies.ActorCriticPolicy's parameter names."""
+        sd = {"log_std": self.log_std.detach().clone()}
+        for name, seq in (("policy_net", self.pi), ("value_net", self.vf)):
+            for idx in (0, 2):
+                sd[f"mlp_extractor.{name}.{idx}.weight"] = seq[idx].weight.detach().clone()
+                sd[f"mlp_extractor.{name}.{idx}.bias"] = seq[idx].bias.detach().clone()
+        for name, lin in (("action_net", self.action_net), ("value_net", self.value_net)):
+            sd[f"{name}.weight"] = lin.weight.detach().clone()
+            sd[f"{name}.bias"] = lin.bias.detach().clone()
+        return sd
+
+
+def compute_gae(rewards, values, dones, last_value, gamma: float, lam: float):
+    """SB3 RolloutBuffer.compute_returns_and_advantage on [T, N] tensors.  dones[t] = episode ended AT step t
+    (the value after it belongs to the next episode)."""
+    T = rewards.shape[0]
+    adv = torch.zeros_like(rewards)
+    last = torch.zeros_like(last_value)
+    for t in reversed(range(T)):
+        nxt = last_value if t == T - 1 else values[t + 1]
+        nonterm = 1.0 - dones[t]
+        delta = rewards[t] + gamma * nxt * nonterm - values[t]
+        last = delta + gamma * lam * nonterm * last
+        adv[t] = last
+    return adv, adv + values
+
+
+@dataclass
+class PPOConfig:
+    n_steps: int = 32
+    n_epochs: int = 10
+    n_minibatches: int = 8
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    clip_range: float = 0.2
+    vf_coef: float = 0.5
+    ent_coef: float = 0.0
+    max_grad_norm: float = 0.5
+    lr: float = 3e-4
+    normalize_advantage: bool = True
+    seed: int = 0
+
+
+@dataclass
+class PPOStats:
+    iterations: int = 0
+    samples: int = 0
+    rollout_s: float = 0.0
+    update_s: float = 0.0
+    history: list = field(default_factory=list)  # per iteration: dict(mean_step_reward, ep_return_mean, ep_len_mean, ...)
+
+
+class PPO:
+    """`env` is a BatchedSo100Env-like object: .num_envs, .obs_dim, .act_dim, .device, reset() -> obs [N, od],
+    step(actions [N, 6]) -> object with obs, reward, terminated, truncated, terminal_obs, ep_return, ep_len."""
+
+    def __init__(self, env, cfg: PPOConfig | None = None):
+        self.env, self.cfg = env, cfg or PPOConfig()
+        self.device = env.device
+        torch.manual_seed(self.cfg.seed)
+        self.policy = MlpPolicy(env.obs_dim, env.act_dim).to(self.device)
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.lr, eps=1e-5)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if self.world > 1:  # identical initial weights on every rank
+            for p in self.policy.parameters():
+                dist.broadcast(p.data, src=0)
+        self.obs = env.reset().clone()
+        self.stats = PPOStats()
+        n, T, od, ad = env.num_envs, self.cfg.n_steps, env.obs_dim, env.act_dim
+        f = dict(device=self.device, dtype=torch.float32)
+        self.buf = {"obs": torch.zeros((T, n, od), **f), "act": torch.zeros((T, n, ad), **f), "logp": torch.zeros((T, n), **f),
+                    "val": torch.zeros((T, n), **f), "rew": torch.zeros((T, n), **f), "done": torch.zeros((T, n), **f)}
+        self._acc = torch.zeros(4, device=self.device, dtype=torch.float64)  # raw reward sum, ep return sum, ep len sum, episodes
+
+    @torch.no_grad()
+    def collect(self):
+        cfg, b = self.cfg, self.buf
+        for t in range(cfg.n_steps):
+            a, logp, v = self.policy.act(self.obs)
+            b["obs"][t], b["act"][t], b["logp"][t], b["val"][t] = self.obs, a, logp, v
+            r = self.env.step(torch.clamp(a, -1.0, 1.0))  # SB3 clips Box actions before env.step (logp is of the raw action)
+            # no host synchronisation inside the rollout loop: masks instead of branches, statistics stay on the device
+            rew = r.reward.clone()
+            term, trunc = r.terminated.bool(), r.truncated.bool()
+            done = term | trunc
+            self._acc[0] += rew.sum()
+            # TimeLimit: bootstrap with the value of the terminal observation (SB3 on_policy_algorithm); rows of envs
+            # that did not finish hold stale (finite) data and are masked out
+            boot = cfg.gamma * self.policy.value(r.terminal_obs)
+            rew = torch.where(trunc, rew + boot, rew)
+            b["rew"][t], b["done"][t] = rew, done.float()
+            df = done.float()
+            self._acc[1] += (r.ep_return * df).sum(); self._acc[2] += (r.ep_len.float() * df).sum(); self._acc[3] += df.sum()
+            self.obs = r.obs.clone()
+        last_value = self.policy.value(self.obs)
+        adv, ret = compute_gae(b["rew"], b["val"], b["done"], last_value, cfg.gamma, cfg.gae_lambda)
+        return adv, ret
+
+    def _allreduce_grads(self):
+        if self.world == 1:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in self.policy.parameters()])
+        dist.all_reduce(flat)
+        flat /= self.world
+        o = 0
+        for p in self.policy.parameters():
+            k = p.numel()
+            p.grad.copy_(flat[o:o + k].view_as(p))
+            o += k
+
+    def update(self, adv, ret):
+        cfg, b = self.cfg, self.buf
+        T, n = b["rew"].shape
+        flat = {k: v.reshape(T * n, *v.shape[2:]) for k, v in b.items()}
+        adv, ret = adv.reshape(-1), ret.reshape(-1)
+        total = T * n
+        mb = total // cfg.n_minibatches
+        info = {}
+        for _ in range(cfg.n_epochs):
+            perm = torch.randperm(total, device=self.device)
+            for k in range(cfg.n_minibatches):
+                idx = perm[k * mb:(k + 1) * mb]
+                a = adv[idx]
+                if cfg.normalize_advantage:
+                    a = (a - a.mean()) / (a.std() + 1e-8)
+                v, logp, ent = self.policy.evaluate(flat["obs"][idx], flat["act"][idx])
+                ratio = torch.exp(logp - flat["logp"][idx])
+                pg = -torch.min(a * ratio, a * torch.clamp(ratio, 1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+                vl = torch.nn.functional.mse_loss(v, ret[idx])
+                loss = pg + cfg.vf_coef * vl - cfg.ent_coef * ent.mean()
+                self.opt.zero_grad(set_to_none=False)
+                loss.backward()
+                self._allreduce_grads()
+                nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
+                self.opt.step()
+                last = (pg.detach(), vl.detach(), ((ratio - 1) - (logp - flat["logp"][idx])).mean().detach())
+        return {"pg_loss": float(last[0]), "v_loss": float(last[1]), "approx_kl": float(last[2])}
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
+    def learn(self, total_samples: int, log_every: int = 10, callback=None) -> PPOStats:
+        per_iter = self.cfg.n_steps * self.env.num_envs * self.world
+        while self.stats.samples < total_samples:
+            self._sync(); t0 = time.perf_counter()
+            adv, ret = self.collect()
+            self._sync(); t1 = time.perf_counter()
+            info = self.update(adv, ret)
+            self._sync(); t2 = time.perf_counter()
+            s = self.stats
+            s.iterations += 1; s.samples += per_iter; s.rollout_s += t1 - t0; s.update_s += t2 - t1
+            raw, ers, els, cnt = (float(x) for x in self._acc.tolist())
+            self._acc.zero_()
+            rec = {"iter": s.iterations, "samples": s.samples, "mean_step_reward": raw / (self.cfg.n_steps * self.env.num_envs),
+                   "ep_return_mean": ers / cnt if cnt else None, "ep_len_mean": els / cnt if cnt else None,
+                   "episodes": int(cnt), "log_std_mean": float(self.policy.log_std.mean()), **info}
+            s.history.append(rec)
+            if callback is not None:
+                callback(rec)
+            elif log_every and s.iterations % log_every == 0:
+                print(rec, flush=True)
+        return self.stats
