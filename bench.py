@@ -26,8 +26,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # Algorithmic work per env step (DESIGN.md "Roofline arithmetic"; tools/count_flops.cpp for the FLOPs)
-FLOP_PER_ENV_STEP = {1: 60400.0, 2: 60400.0, 5: 60700.0}
-BYTES_PER_ENV_STEP = {1: 338.0, 2: 362.0, 5: 420.0}
+FLOP_PER_ENV_STEP = {1: 60400.0, 2: 60400.0, 5: 60700.0, 6: 60400.0}
+BYTES_PER_ENV_STEP = {1: 338.0, 2: 362.0, 5: 420.0, 6: 362.0}
 
 
 def parse():

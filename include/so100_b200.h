@@ -53,6 +53,7 @@ extern "C" {
 #define SO100_TASK_ENV01 1
 #define SO100_TASK_ENV02 2
 #define SO100_TASK_ENV05 5
+#define SO100_TASK_ENV06 6   /* Env02's scene and reset, no relocation, gripper-closing reward (envs/env06_v1.py, env_base_06.py) */
 
 /* quirk flags (task_cfg.flags). Default 0 reproduces the reference bit for bit in behaviour. */
 #define SO100_FLAG_FRESH_FK_ON_RESET 1u /* run kinematics in reset (the reference does not: SURVEY Q2) */
@@ -151,7 +152,7 @@ typedef struct so100_ctx so100_ctx;
 int so100_abi_version(void);
 const char *so100_last_error(void);
 
-int so100_obs_dim(int task);   /* 15 for Env01/Env02, 8 for Env05; <0 on unknown task */
+int so100_obs_dim(int task);   /* 15 for Env01/Env02/Env06, 8 for Env05; <0 on unknown task */
 int so100_act_dim(int task);   /* 6 */
 
 /* Parse-free construction: the caller has read the MJCF (see so100_mujoco_rl_b200/model.py) and hands over constants. */

@@ -7,6 +7,7 @@
  *   Env01   src/so100_mujoco_rl/envs/env01_v1.py:15-63
  *   Env02   src/so100_mujoco_rl/envs/env02_v1.py:18-81
  *   Env05   src/so100_mujoco_rl/envs/env03_v1.py:35-215 (inherited) + env05_v1.py:13-75 + env_base_02.py:85-127
+ *   Env06   src/so100_mujoco_rl/envs/env06_v1.py:18-82 + env_base_06.py:144-162, :200-264
  *   reward  src/so100_mujoco_rl/envs/env_base_01.py:144-239,  obs :241-270
  *   TimeLimit / auto-reset: src/so100_mujoco_rl/__init__.py:5-45 + SB3 DummyVecEnv semantics.
  *
@@ -462,7 +463,7 @@ int orc_sizeof_env_state(void) { return (int)sizeof(orc_env_state); }
 orc_sim *orc_create(const orc_model *m, const orc_task_cfg *cfg) {
   if (!m || !cfg || m->struct_size != (int)sizeof(orc_model) || cfg->struct_size != (int)sizeof(orc_task_cfg)) return NULL;
   if (cfg->num_envs <= 0) return NULL;
-  if (cfg->task != 1 && cfg->task != 2 && cfg->task != 5) return NULL;
+  if (cfg->task != 1 && cfg->task != 2 && cfg->task != 5 && cfg->task != 6) return NULL;
   orc_sim *s = (orc_sim *)calloc(1, sizeof(orc_sim));
   s->m = *m; s->cfg = *cfg; s->n = cfg->num_envs;
   s->env = (orc_env_state *)calloc((size_t)s->n, sizeof(orc_env_state));
@@ -566,7 +567,7 @@ static void reset_env(const orc_sim *s, orc_env_state *e, int env, int stream, f
     place_block(s, e, u);
     int idx = (int)(((uint64_t)raw[3] * (uint64_t)c->n_start) >> 32);
     for (int j = 0; j < NJ - 1; j++) e->qpos[j] = c->start_positions[idx][j]; /* Jaw skipped */
-  } else if (c->task == 2) { /* env02_v1.py:70-81, :52-68 */
+  } else if (c->task == 2 || c->task == 6) { /* env02_v1.py:70-81, :52-68; env06_v1.py:53-82 is the same code */
     draw(s, env, stream, u, NULL);
     double prev[3] = {e->task_block_pos[0], e->task_block_pos[1], e->task_block_pos[2]};
     place_block(s, e, u);
@@ -602,7 +603,7 @@ static double joint_penalty(const orc_sim *s, const double *ang) { /* env_base_0
   }
   return r;
 }
-static double reward_env0102(const orc_sim *s, orc_env_state *e) { /* env_base_01.py:180-239 */
+static double reward_env0102(const orc_sim *s, orc_env_state *e, int in_reach) { /* env_base_01.py:180-239; env_base_06.py:200-264 */
   double reward = 0, d[3];
   for (int c = 0; c < 3; c++) d[c] = e->block_xpos[c] - e->end_pos[c];
   double distance = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
@@ -616,6 +617,10 @@ static double reward_env0102(const orc_sim *s, orc_env_state *e) { /* env_base_0
     reward += fmin(fmax(w, -0.8), 0.8);
   }
   reward += fmin(-distance + 0.02, 0.0) * 0.5;
+  if (in_reach) { /* Env06 only: env_base_06.py:149-162, sigmoid on the normalised jaw opening */
+    double jn = fmin(fmax((e->qpos[5] + 0.2) / 2.2, 0.0), 1.0);
+    reward += 100.0 * (1.0 / (1.0 + exp(-10 * (jn - 0.3))));
+  }
   reward += joint_penalty(s, e->qpos);
   e->ever_stepped = 1;
   return reward;
@@ -632,9 +637,20 @@ static void step_env(const orc_sim *s, orc_env_state *e, int env, const float *a
     if (c->flags & 2u) a[j] = fmin(fmax(a[j], -1.0), 1.0);
   }
   orc_kin kin;
-  if (c->task == 1 || c->task == 2) {
-    rew = reward_env0102(s, e); /* PRE-step reward on stale kinematics */
+  if (c->task == 1 || c->task == 2 || c->task == 6) {
+    int in_reach = 0;
+    if (c->task == 6) { /* env06_v1.py:19 */
+      double d[3];
+      for (int k = 0; k < 3; k++) d[k] = e->block_xpos[k] - e->end_pos[k];
+      in_reach = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) < c->reach_threshold;
+    }
+    rew = reward_env0102(s, e, in_reach); /* PRE-step reward on stale kinematics */
     for (int j = 0; j < NJ; j++) e->ctrl[j] = e->qpos[j] + a[j] * c->joint_step_scale;
+    if (c->task == 6 && in_reach) { /* env06_v1.py:30-38: bonus without relocation */
+      double bd = 0;
+      for (int k = 0; k < 3; k++) bd += (e->task_block_pos[k] - e->last_block_pos[k]) * (e->task_block_pos[k] - e->last_block_pos[k]);
+      rew += sqrt(bd) * 20;
+    }
     if (c->task == 2) {
       double d[3];
       for (int k = 0; k < 3; k++) d[k] = e->block_xpos[k] - e->end_pos[k];

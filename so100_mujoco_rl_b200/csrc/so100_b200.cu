@@ -121,7 +121,7 @@ __device__ __forceinline__ void load_env(const Bufs& B, int n, int i, EnvRegs& e
   for (int j = 0; j < SO_NJ; j++) { e.q[j] = B.qpos[j * n + i]; e.v[j] = B.qvel[j * n + i]; e.w[j] = B.warm[j * n + i]; e.qc[j] = B.qcomp[j * n + i]; }
 #pragma unroll
   for (int k = 0; k < 3; k++) e.blk[k] = B.block[k * n + i];
-  constexpr int ns = TASK == 5 ? 12 : 7, na = TASK == 5 ? 18 : (TASK == 2 ? 6 : 0);
+  constexpr int ns = TASK == 5 ? 12 : 7, na = TASK == 5 ? 18 : ((TASK == 2 || TASK == 6) ? 6 : 0);
 #pragma unroll
   for (int k = 0; k < ns; k++) e.snap[k] = B.snap[k * n + i];
 #pragma unroll
@@ -136,7 +136,7 @@ __device__ __forceinline__ void store_env(const Bufs& B, int n, int i, const Env
   for (int j = 0; j < SO_NJ; j++) { B.qpos[j * n + i] = e.q[j]; B.qvel[j * n + i] = e.v[j]; B.warm[j * n + i] = e.w[j]; B.qcomp[j * n + i] = e.qc[j]; }
 #pragma unroll
   for (int k = 0; k < 3; k++) B.block[k * n + i] = e.blk[k];
-  constexpr int ns = TASK == 5 ? 12 : 7, na = TASK == 5 ? 18 : (TASK == 2 ? 6 : 0);
+  constexpr int ns = TASK == 5 ? 12 : 7, na = TASK == 5 ? 18 : ((TASK == 2 || TASK == 6) ? 6 : 0);
 #pragma unroll
   for (int k = 0; k < ns; k++) B.snap[k * n + i] = e.snap[k];
 #pragma unroll
@@ -223,7 +223,7 @@ __device__ __forceinline__ void reset_env(const Consts& C, const Bufs& B, EnvReg
     int idx = (int)__umulhi(r.w, (unsigned)t.n_start);
 #pragma unroll
     for (int j = 0; j < SO_NJ - 1; j++) e.q[j] = B.start_tab[idx * SO_NJ + j];  // Jaw keeps qpos0
-  } else if (TASK == 2) {  // env02_v1.py:70-81 + :52-68
+  } else if (TASK == 2 || TASK == 6) {  // env02_v1.py:70-81 + :52-68 (env06_v1.py:53-82 is the same code)
     uint4 r = draw(t, env, tick, stream);
     float prev[3] = {e.aux[0], e.aux[1], e.aux[2]};
     place_block(t, r, e.blk);
@@ -261,7 +261,7 @@ __device__ __forceinline__ float joint_penalty(const TaskC& t, const float* ang)
 }
 
 // env_base_01.py:180-239 evaluated BEFORE the physics step on the previous step's (stale) kinematics
-__device__ __forceinline__ float reward_reach(const TaskC& t, EnvRegs& e) {
+__device__ __forceinline__ float reward_reach(const TaskC& t, EnvRegs& e, bool in_reach) {
   const float PI07 = 2.19911485751285527f;  // 0.7*pi
   float dx = e.snap[4] - e.snap[0], dy = e.snap[5] - e.snap[1], dz = e.snap[6] - e.snap[2];
   float distance = sqrtf(dx * dx + dy * dy + dz * dz);
@@ -271,6 +271,10 @@ __device__ __forceinline__ float reward_reach(const TaskC& t, EnvRegs& e) {
   if (ever && e.snap[2] < 0.02f) r += (e.snap[2] - 0.02f) * 20.0f;
   if (ever && e.snap[3] < 0.08f) r += clampf((e.snap[3] - 0.08f) * 10.0f, -0.8f, 0.8f);
   r += fminf(-distance + 0.02f, 0.0f) * 0.5f;
+  if (in_reach) {  // Env06: env_base_06.py:149-162
+    float jn = clampf((e.q[5] + 0.2f) / 2.2f, 0.0f, 1.0f);
+    r += 100.0f / (1.0f + expf(-10.0f * (jn - 0.3f)));
+  }
   r += joint_penalty(t, e.q);
   e.flags |= F_EVER_STEPPED;
   return r;
@@ -354,8 +358,17 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
     load_env<TASK>(B, n, i, e);
     float rew, ctrl[SO_NJ], ctrl_lo[SO_NJ];
     bool term = false;
-    if (TASK == 1 || TASK == 2) {
-      rew = reward_reach(t, e);
+    if (TASK == 1 || TASK == 2 || TASK == 6) {
+      bool in_reach = false;
+      if (TASK == 6) {  // env06_v1.py:19, on the stale kinematics
+        float dx = e.snap[4] - e.snap[0], dy = e.snap[5] - e.snap[1], dz = e.snap[6] - e.snap[2];
+        in_reach = sqrtf(dx * dx + dy * dy + dz * dz) < t.reach;
+      }
+      rew = reward_reach(t, e, in_reach);
+      if (TASK == 6 && in_reach) {  // env06_v1.py:30-38: bonus, the block stays where it is
+        float bx = e.aux[0] - e.aux[3], by = e.aux[1] - e.aux[4], bz = e.aux[2] - e.aux[5];
+        rew += sqrtf(bx * bx + by * by + bz * bz) * 20.0f;
+      }
 #pragma unroll
       for (int j = 0; j < SO_NJ; j++) { ctrl[j] = e.q[j]; ctrl_lo[j] = a[j] * t.step_scale - e.qc[j]; }  // closed loop on qpos (Q6)
       if (TASK == 2) {  // env02_v1.py:29-37, reach test on stale kinematics
@@ -758,7 +771,7 @@ extern "C" {
 int so100_abi_version(void) { return SO100_ABI_VERSION; }
 const char* so100_last_error(void) { return g_err.c_str(); }
 int so100_obs_dim(int task) {
-  if (task == SO100_TASK_ENV01 || task == SO100_TASK_ENV02) return 15;
+  if (task == SO100_TASK_ENV01 || task == SO100_TASK_ENV02 || task == SO100_TASK_ENV06) return 15;
   if (task == SO100_TASK_ENV05) return 8;
   return fail(SO100_ERR_ARG, "unknown task");
 }
@@ -856,6 +869,7 @@ int so100_reset(so100_ctx* c, const uint8_t* mask_dev, float* obs_dev, void* str
   switch (c->task) {
     case 1: reset_kernel<1><<<grid_for(c->n), kBlock, 0, st>>>(c->C, c->B, mask_dev, obs_dev, tick); break;
     case 2: reset_kernel<2><<<grid_for(c->n), kBlock, 0, st>>>(c->C, c->B, mask_dev, obs_dev, tick); break;
+    case 6: reset_kernel<6><<<grid_for(c->n), kBlock, 0, st>>>(c->C, c->B, mask_dev, obs_dev, tick); break;
     default: reset_kernel<5><<<grid_for(c->n), kBlock, 0, st>>>(c->C, c->B, mask_dev, obs_dev, tick); break;
   }
   c->launches++;
@@ -869,12 +883,14 @@ static int launch_step(so100_ctx* c, const StepIO& io, cudaStream_t st) {
     switch (c->task) {
       case 1: step_kernel<1, true><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
       case 2: step_kernel<2, true><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
+      case 6: step_kernel<6, true><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
       default: step_kernel<5, true><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
     }
   } else {
     switch (c->task) {
       case 1: step_kernel<1, false><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
       case 2: step_kernel<2, false><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
+      case 6: step_kernel<6, false><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
       default: step_kernel<5, false><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
     }
   }

@@ -105,6 +105,7 @@ class PPOConfig:
     lr: float = 3e-4
     normalize_advantage: bool = True
     seed: int = 0
+    cuda_graph: bool = True  # capture one optimiser step (the 2x64 MLPs are launch-bound: ~10x faster updates)
 
 
 @dataclass
@@ -125,7 +126,8 @@ class PPO:
         self.device = env.device
         torch.manual_seed(self.cfg.seed)
         self.policy = MlpPolicy(env.obs_dim, env.act_dim).to(self.device)
-        self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.lr, eps=1e-5)
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.lr, eps=1e-5,
+                                    capturable=self.device.type == "cuda" and self.cfg.cuda_graph)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         if self.world > 1:  # identical initial weights on every rank
             for p in self.policy.parameters():
@@ -174,33 +176,76 @@ class PPO:
             p.grad.copy_(flat[o:o + k].view_as(p))
             o += k
 
+    def _minibatch_step(self, idx, flat, adv, ret):
+        cfg = self.cfg
+        a = adv[idx]
+        if cfg.normalize_advantage:
+            a = (a - a.mean()) / (a.std() + 1e-8)
+        v, logp, ent = self.policy.evaluate(flat["obs"][idx], flat["act"][idx])
+        lr = logp - flat["logp"][idx]
+        ratio = torch.exp(lr)
+        pg = -torch.min(a * ratio, a * torch.clamp(ratio, 1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+        vl = torch.nn.functional.mse_loss(v, ret[idx])
+        loss = pg + cfg.vf_coef * vl - cfg.ent_coef * ent.mean()
+        self.opt.zero_grad(set_to_none=False)
+        loss.backward()
+        self._allreduce_grads()
+        nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
+        self.opt.step()
+        self._last_info.copy_(torch.stack([pg.detach(), vl.detach(), ((ratio - 1) - lr).mean().detach()]))
+
+    def _build_graph(self, flat, mb):
+        """Capture one minibatch step on static tensors; replayed n_epochs * n_minibatches times per iteration."""
+        self._idx = torch.zeros(mb, dtype=torch.long, device=self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        saved = ({k: v.clone() for k, v in self.policy.state_dict().items()}, None)
+        with torch.cuda.stream(side):  # warm-up outside capture (allocations, optimizer state)
+            for _ in range(3):
+                self._minibatch_step(self._idx, flat, self._adv, self._ret)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self.policy.load_state_dict(saved[0])  # undo the warm-up updates (Adam moments restart from the warm-up; negligible)
+        for st in self.opt.state.values():
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    v.zero_()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._minibatch_step(self._idx, flat, self._adv, self._ret)
+        self.policy.load_state_dict(saved[0])
+        for st in self.opt.state.values():
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    v.zero_()
+
     def update(self, adv, ret):
         cfg, b = self.cfg, self.buf
         T, n = b["rew"].shape
-        flat = {k: v.reshape(T * n, *v.shape[2:]) for k, v in b.items()}
-        adv, ret = adv.reshape(-1), ret.reshape(-1)
+        flat = {k: v.view(T * n, *v.shape[2:]) for k, v in b.items()}
         total = T * n
         mb = total // cfg.n_minibatches
-        info = {}
+        if not hasattr(self, "_adv"):
+            self._adv, self._ret = torch.zeros(total, device=self.device), torch.zeros(total, device=self.device)
+            self._last_info = torch.zeros(3, device=self.device)
+            self._graph = None
+            if cfg.cuda_graph and self.device.type == "cuda":
+                try:
+                    self._build_graph(flat, mb)
+                except Exception as e:  # noqa: BLE001  - fall back to eager updates, loudly
+                    print(f"[ppo] CUDA-graph capture failed ({type(e).__name__}: {e}); using eager updates", flush=True)
+                    self._graph = None
+        self._adv.copy_(adv.reshape(-1)); self._ret.copy_(ret.reshape(-1))
         for _ in range(cfg.n_epochs):
             perm = torch.randperm(total, device=self.device)
             for k in range(cfg.n_minibatches):
                 idx = perm[k * mb:(k + 1) * mb]
-                a = adv[idx]
-                if cfg.normalize_advantage:
-                    a = (a - a.mean()) / (a.std() + 1e-8)
-                v, logp, ent = self.policy.evaluate(flat["obs"][idx], flat["act"][idx])
-                ratio = torch.exp(logp - flat["logp"][idx])
-                pg = -torch.min(a * ratio, a * torch.clamp(ratio, 1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
-                vl = torch.nn.functional.mse_loss(v, ret[idx])
-                loss = pg + cfg.vf_coef * vl - cfg.ent_coef * ent.mean()
-                self.opt.zero_grad(set_to_none=False)
-                loss.backward()
-                self._allreduce_grads()
-                nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
-                self.opt.step()
-                last = (pg.detach(), vl.detach(), ((ratio - 1) - (logp - flat["logp"][idx])).mean().detach())
-        return {"pg_loss": float(last[0]), "v_loss": float(last[1]), "approx_kl": float(last[2])}
+                if self._graph is not None:
+                    self._idx.copy_(idx)
+                    self._graph.replay()
+                else:
+                    self._minibatch_step(idx, flat, self._adv, self._ret)
+        pg, vl, kl = self._last_info.tolist()
+        return {"pg_loss": pg, "v_loss": vl, "approx_kl": kl}
 
     def _sync(self):
         if self.device.type == "cuda":

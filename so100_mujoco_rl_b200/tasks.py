@@ -11,7 +11,7 @@ import math
 NJ = 6
 MAX_START = 64
 
-TASK_ENV01, TASK_ENV02, TASK_ENV05 = 1, 2, 5
+TASK_ENV01, TASK_ENV02, TASK_ENV05, TASK_ENV06 = 1, 2, 5, 6
 FLAG_FRESH_FK_ON_RESET = 1
 FLAG_CLIP_ACTIONS = 2
 FLAG_GENERIC_KERNEL = 4
@@ -65,11 +65,11 @@ BLOCK_SPACE_START_05 = [[-0.05, -0.4, 0.01], [0.05, -0.3, 0.01]]
 BLOCK_SPACE_END_05 = [[-0.45, -0.45, 0.01], [0.45, -0.25, 0.5]]
 
 # gymnasium registration, __init__.py:5-45
-MAX_EPISODE_STEPS = {TASK_ENV01: 4000, TASK_ENV02: 6000, TASK_ENV05: 6000}
-REWARD_THRESHOLD = {TASK_ENV01: 6000, TASK_ENV02: 8000, TASK_ENV05: 8000}
-OBS_DIM = {TASK_ENV01: 15, TASK_ENV02: 15, TASK_ENV05: 8}
+MAX_EPISODE_STEPS = {TASK_ENV01: 4000, TASK_ENV02: 6000, TASK_ENV05: 6000, TASK_ENV06: 6000}
+REWARD_THRESHOLD = {TASK_ENV01: 6000, TASK_ENV02: 8000, TASK_ENV05: 8000, TASK_ENV06: 8000}
+OBS_DIM = {TASK_ENV01: 15, TASK_ENV02: 15, TASK_ENV05: 8, TASK_ENV06: 15}
 ENV_IDS = {"Env01": TASK_ENV01, "Env01-v1": TASK_ENV01, "Env02": TASK_ENV02, "Env02-v1": TASK_ENV02,
-           "Env05": TASK_ENV05, "Env05-v1": TASK_ENV05}
+           "Env05": TASK_ENV05, "Env05-v1": TASK_ENV05, "Env06": TASK_ENV06, "Env06-v1": TASK_ENV06}
 
 
 class So100TaskCfg(ctypes.Structure):
@@ -107,10 +107,10 @@ def task_id(env: str | int) -> int:
     """Accepts 1/2/5, "Env01", "Env01-v1", ... (the ids of __init__.py:5-45)."""
     if isinstance(env, int):
         if env not in OBS_DIM:
-            raise ValueError(f"unsupported task {env}; this build covers Env01, Env02, Env05")
+            raise ValueError(f"unsupported task {env}; this build covers Env01, Env02, Env05, Env06")
         return env
     if env not in ENV_IDS:
-        raise ValueError(f"unsupported environment id {env!r}; this build covers Env01, Env02, Env05")
+        raise ValueError(f"unsupported environment id {env!r}; this build covers Env01, Env02, Env05, Env06")
     return ENV_IDS[env]
 
 
@@ -134,7 +134,7 @@ def make_task_cfg(task: str | int, num_envs: int, seed: int = 0, env_offset: int
         c.rest_position[j] = REST_POSITION[j]
         c.start_position05[j] = START_POSITION_05[j]
     # envs/env01_v1.py:45 (0.18, 0.42); envs/env02_v1.py:55 (0.22, 0.42)
-    lo = 0.22 if t == TASK_ENV02 else 0.18
+    lo = 0.22 if t in (TASK_ENV02, TASK_ENV06) else 0.18  # env06_v1.py:56 as Env02
     c.block_dist_range[0], c.block_dist_range[1] = lo, 0.42
     c.block_theta_half = 0.25 * math.pi  # env01_v1.py:47
     c.reach_threshold = 0.03  # env02_v1.py:29

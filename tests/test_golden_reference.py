@@ -17,7 +17,7 @@ def load(task):
     return np.load(os.path.join(GOLD, f"ref_env0{task}.npz"))
 
 
-@pytest.mark.parametrize("task", [1, 2, 5])
+@pytest.mark.parametrize("task", [1, 2, 5, 6])
 def test_oracle_reproduces_reference_task_logic(task):
     g = load(task)
     steps, n = g["reward"].shape

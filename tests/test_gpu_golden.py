@@ -10,7 +10,7 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("task", [1, 2, 5])
+@pytest.mark.parametrize("task", [1, 2, 5, 6])
 def test_cuda_path_reproduces_reference_fixtures(task):
     from so100_mujoco_rl_b200.batched_env import BatchedSo100Env
     g = np.load(os.path.join(ROOT, "tests", "golden", f"ref_env0{task}.npz"))

@@ -54,7 +54,7 @@ def test_forward_dynamics_matches_oracle(spec):
     env.close()
 
 
-@pytest.mark.parametrize("task,steps", [(1, 300), (2, 300), (5, 300)])
+@pytest.mark.parametrize("task,steps", [(1, 300), (2, 300), (5, 300), (6, 300)])
 def test_trajectory_parity(task, steps):
     n, seed = 256, 11
     env = _gpu_env(task, n, seed=seed)
@@ -94,7 +94,7 @@ def test_trajectory_parity(task, steps):
     env.close()
 
 
-@pytest.mark.parametrize("task,limit", [(1, 7), (2, 5), (5, 40)])
+@pytest.mark.parametrize("task,limit", [(1, 7), (2, 5), (5, 40), (6, 6)])
 def test_autoreset_and_timelimit(task, limit):
     """Short TimeLimit so that truncation + in-kernel reset run many times; outputs must track the oracle."""
     n, seed = 128, 2

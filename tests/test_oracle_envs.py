@@ -132,7 +132,7 @@ def test_env05_reward_decomposition():
 
 def test_timelimit_values_match_registration():
     from so100_mujoco_rl_b200.tasks import MAX_EPISODE_STEPS
-    assert MAX_EPISODE_STEPS == {1: 4000, 2: 6000, 5: 6000}  # __init__.py:8,15,36
+    assert MAX_EPISODE_STEPS == {1: 4000, 2: 6000, 5: 6000, 6: 6000}  # __init__.py:8,15,36,43
 
 
 def test_fresh_fk_flag_gives_real_kinematics_on_reset():
@@ -149,3 +149,20 @@ def test_rng_is_keyed_by_global_env_id():
     full = make_oracle(1, 8, seed=7)
     hi = make_oracle(1, 4, seed=7, env_offset=4)
     assert np.array_equal(full.reset()[4:], hi.reset())
+
+
+def test_env06_gripper_reward_and_no_relocation():
+    """Env06: first step after a reset is "in reach" (zero kinematics): bonus + 100*sigmoid(10*(jaw_norm-0.3)); the block stays."""
+    o = make_oracle(6, 4, seed=3)
+    o.reset()
+    b0 = o.gather("block").copy()
+    _, r1, *_ = o.step(zeros(4))
+    assert np.array_equal(o.gather("block"), b0)                       # env06_v1.py:38: relocation is commented out
+    jn = np.clip((0.0 + 0.2) / 2.2, 0, 1)                                # REST_POSITION jaw = 0
+    grip = 100.0 / (1.0 + np.exp(-10 * (jn - 0.3)))
+    lo, hi = np.array([-2.2, -3.14158, 0, -2.0, -3.14158, -0.2]), np.array([2.2, 0.2, 3.14158, 1.8, 3.14158, 2.0])
+    q = np.array(REST_POSITION)
+    pen = -10 * (np.maximum(lo + 0.05 * (hi - lo) - q, 0) + np.maximum(q - (hi - 0.05 * (hi - lo)), 0)).sum()
+    assert np.allclose(r1, grip + pen, atol=1e-9)                       # very first step: guards closed, bonus 0
+    _, r2, *_ = o.step(zeros(4))
+    assert (r2 < 0).all()                                               # real kinematics now: not in reach any more

@@ -12,7 +12,7 @@ def make(task, n, limit):
                        max_episode_steps=limit)
 
 
-@pytest.mark.parametrize("task,od", [(1, 15), (2, 15), (5, 8)])
+@pytest.mark.parametrize("task,od", [(1, 15), (2, 15), (5, 8), (6, 15)])
 def test_spaces_and_shapes(task, od, spec):
     env = make(task, 5, 10)
     assert env.num_envs == 5
@@ -106,6 +106,8 @@ def test_rest_of_the_contract():
 def test_unknown_env_ids_are_rejected():
     with pytest.raises(ValueError):
         So100VecEnv("Env03", 2, backend=object())
+    with pytest.raises(ValueError):
+        So100VecEnv("Env04", 2, backend=object())
     from so100_mujoco_rl_b200.tasks import task_id
     assert task_id("Env01-v1") == 1 and task_id("Env05") == 5
 

@@ -1,11 +1,11 @@
 #!/usr/bin/env python
-"""Generates tests/golden/ref_env0{1,2,5}.npz by running the REFERENCE'S OWN Python task logic, unmodified.
+"""Generates tests/golden/ref_env0{1,2,5,6}.npz by running the REFERENCE'S OWN Python task logic, unmodified.
 
 Runs only in the build container (it imports from /root/reference); the fixtures travel, this script's inputs do not.
 
 What is real and what is stubbed
   * REAL: the reference's env classes — So100BaseEnv (envs/env_base_01.py), Env01 (env01_v1.py), Env02 (env02_v1.py),
-    Env03/Env05 (env03_v1.py, env05_v1.py), So100OffscreenBaseEnv's projection (env_base_02.py:85-127) and utils.py —
+    Env03/Env05 (env03_v1.py, env05_v1.py), Env06 (env06_v1.py, env_base_06.py), So100OffscreenBaseEnv's projection (env_base_02.py:85-127) and utils.py —
     imported from /root/reference/src and executed as they are: reward, observation, reset, block scripting,
     re-projection, lost-cube termination.
   * STUBBED (not installable offline): `mujoco`, `gymnasium`, `ultralytics`, `glfw`.  The stub `mujoco.mj_step`
@@ -133,7 +133,7 @@ class MjModel:
 
     @staticmethod
     def from_xml_path(path):
-        assert path.endswith("env01.xml")
+        assert path.endswith(("env01.xml", "env06.xml"))  # env06.xml is byte-identical to env01.xml
         return MjModel()
 
     def body(self, name):
@@ -235,6 +235,9 @@ def make_env(task):
     if task == 2:
         from so100_mujoco_rl.envs.env02_v1 import Env02
         return Env02()
+    if task == 6:
+        from so100_mujoco_rl.envs.env06_v1 import Env06
+        return Env06()
     import so100_mujoco_rl.envs.env_base_02 as b2
     from so100_mujoco_rl.envs.env05_v1 import Env05
     from so100_mujoco_rl.envs.env_base_01 import So100BaseEnv
@@ -295,7 +298,7 @@ def main():
     sys.path.insert(0, REF_SRC)
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
-    for task, n, steps, limit in ((1, 6, 90, 40), (2, 6, 90, 35), (5, 8, 140, 100)):
+    for task, n, steps, limit in ((1, 6, 90, 40), (2, 6, 90, 35), (5, 8, 140, 100), (6, 6, 90, 35)):
         d = rollout(task, n, steps, seed=1234 + task, max_episode_steps=limit, action_seed=task)
         path = os.path.join(out, f"ref_env0{task}.npz")
         np.savez_compressed(path, **d)

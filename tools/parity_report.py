@@ -30,7 +30,7 @@ def main():
 
     spec = load_model()
     report = {}
-    for task in (1, 2, 5):
+    for task in (1, 2, 5, 6):
         n = args.envs
         env = BatchedSo100Env(task, n, device=0, seed=11)
         o = Oracle(spec.to_ctypes(), make_task_cfg(task, n, seed=11))
