@@ -1,0 +1,121 @@
+"""C-ABI behaviours beyond parity: state get/set round trip + replay, masked reset, non-finite state recovery,
+argument checking, the host-buffer path on ragged sizes."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _env(task, n, **kw):
+    from so100_mujoco_rl_b200.batched_env import BatchedSo100Env
+    return BatchedSo100Env(task, n, device=0, **kw)
+
+
+@pytest.mark.parametrize("task", [1, 2, 5, 6])
+def test_state_roundtrip_replays_bit_exactly(task):
+    n = 200
+    env = _env(task, n, seed=5)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    acts = [torch.rand((n, 6), device="cuda", generator=g) * 2 - 1 for _ in range(12)]
+    for a in acts[:5]:
+        env.step(a)
+    snap, tick = env.get_state(), env.tick
+    out1 = [(r.obs.clone(), r.reward.clone()) for r in (env.step(a) for a in acts[5:])]
+    env.set_state(snap)
+    env.tick = tick
+    out2 = [(r.obs.clone(), r.reward.clone()) for r in (env.step(a) for a in acts[5:])]
+    for (o1, r1), (o2, r2) in zip(out1, out2):
+        assert torch.equal(o1, o2) and torch.equal(r1, r2)
+
+
+def test_masked_reset_touches_only_selected_envs():
+    n = 64
+    env = _env(1, n, seed=1)
+    env.reset()
+    for _ in range(3):
+        env.step(torch.zeros((n, 6), device="cuda"))
+    before = env.get_state()
+    obs_before = env.obs.clone()
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    mask[::4] = 1
+    obs = env.reset(mask)
+    after = env.get_state()
+    keep = mask == 0
+    assert torch.equal(after["qpos"][:, keep], before["qpos"][:, keep]) and torch.equal(obs[keep], obs_before[keep])
+    assert (after["counters"][0, mask == 1] == 0).all() and (after["qvel"][:, mask == 1] == 0).all()
+    assert (obs[mask == 1, 6:] == 0).all()
+
+
+def test_non_finite_state_is_reset_and_counted():
+    n = 32
+    env = _env(1, n, seed=2)
+    env.reset()
+    env.step(torch.zeros((n, 6), device="cuda"))
+    st = env.get_state()
+    st["qvel"][2, 7] = float("nan")
+    st["qpos"][0, 9] = float("inf")
+    env.set_state(st)
+    r = env.step(torch.zeros((n, 6), device="cuda"))
+    assert env.stats()["nan_resets"] == 2
+    assert torch.isfinite(r.obs).all()
+    assert r.truncated[7] == 1 and r.truncated[9] == 1 and int(r.truncated.sum()) == 2
+    assert (env.get_state()["counters"][0, [7, 9]] == 0).all()
+
+
+def test_argument_errors_surface_as_exceptions():
+    from so100_mujoco_rl_b200._native import So100Error
+    env = _env(2, 8)
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((7, 6), device="cuda"))
+    with pytest.raises(ValueError):
+        env.reset(torch.zeros(3, dtype=torch.uint8, device="cuda"))
+    with pytest.raises(So100Error):
+        env.tick = -1
+    with pytest.raises(ValueError):
+        _env("Env03", 8)
+    with pytest.raises(So100Error):
+        _env(1, 0)
+
+
+@pytest.mark.parametrize("n", [1, 255, 257, 16385 + 77])
+def test_host_path_on_ragged_sizes(n):
+    """so100_step_host pipelines chunks of envs; every size must give what the device path gives."""
+    e1, e2 = _env(5, n, seed=4), _env(5, n, seed=4)
+    host = e2.alloc_host()
+    assert torch.equal(e1.reset().cpu(), e2.reset_host(host))
+    rng = np.random.default_rng(0)
+    for _ in range(4):
+        a = torch.from_numpy(rng.uniform(-1, 1, (n, 6)).astype(np.float32))
+        r = e1.step(a.cuda())
+        host["actions"].copy_(a)
+        e2.step_host(host)
+        assert torch.equal(r.obs.cpu(), host["obs"]) and torch.equal(r.reward.cpu(), host["reward"])
+        assert torch.equal(r.terminated.cpu(), host["terminated"]) and torch.equal(r.truncated.cpu(), host["truncated"])
+
+
+def test_host_path_delivers_terminal_rows_when_an_episode_ends():
+    n = 300
+    env = _env(1, n, seed=6, max_episode_steps=3)
+    host = env.alloc_host()
+    env.reset_host(host)
+    for t in range(1, 7):
+        host["actions"].zero_()
+        env.step_host(host)
+        if t % 3 == 0:
+            assert host["truncated"].all() and (host["ep_len"] == 3).all()
+            assert not (host["terminal_obs"][:, 6:] == 0).all() and (host["obs"][:, 6:] == 0).all()
+
+
+def test_vec_env_adapter_on_the_gpu_backend():
+    from so100_mujoco_rl_b200 import So100VecEnv
+    env = So100VecEnv("Env02", 128, device=0, seed=3, max_episode_steps=5)
+    obs = env.reset()
+    assert obs.shape == (128, 15) and obs.dtype == np.float32
+    for t in range(1, 11):
+        obs, rew, dones, infos = env.step(env.action_space.sample()[None].repeat(128, 0))
+        assert dones.all() == (t % 5 == 0)
+        if dones.all():
+            assert all(i["TimeLimit.truncated"] and i["episode"]["l"] == 5 for i in infos)
+    env.close()
