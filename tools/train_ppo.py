@@ -2,6 +2,11 @@
 """Trains the GPU PPO on a batched so100 env and writes the learning curve (gpurun_out/ppo_<env>.json).
 
     python tools/train_ppo.py --env Env01 --num-envs 4096 --samples 30000000
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \
+        tools/train_ppo.py --env Env05 --num-envs 65536 --samples 2e9          # BASELINE config 5: env-sharded, data-parallel
+
+Multi-GPU: one process per GPU, `--num-envs` envs on EACH rank (weak scaling), global env ids rank*num_envs...;
+gradients are averaged with one flat NCCL all-reduce per minibatch; the env step path has no collective.
 """
 import argparse
 import json
@@ -26,27 +31,48 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out"))
     args = ap.parse_args()
     import torch
+    import torch.distributed as dist
     from so100_mujoco_rl_b200.batched_env import BatchedSo100Env
     from so100_mujoco_rl_b200.ppo import PPO, PPOConfig
-    env = BatchedSo100Env(args.env, args.num_envs, device=0, seed=args.seed, max_episode_steps=args.max_episode_steps or None)
+    from so100_mujoco_rl_b200.sharding import dist_env
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    env = BatchedSo100Env(args.env, args.num_envs, device=local_rank, seed=args.seed, env_offset=rank * args.num_envs,
+                          max_episode_steps=args.max_episode_steps or None)
     algo = PPO(env, PPOConfig(n_steps=args.n_steps, n_minibatches=args.minibatches, n_epochs=args.epochs, seed=args.seed))
     hist = []
 
     def cb(rec):
         hist.append(rec)
-        if rec["iter"] % 20 == 0 or rec["iter"] == 1:
+        if rank == 0 and (rec["iter"] % 20 == 0 or rec["iter"] == 1):
             print(json.dumps(rec), flush=True)
     t0 = time.time()
     st = algo.learn(int(args.samples), log_every=0, callback=cb)
     wall = time.time() - t0
-    out = {"env": args.env, "num_envs": args.num_envs, "n_steps": args.n_steps, "samples": st.samples, "wall_s": wall,
+    graphed = algo._graph is not None
+    if world > 1:
+        # a captured CUDA graph holds NCCL kernels: drop it and drain the device before tearing the group down
+        # (destroying the communicator under a live graph can hang at exit)
+        algo._graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+    if rank != 0:
+        sys.stdout.flush()
+        os._exit(0)
+    out = {"env": args.env, "num_envs": args.num_envs, "n_gpus": world, "cuda_graph_update": graphed, "n_steps": args.n_steps, "samples": st.samples, "wall_s": wall,
            "rollout_s": st.rollout_s, "update_s": st.update_s, "samples_per_s": st.samples / wall,
            "rollout_env_steps_per_s": st.samples / st.rollout_s, "history": hist[:: max(1, len(hist) // 200)] + hist[-1:],
            "kernel_variant": env.kernel_variant, "stats": env.stats()}
     os.makedirs(args.out, exist_ok=True)
-    path = os.path.join(args.out, f"ppo_{args.env}_s{args.seed}.json")
+    path = os.path.join(args.out, f"ppo_{args.env}_s{args.seed}" + (f"_{world}gpu" if world > 1 else "") + ".json")
     json.dump(out, open(path, "w"), indent=1)
-    print("wrote", path, {k: out[k] for k in ("samples", "wall_s", "rollout_s", "update_s", "samples_per_s")})
+    print("wrote", path, {k: out[k] for k in ("n_gpus", "samples", "wall_s", "rollout_s", "update_s", "samples_per_s", "cuda_graph_update")})
+    if world > 1:
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
