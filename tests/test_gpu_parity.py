@@ -198,3 +198,30 @@ def test_specialised_and_generic_kernels_agree():
     assert (sa["qpos"] - sb["qpos"]).abs().max() < 2e-5
     assert (sa["qvel"] - sb["qvel"]).abs().max() < 1e-3
     assert torch.equal(ra.terminated, rb.terminated)
+
+
+def test_full_length_episode_crosses_the_real_timelimit():
+    """Env01 with its registered 4000-step TimeLimit (src/so100_mujoco_rl/__init__.py:8): 4010 steps, so every env is
+    truncated and auto-reset once at step 4000; flags, terminal observations, episode statistics and the state after
+    64 160 substeps must still track the oracle."""
+    n = 48
+    env, o = _gpu_env(1, n, seed=13), make_oracle(1, n, seed=13)
+    env.reset(); o.reset(nthreads=0)
+    rng = np.random.default_rng(2)
+    worst_obs = worst_rew = 0.0
+    for t in range(1, 4011):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        r = env.step(torch.from_numpy(a).cuda())
+        oo, ro, to, co, tobs, epr, epl = o.step(a, nthreads=0)
+        if t % 50 == 0 or t >= 3995:
+            tg, cg = r.terminated.cpu().numpy(), r.truncated.cpu().numpy()
+            assert (tg == to).all() and (cg == co).all(), t
+            worst_obs = max(worst_obs, float(np.abs(r.obs.cpu().numpy() - oo).max()))
+            worst_rew = max(worst_rew, float(np.abs(r.reward.cpu().numpy() - ro).max()))
+        if t == 4000:
+            assert co.all() and (r.ep_len.cpu().numpy() == 4000).all()
+            assert np.abs(r.terminal_obs.cpu().numpy() - tobs).max() < 1e-4
+            assert np.abs(r.ep_return.cpu().numpy() - epr).max() < 2e-2 * max(1.0, float(np.abs(epr).max()) / 100)
+    dq = np.abs(env.get_state()["qpos"].cpu().numpy() - _oracle_soa(o, "qpos")).max()
+    print(f"4010 steps: max|dq| {dq:.2e} max|dobs| {worst_obs:.2e} max|drew| {worst_rew:.2e}")
+    assert worst_obs < 1e-4 and worst_rew < 1e-3 and dq < 1e-4
