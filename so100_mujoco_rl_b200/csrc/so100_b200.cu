@@ -311,8 +311,10 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
       float f = t.kp[j] * ((cc[j] - e.q[j]) + (cl[j] + e.qc[j])) - t.kv[j] * e.v[j];  // differences first: no cancellation
       b[j] = clampf(f, t.frc_lo[j], t.frc_hi[j]) - bias[j];
     }
-    // ctrl changes once per env step: the first substep's warm start is far (5 sweeps), later ones are within a few %
-    // of the solution and every sweep contracts the error ~100x (3 sweeps)
+    // ctrl changes once per env step, so the first substep's warm start is far: 5 sweeps (each contracts the error
+    // ~100x); afterwards qacc moves a few % per substep: 3 sweeps.  The solver adds per-lane sweeps if the last one
+    // still moved qacc by > 1e-3.  (Extrapolating the warm start to save a sweep was measured: no faster, 6x less
+    // accurate - profiles/r1_variants.md.)
     float d = solve_qacc<float>(C.con, M, b, e.q, e.qc, e.v, e.w, sub == 0 ? 5 : 3);
     float amax = 1.0f;
 #pragma unroll

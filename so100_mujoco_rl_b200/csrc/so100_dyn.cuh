@@ -334,9 +334,11 @@ SO_HD T solve_qacc(const ConC<T>& K, const T* M, const T* b, const T* q, const T
         T x2 = solve1(m + Dl, rm2[j], kap2[j], cc + Dl * xl[j], af[j], K.fr_loss[j]);
         x = sDl[j] * (x - xl[j]) < T(0) ? x2 : x;
       }
-      T d = x - a[j];
-      d = d < T(0) ? -d : d;
-      last = d > last ? d : last;
+      if (sw >= sweeps - 1) {  // only the last scheduled sweep (and the extra ones) feed the convergence test
+        T d = x - a[j];
+        d = d < T(0) ? -d : d;
+        last = d > last ? d : last;
+      }
       a[j] = x;
     }
   }

@@ -3,19 +3,14 @@
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p build
-build() { # tag block minblocks sync
+build() { # tag block minblocks sync [extra flags]
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared \
-    -DSO100_BLOCK=$2 -DSO100_MINBLOCKS=$3 -DSO100_SYNC=$4 -Xptxas -v \
+    -DSO100_BLOCK=$2 -DSO100_MINBLOCKS=$3 -DSO100_SYNC=$4 $5 -Xptxas -v \
     -o build/libso100_$1.so so100_mujoco_rl_b200/csrc/so100_b200.cu 2>&1 | grep -A2 "step_kernelILi1E" | grep -E "registers|spill" | tr '\n' ' '
   echo " <- $1"
 }
-build b64x7 64 7 0 &
-build b64x7s 64 7 1 &
-build b448 448 1 0 &
-build b448s 448 1 1 &
-wait
 build b256s 256 2 1 &
+build b256 256 2 0 &
 build b224s 224 2 1 &
-build b128s 128 4 1 &
-build b128 128 4 0 &
+build b64x7 64 7 0 &
 wait
