@@ -225,3 +225,40 @@ def test_full_length_episode_crosses_the_real_timelimit():
     dq = np.abs(env.get_state()["qpos"].cpu().numpy() - _oracle_soa(o, "qpos")).max()
     print(f"4010 steps: max|dq| {dq:.2e} max|dobs| {worst_obs:.2e} max|drew| {worst_rew:.2e}")
     assert worst_obs < 1e-4 and worst_rew < 1e-3 and dq < 1e-4
+
+
+def test_env02_scripted_reach_fires_relocations_mid_episode(spec):
+    """BASELINE config 3: a subset of envs is servoed onto the block (damped Jacobian-transpose steps from the
+    kernel's own kinematics) so that reach -> bonus -> relocate fires during episodes, not only on the stale
+    first step; GPU and oracle must agree on every relocation."""
+    n, steps = 64, 400
+    env, o = _gpu_env(2, n, seed=17), make_oracle(2, n, seed=17)
+    obs = env.reset().cpu().numpy(); o.reset()
+    rng = np.random.default_rng(3)
+    reloc = 0
+    blk_prev = _oracle_soa(o, "block").T.copy()
+    for t in range(steps):
+        q = torch.tensor(obs[:, :6].T.copy(), device="cuda")
+        z = torch.zeros_like(q)
+        base = env.forward_dynamics(q, z, q)[3][:3].T.cpu().numpy()          # end_pos(q)   [n, 3]
+        J = np.zeros((n, 3, 6))
+        for j in range(6):
+            qp = q.clone(); qp[j] += 1e-3
+            J[:, :, j] = (env.forward_dynamics(qp, z, qp)[3][:3].T.cpu().numpy() - base) / 1e-3
+        target = _oracle_soa(o, "block").T
+        err = target - base
+        a = np.einsum("nij,ni->nj", J, err) * 400.0
+        a = np.clip(a + rng.normal(0, 0.05, a.shape), -1, 1).astype(np.float32)
+        a[n // 2:] = rng.uniform(-1, 1, (n - n // 2, 6)).astype(np.float32)     # the other half acts randomly
+        r = env.step(torch.from_numpy(a).cuda())
+        oo, ro, to, co, *_ = o.step(a)
+        obs = r.obs.cpu().numpy()
+        assert np.abs(obs - oo).max() < 5e-5 and np.abs(r.reward.cpu().numpy() - ro).max() < 2e-3, t
+        blk = _oracle_soa(o, "block").T
+        moved = np.abs(blk - blk_prev).sum(axis=1) > 0
+        if t > 0:
+            reloc += int(moved.sum())
+        blk_prev = blk.copy()
+        assert np.abs(env.get_state()["block"].cpu().numpy().T - blk).max() < 1e-6
+    print(f"Env02 scripted reach: {reloc} mid-episode relocations in {steps} steps ({n // 2} scripted envs)")
+    assert reloc >= 10

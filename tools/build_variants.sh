@@ -10,7 +10,10 @@ build() { # tag block minblocks sync [extra flags]
   echo " <- $1"
 }
 build b256s 256 2 1 &
-build b256 256 2 0 &
-build b224s 224 2 1 &
-build b64x7 64 7 0 &
+build skew2k 256 2 1 "-DSO100_SKEW=2000" &
+build skew4k 256 2 1 "-DSO100_SKEW=4000" &
+build skew7k 256 2 1 "-DSO100_SKEW=7000" &
+wait
+build b128s4 128 4 1 &
+build b128s4skew 128 4 1 "-DSO100_SKEW=3500" &
 wait
