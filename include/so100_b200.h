@@ -218,6 +218,14 @@ int so100_host_forward(const so100_model *model, int n, const double *qpos, cons
 #define SO100_N_DYN_CONSTANTS 141
 int so100_host_constants(const so100_model *model, double *out /*[141]*/);
 
+/*
+ * The fp32 constraint-solver and servo constants the kernels consume (host only): friction-loss rows (D, B, loss),
+ * joint ranges, limit rows (B, K, invweight0, solimp and its reciprocals), then kp, kv, ctrlrange, forcerange, timestep.
+ * 16 x 6 + 6 x 6 + 1 floats.  tools/gen_so100_dyn.py bakes them into csrc/so100_dyn_gen.cuh as literals.
+ */
+#define SO100_N_SOLVER_CONSTANTS 133
+int so100_host_solver_constants(const so100_model *model, float *out, int n_out /* = SO100_N_SOLVER_CONSTANTS */);
+
 /* Which step kernel this ctx launches: 0 = generic (constants at run time), 1 = specialised to the baked so100 model. */
 int so100_kernel_variant(so100_ctx *ctx);
 

@@ -20,6 +20,7 @@ EXPORTS = [
     "so100_reset", "so100_step", "so100_reset_host", "so100_step_host", "so100_get_state", "so100_set_state",
     "so100_get_tick", "so100_set_tick", "so100_forward_dynamics", "so100_host_forward", "so100_get_derived",
     "so100_get_stats", "so100_bench_fp32_peak", "so100_host_constants", "so100_kernel_variant",
+    "so100_host_solver_constants",
 ]
 
 
@@ -68,6 +69,7 @@ def lib() -> ctypes.CDLL:
     L.so100_forward_dynamics.argtypes = [vp, ci] + [vp] * 7 + [vp]
     L.so100_host_forward.argtypes = [ctypes.POINTER(So100Model), ci, dp, dp, dp, dp, dp, dp, dp, ci, ci]
     L.so100_host_constants.argtypes = [ctypes.POINTER(So100Model), dp]
+    L.so100_host_solver_constants.argtypes = [ctypes.POINTER(So100Model), ctypes.POINTER(ctypes.c_float), ci]
     L.so100_kernel_variant.argtypes = [vp]
     L.so100_get_derived.argtypes = [vp, dp, dp, dp]
     L.so100_get_stats.argtypes = [vp, i64p, i64p, i64p]

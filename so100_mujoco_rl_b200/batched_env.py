@@ -125,11 +125,15 @@ class BatchedSo100Env:
         _native.check(self._L.so100_reset_host(self._h, host["obs"].data_ptr(), self._stream()))
         return host["obs"]
 
-    def step_host(self, host: dict, with_terminal: bool = True) -> dict:
-        """actions are read from host['actions']; results land in the other host buffers (synchronous)."""
+    def step_host(self, host: dict, with_terminal: bool = True, actions: torch.Tensor | None = None) -> dict:
+        """actions are read from host['actions'] (or from `actions`, a host float32 [N, 6] tensor); results land in the
+        other host buffers (synchronous).  With pinned buffers the library replays a cached CUDA graph per buffer set."""
         opt = (lambda k: host[k].data_ptr()) if with_terminal else (lambda k: None)
+        act = host["actions"] if actions is None else actions
+        if act.device.type != "cpu" or act.dtype != torch.float32 or not act.is_contiguous() or act.shape != (self.num_envs, NJ):
+            raise ValueError(f"host actions must be a contiguous CPU float32 tensor of shape ({self.num_envs}, {NJ})")
         _native.check(self._L.so100_step_host(
-            self._h, host["actions"].data_ptr(), host["obs"].data_ptr(), host["reward"].data_ptr(),
+            self._h, act.data_ptr(), host["obs"].data_ptr(), host["reward"].data_ptr(),
             host["terminated"].data_ptr(), host["truncated"].data_ptr(), opt("terminal_obs"), opt("ep_return"),
             opt("ep_len"), self._stream()))
         return host

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cmath>
@@ -55,8 +56,8 @@ struct TaskC {
   unsigned flags;
   unsigned seed_lo, seed_hi;
   long long env_offset;
-  float h, dt_env, step_scale;
-  float kp[SO_NJ], kv[SO_NJ], ctrl_lo[SO_NJ], ctrl_hi[SO_NJ], frc_lo[SO_NJ], frc_hi[SO_NJ];
+  float dt_env, step_scale;
+  ActC<float> act;                     // servo gains, clamps, timestep
   float pen_lo[SO_NJ], pen_hi[SO_NJ];  // joint-penalty thresholds, env_base_01.py:155-156
   float rest[SO_NJ], start05[SO_NJ];
   float dist_lo, dist_hi, theta_half, reach;
@@ -85,6 +86,7 @@ struct StepIO {
   unsigned tick;
   int env_lo, env_hi;   // this launch covers envs [env_lo, env_hi) (the host path pipelines chunks)
   int* any_done;        // optional: set to 1 if any env of the launch finished an episode
+  const unsigned* tick_dev;  // optional: the tick is read from device memory (replayed CUDA graphs of the host path)
 };
 
 // ------------------------------------------------------------------------------------------------ device helpers
@@ -286,15 +288,21 @@ __device__ __forceinline__ float reward_reach(const TaskC& t, EnvRegs& e, bool i
 template <int TASK, bool SPEC>
 __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs& e, const float* ctrl_hi, const float* ctrl_lo, bool live) {
   const TaskC& t = C.t;
+  // SPEC: the solver / servo constants of the so100 MJCF are literals (immediates after unrolling), not constant-bank loads
+  ConC<float> Kg;
+  ActC<float> Ag;
+  if (SPEC) so100_gen_solver_constants(Kg, Ag);
+  const ConC<float>& K = SPEC ? Kg : C.con;
+  const ActC<float>& A = SPEC ? Ag : t.act;
   float cc[SO_NJ], cl[SO_NJ];
 #pragma unroll
   for (int j = 0; j < SO_NJ; j++) {
     float sum = ctrl_hi[j] + ctrl_lo[j];
-    bool in = sum >= t.ctrl_lo[j] && sum <= t.ctrl_hi[j];
-    cc[j] = in ? ctrl_hi[j] : clampf(sum, t.ctrl_lo[j], t.ctrl_hi[j]);
+    bool in = sum >= A.ctrl_lo[j] && sum <= A.ctrl_hi[j];
+    cc[j] = in ? ctrl_hi[j] : clampf(sum, A.ctrl_lo[j], A.ctrl_hi[j]);
     cl[j] = in ? ctrl_lo[j] : 0.0f;
   }
-  float worst = 0.0f;
+  bool unconverged = false;
 #pragma unroll 1
   for (int sub = 0; sub < t.nsub; sub++) {
 #if SO100_SYNC
@@ -302,34 +310,34 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
 #endif
     float s[SO_NJ], c[SO_NJ], bias[SO_NJ], M[21], b[SO_NJ];
 #pragma unroll
-    for (int j = 0; j < SO_NJ; j++) sincosf(e.q[j], &s[j], &c[j]);
+    for (int j = 0; j < SO_NJ; j++) so_sincos(e.q[j], &s[j], &c[j]);
     if (sub == t.nsub - 1) take_snapshot<TASK>(C, s, c, e);  // kinematics of the LAST substep's start state (Q3)
     if (SPEC) dyn_bias_mass_so100<float>(s, c, e.v, bias, M);  // constants folded at build time (so100 MJCF)
     else dyn_bias_mass<float>(C.dyn, s, c, e.v, bias, M);       // any other model: constants from the ctx
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {
-      float f = t.kp[j] * ((cc[j] - e.q[j]) + (cl[j] + e.qc[j])) - t.kv[j] * e.v[j];  // differences first: no cancellation
-      b[j] = clampf(f, t.frc_lo[j], t.frc_hi[j]) - bias[j];
+      float f = A.kp[j] * ((cc[j] - e.q[j]) + (cl[j] + e.qc[j])) - A.kv[j] * e.v[j];  // differences first: no cancellation
+      b[j] = clampf(f, A.frc_lo[j], A.frc_hi[j]) - bias[j];
     }
     // ctrl changes once per env step, so the first substep's warm start is far: 5 sweeps (each contracts the error
     // ~100x); afterwards qacc moves a few % per substep: 3 sweeps.  The solver adds per-lane sweeps if the last one
     // still moved qacc by > 1e-3.  (Extrapolating the warm start to save a sweep was measured: no faster, 6x less
     // accurate - profiles/r1_variants.md.)
-    float d = solve_qacc<float>(C.con, M, b, e.q, e.qc, e.v, e.w, sub == 0 ? 5 : 3);
+    float d = solve_qacc<float>(K, M, b, e.q, e.qc, e.v, e.w, sub == 0 ? 5 : 3);
     float amax = 1.0f;
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {
       amax = fmaxf(amax, fabsf(e.w[j]));
-      e.v[j] += t.h * e.w[j];   // mj_Euler (semi-implicit; no joint damping in this model)
-      float y = __fsub_rn(__fmul_rn(t.h, e.v[j]), e.qc[j]);  // compensated sum: 16 000 substeps of 1e-5 rad increments on |q| ~ 3
+      e.v[j] += A.h * e.w[j];   // mj_Euler (semi-implicit; no joint damping in this model)
+      float y = __fsub_rn(__fmul_rn(A.h, e.v[j]), e.qc[j]);  // compensated sum: 16 000 substeps of 1e-5 rad increments on |q| ~ 3
       float s1 = __fadd_rn(e.q[j], y);
       e.qc[j] = __fsub_rn(__fsub_rn(s1, e.q[j]), y);
       e.q[j] = s1;
     }
-    worst = fmaxf(worst, d / amax);
+    unconverged |= d > 2e-3f * amax;
   }
   // the last sweep's largest update bounds the error BEFORE that sweep; the sweep itself contracts it ~100x more
-  if (worst > 2e-3f && live) atomicAdd(&B.stats[0], 1ULL);
+  if (unconverged && live) atomicAdd(&B.stats[0], 1ULL);
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -340,6 +348,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
   const TaskC& t = C.t;
   const int n = t.n, base = io.env_lo + blockIdx.x * kBlock, hi = io.env_hi;
   const bool live = base + (int)threadIdx.x < hi;
+  const unsigned tick = io.tick_dev ? __ldg(io.tick_dev) : io.tick;
   const int i = live ? base + (int)threadIdx.x : hi - 1;  // tail threads shadow the last env (they must reach every barrier); nothing they compute is stored
   // coalesced load of the CTA's action rows through shared memory
   for (int k = threadIdx.x; k < kBlock * SO_NJ; k += kBlock) {
@@ -378,7 +387,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
         if (sqrtf(dx * dx + dy * dy + dz * dz) < t.reach) {
           float bx = e.aux[0] - e.aux[3], by = e.aux[1] - e.aux[4], bz = e.aux[2] - e.aux[5];
           rew += sqrtf(bx * bx + by * by + bz * bz) * 20.0f;
-          uint4 r = draw(t, i, io.tick, STREAM_TASK);
+          uint4 r = draw(t, i, tick, STREAM_TASK);
 #pragma unroll
           for (int k = 0; k < 3; k++) e.aux[3 + k] = e.aux[k];
           place_block(t, r, e.blk);
@@ -387,7 +396,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
         }
       }
       physics<TASK, SPEC>(C, B, e, ctrl, ctrl_lo, live);
-      write_obs<TASK>(t, e, i, io.tick, STREAM_NOISE, obs);
+      write_obs<TASK>(t, e, i, tick, STREAM_NOISE, obs);
     } else {  // env03_v1.py:124-201
       float time = (float)e.elapsed * t.dt_env;
       float f = fminf(time / t.ramp, 1.0f);
@@ -401,7 +410,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
       float dx = e.aux[12] - e.blk[0], dy = e.aux[13] - e.blk[1], dz = e.aux[14] - e.blk[2];
       float dist = sqrtf(dx * dx + dy * dy + dz * dz);
       if (!((float)(e.elapsed - e.t0step) * t.dt_env < e.aux[15] && dist > 0.02f)) {  // :77-93
-        uint4 r = draw(t, i, io.tick, STREAM_TASK);
+        uint4 r = draw(t, i, tick, STREAM_TASK);
         e.aux[12] = smin[0] + (smax[0] - smin[0]) * u01(r.x);
         e.aux[13] = smin[1] + (smax[1] - smin[1]) * u01(r.y);
         e.aux[14] = smin[2] + (smax[2] - smin[2]) * u01(r.z);
@@ -411,14 +420,14 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
       dx = e.aux[12] - e.blk[0]; dy = e.aux[13] - e.blk[1]; dz = e.aux[14] - e.blk[2];  // :95-122
       dist = sqrtf(dx * dx + dy * dy + dz * dz);
       if (dist > 0.0f) {
-        float sd = fminf(speed * t.h, dist) / dist;
+        float sd = fminf(speed * t.act.h, dist) / dist;
         e.blk[0] += dx * sd; e.blk[1] += dy * sd; e.blk[2] += dz * sd;
       }
       float newcmd[SO_NJ];
 #pragma unroll
       for (int j = 0; j < SO_NJ; j++) { newcmd[j] = e.aux[j] + a[j] * t.step_scale; ctrl[j] = newcmd[j]; ctrl_lo[j] = 0.0f; }  // open loop (Q6)
       physics<TASK, SPEC>(C, B, e, ctrl, ctrl_lo, live);
-      write_obs<TASK>(t, e, i, io.tick, STREAM_NOISE, obs);
+      write_obs<TASK>(t, e, i, tick, STREAM_NOISE, obs);
       if (obs[6] == -1.0f && obs[7] == -1.0f) {  // :152-164
         if (e.miss > t.lost_limit) term = true;
         e.miss += 1;
@@ -432,7 +441,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
       float pen = 0.0f;
 #pragma unroll
       for (int j = 0; j < SO_NJ; j++) {  // env_base_01.py:165-178 with timestep 0.002 (Q8)
-        float av = (newcmd[j] - e.aux[j]) / t.h;
+        float av = (newcmd[j] - e.aux[j]) / t.act.h;
         if (e.flags & F_ANGVEL_VALID) pen += fabsf(av - e.aux[6 + j]) * 0.0025f;
         e.aux[6 + j] = av;
       }
@@ -465,7 +474,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
       if (live && io.ep_len_out) io.ep_len_out[i] = e.elapsed;
       if (live && bad) io.truncated[i] = term ? 0 : 1;
       if (live && io.any_done) *io.any_done = 1;
-      reset_env<TASK>(C, B, e, i, io.tick, STREAM_RESET, obs);
+      reset_env<TASK>(C, B, e, i, tick, STREAM_RESET, obs);
     }
     if (live) store_env<TASK>(B, n, i, e);
 #pragma unroll
@@ -504,8 +513,8 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const __grid_constant__
   dyn_bias_mass<float>(C.dyn, s, c, v, bias, M);
 #pragma unroll
   for (int j = 0; j < SO_NJ; j++) {
-    float f = t.kp[j] * clampf(ctrl[j * n + i], t.ctrl_lo[j], t.ctrl_hi[j]) - t.kp[j] * q[j] - t.kv[j] * v[j];
-    b[j] = clampf(f, t.frc_lo[j], t.frc_hi[j]) - bias[j];
+    float f = t.act.kp[j] * clampf(ctrl[j * n + i], t.act.ctrl_lo[j], t.act.ctrl_hi[j]) - t.act.kp[j] * q[j] - t.act.kv[j] * v[j];
+    b[j] = clampf(f, t.act.frc_lo[j], t.act.frc_hi[j]) - bias[j];
   }
   float zc[SO_NJ] = {0, 0, 0, 0, 0, 0};
   solve_qacc<float>(C.con, M, b, q, zc, v, a, 12);
@@ -712,8 +721,31 @@ int build_host_model(const so100_model& m, HostModel& H) {
     if (!(H.con.hi[j] > H.con.lo[j])) return fail(SO100_ERR_MODEL, "joint range must have hi > lo");
     const double* sl = m.jnt_solimp_limit[j];
     H.con.imp0[j] = sl[0]; H.con.imp1[j] = sl[1]; H.con.imp_w[j] = sl[2]; H.con.imp_mid[j] = sl[3]; H.con.imp_pow[j] = sl[4];
+    H.con.imp_rw[j] = sl[2] > 1e-15 ? 1.0 / sl[2] : 0.0;
+    H.con.imp_rmid[j] = sl[3] > 0 ? 1.0 / sl[3] : 0.0;
+    H.con.imp_r1mid[j] = sl[3] < 1 ? 1.0 / (1.0 - sl[3]) : 0.0;
   }
   return SO100_OK;
+}
+
+// fp32 solver / servo constants exactly as the kernels consume them (also what so100_dyn_gen.cuh bakes in)
+void solver_constants_f32(const so100_model& m, const HostModel& H, ConC<float>& K, ActC<float>& A) {
+#define CASTF(f) cast_arr(H.con.f, K.f, SO_NJ)
+  CASTF(fr_D); CASTF(fr_B); CASTF(fr_loss); CASTF(lo); CASTF(hi); CASTF(lim_B); CASTF(lim_K); CASTF(invw);
+  CASTF(imp0); CASTF(imp1); CASTF(imp_w); CASTF(imp_mid); CASTF(imp_pow); CASTF(imp_rw); CASTF(imp_rmid); CASTF(imp_r1mid);
+#undef CASTF
+  for (int j = 0; j < SO_NJ; j++) {
+    A.kp[j] = (float)m.act_kp[j]; A.kv[j] = (float)H.kv[j];
+    A.ctrl_lo[j] = (float)m.act_ctrlrange[j][0]; A.ctrl_hi[j] = (float)m.act_ctrlrange[j][1];
+    A.frc_lo[j] = (float)m.act_forcerange[j][0]; A.frc_hi[j] = (float)m.act_forcerange[j][1];
+  }
+  A.h = (float)m.timestep;
+}
+static_assert(sizeof(ConC<float>) == 16 * SO_NJ * 4 && sizeof(ActC<float>) == (6 * SO_NJ + 1) * 4, "flat float layout");
+constexpr int kNSolverConstants = 16 * SO_NJ + 6 * SO_NJ + 1;
+void flatten_solver(const ConC<float>& K, const ActC<float>& A, float* out) {
+  memcpy(out, &K, sizeof K);
+  memcpy(out + 16 * SO_NJ, &A, sizeof A);
 }
 
 }  // namespace
@@ -745,11 +777,21 @@ struct so100_ctx {
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_tobs = nullptr, *h_epr = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
   int* h_epl = nullptr;
-  // host path pipeline: chunks of envs on helper streams so that H2D, kernel and D2H overlap
-  static constexpr int kMaxChunks = 4;
-  cudaStream_t hs[kMaxChunks] = {};
+  // host path pipeline: chunks of envs on helper streams so that H2D, kernel and D2H overlap; with pinned host buffers
+  // the whole pipeline is a cached CUDA graph (one cudaGraphLaunch per step instead of ~7 API calls per chunk)
+  static constexpr int kMaxChunks = 16, kMaxGraphs = 16;
+  int n_chunks = 4;
+  cudaStream_t hs[kMaxChunks] = {}, cap = nullptr;
   cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {};
   int *d_any_done = nullptr, *p_any_done = nullptr;  // device flag + pinned host copy
+  unsigned *d_tick = nullptr, *p_tick = nullptr;     // tick as the graph's kernels read it + pinned source
+  struct HostGraph {
+    const void* key[5] = {};
+    bool want_term = false;
+    cudaGraphExec_t exec = nullptr;
+    int64_t last_use = 0;
+  } graphs[kMaxGraphs];
+  int64_t graph_launches = 0;
 };
 
 static void free_ctx(so100_ctx* c) {
@@ -760,6 +802,10 @@ static void free_ctx(so100_ctx* c) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->d_any_done) cudaFree(c->d_any_done);
   if (c->p_any_done) cudaFreeHost(c->p_any_done);
+  if (c->d_tick) cudaFree(c->d_tick);
+  if (c->p_tick) cudaFreeHost(c->p_tick);
+  for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (c->cap) cudaStreamDestroy(c->cap);
   for (int k = 0; k < so100_ctx::kMaxChunks; k++) {
     if (c->hs[k]) cudaStreamDestroy(c->hs[k]);
     if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
@@ -801,7 +847,14 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
   {
     double flat[SO100_N_DYN_CONSTANTS];
     flatten_dyn(c->H.dyn, flat);
-    c->specialised = memcmp(flat, kGenDynConstants, sizeof flat) == 0 && !(cfg->flags & SO100_FLAG_GENERIC_KERNEL);
+    ConC<float> K;
+    ActC<float> A;
+    float sflat[kNSolverConstants];
+    solver_constants_f32(*m, c->H, K, A);
+    flatten_solver(K, A, sflat);
+    static_assert(SO100_GEN_NS == kNSolverConstants, "so100_dyn_gen.cuh is stale: run tools/gen_so100_dyn.py");
+    c->specialised = memcmp(flat, kGenDynConstants, sizeof flat) == 0 && memcmp(sflat, kGenSolverConstants, sizeof sflat) == 0 &&
+                     !(cfg->flags & SO100_FLAG_GENERIC_KERNEL);
   }
   // fp64 -> fp32 constants
   Consts& C = c->C;
@@ -813,10 +866,6 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
     d.m = (float)s.m; d.arm = (float)s.arm;
   }
   cast_arr(c->H.dyn.a0, C.dyn.a0, 3);
-#define CASTF(f) cast_arr(c->H.con.f, C.con.f, SO_NJ)
-  CASTF(fr_D); CASTF(fr_B); CASTF(fr_loss); CASTF(lo); CASTF(hi); CASTF(lim_B); CASTF(lim_K); CASTF(invw);
-  CASTF(imp0); CASTF(imp1); CASTF(imp_w); CASTF(imp_mid); CASTF(imp_pow);
-#undef CASTF
   cast_arr(c->H.kin.base_R, C.kin.base_R, 9); cast_arr(c->H.kin.base_p, C.kin.base_p, 3);
   cast_arr(c->H.kin.ee_off, C.kin.ee_off, 3); cast_arr(c->H.kin.cam_pos, C.kin.cam_pos, 3); cast_arr(c->H.kin.cam_R, C.kin.cam_R, 9);
   C.kin.ee_body = c->H.kin.ee_body; C.kin.wrist_body = c->H.kin.wrist_body; C.kin.cam_body = c->H.kin.cam_body;
@@ -825,11 +874,9 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
   t.lost_limit = cfg->lost_limit; t.nsub = m->nsubstep; t.flags = cfg->flags;
   t.seed_lo = (unsigned)(cfg->seed & 0xFFFFFFFFull); t.seed_hi = (unsigned)(cfg->seed >> 32);
   t.env_offset = cfg->env_offset;
-  t.h = (float)m->timestep; t.dt_env = (float)(m->timestep * m->nsubstep); t.step_scale = (float)cfg->joint_step_scale;
+  t.dt_env = (float)(m->timestep * m->nsubstep); t.step_scale = (float)cfg->joint_step_scale;
+  solver_constants_f32(*m, c->H, C.con, t.act);
   for (int j = 0; j < SO_NJ; j++) {
-    t.kp[j] = (float)m->act_kp[j]; t.kv[j] = (float)c->H.kv[j];
-    t.ctrl_lo[j] = (float)m->act_ctrlrange[j][0]; t.ctrl_hi[j] = (float)m->act_ctrlrange[j][1];
-    t.frc_lo[j] = (float)m->act_forcerange[j][0]; t.frc_hi[j] = (float)m->act_forcerange[j][1];
     double lo = m->jnt_range[j][0], hi = m->jnt_range[j][1];
     t.pen_lo[j] = (float)(lo + 0.05 * (hi - lo)); t.pen_hi[j] = (float)(hi - 0.05 * (hi - lo));
     t.rest[j] = (float)cfg->rest_position[j]; t.start05[j] = (float)cfg->start_position05[j];
@@ -907,7 +954,7 @@ int so100_step(so100_ctx* c, const float* actions_dev, float* obs_dev, float* re
   CU(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   c->tick += 1;
-  StepIO io{actions_dev, obs_dev, reward_dev, terminal_obs_dev, ep_return_dev, terminated_dev, truncated_dev, ep_len_dev, (unsigned)c->tick, 0, c->n, nullptr};
+  StepIO io{actions_dev, obs_dev, reward_dev, terminal_obs_dev, ep_return_dev, terminated_dev, truncated_dev, ep_len_dev, (unsigned)c->tick, 0, c->n, nullptr, nullptr};
   return launch_step(c, io, st);
 }
 
@@ -924,6 +971,13 @@ static int ensure_staging(so100_ctx* c) {
   CU(cudaMalloc((void**)&c->h_trunc, n));
   CU(cudaMalloc((void**)&c->d_any_done, sizeof(int)));
   CU(cudaMallocHost((void**)&c->p_any_done, sizeof(int)));
+  CU(cudaMalloc((void**)&c->d_tick, sizeof(unsigned)));
+  CU(cudaMallocHost((void**)&c->p_tick, sizeof(unsigned)));
+  CU(cudaStreamCreateWithFlags(&c->cap, cudaStreamNonBlocking));
+  if (const char* e = getenv("SO100_HOST_CHUNKS")) {  // tuning knob of the host path (default 4: measured best of 1..16, profiles/r1_e2e_chunks.txt)
+    int v = atoi(e);
+    if (v >= 1 && v <= so100_ctx::kMaxChunks) c->n_chunks = v;
+  }
   for (int k = 0; k < so100_ctx::kMaxChunks; k++) {
     CU(cudaStreamCreateWithFlags(&c->hs[k], cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
@@ -945,20 +999,16 @@ int so100_reset_host(so100_ctx* c, float* obs_host, void* stream) {
   return SO100_OK;
 }
 
-int so100_step_host(so100_ctx* c, const float* actions_host, float* obs_host, float* reward_host, uint8_t* terminated_host,
-                    uint8_t* truncated_host, float* terminal_obs_host, float* ep_return_host, int32_t* ep_len_host, void* stream) {
-  if (!c || !actions_host || !obs_host || !reward_host || !terminated_host || !truncated_host) return fail(SO100_ERR_ARG, "null argument");
-  CU(cudaSetDevice(c->device));
-  int rc = ensure_staging(c);
-  if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
+// Enqueue the chunked H2D -> step_kernel -> D2H pipeline: forks from `st` onto the helper streams and joins back.
+// Runs either live on the caller's stream or under stream capture (st == c->cap) to build the cached graph.
+static int enqueue_host_pipeline(so100_ctx* c, cudaStream_t st, const float* actions_host, float* obs_host, float* reward_host,
+                                 uint8_t* terminated_host, uint8_t* truncated_host, bool want_term, bool tick_from_dev) {
   const size_t od = (size_t)c->obs_dim;
-  const bool want_term = terminal_obs_host || ep_return_host || ep_len_host;
   // chunks are multiples of the CTA size; small batches are not worth splitting
-  int nchunk = c->n >= 4 * 4096 ? so100_ctx::kMaxChunks : 1;
+  int nchunk = c->n >= 4 * 4096 ? c->n_chunks : 1;
   int per = ((c->n + nchunk - 1) / nchunk + kBlock - 1) / kBlock * kBlock;
-  c->tick += 1;
   CU(cudaMemsetAsync(c->d_any_done, 0, sizeof(int), st));
+  if (tick_from_dev) CU(cudaMemcpyAsync(c->d_tick, c->p_tick, sizeof(unsigned), cudaMemcpyHostToDevice, st));
   CU(cudaEventRecord(c->ev_start, st));
   for (int k = 0; k < nchunk; k++) {
     int lo = k * per, hi = lo + per < c->n ? lo + per : c->n;
@@ -968,8 +1018,8 @@ int so100_step_host(so100_ctx* c, const float* actions_host, float* obs_host, fl
     CU(cudaStreamWaitEvent(hs, c->ev_start, 0));
     CU(cudaMemcpyAsync(c->h_act + (size_t)lo * SO_NJ, actions_host + (size_t)lo * SO_NJ, cnt * SO_NJ * 4, cudaMemcpyHostToDevice, hs));
     StepIO io{c->h_act, c->h_obs, c->h_rew, want_term ? c->h_tobs : nullptr, want_term ? c->h_epr : nullptr, c->h_term, c->h_trunc,
-              want_term ? c->h_epl : nullptr, (unsigned)c->tick, lo, hi, c->d_any_done};
-    rc = launch_step(c, io, hs);
+              want_term ? c->h_epl : nullptr, (unsigned)c->tick, lo, hi, c->d_any_done, tick_from_dev ? c->d_tick : nullptr};
+    int rc = launch_step(c, io, hs);
     if (rc) return rc;
     CU(cudaMemcpyAsync(obs_host + (size_t)lo * od, c->h_obs + (size_t)lo * od, cnt * od * 4, cudaMemcpyDeviceToHost, hs));
     CU(cudaMemcpyAsync(reward_host + lo, c->h_rew + lo, cnt * 4, cudaMemcpyDeviceToHost, hs));
@@ -979,6 +1029,63 @@ int so100_step_host(so100_ctx* c, const float* actions_host, float* obs_host, fl
   }
   for (int k = 0; k < nchunk; k++) CU(cudaStreamWaitEvent(st, c->ev_done[k], 0));
   CU(cudaMemcpyAsync(c->p_any_done, c->d_any_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+  return SO100_OK;
+}
+
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+int so100_step_host(so100_ctx* c, const float* actions_host, float* obs_host, float* reward_host, uint8_t* terminated_host,
+                    uint8_t* truncated_host, float* terminal_obs_host, float* ep_return_host, int32_t* ep_len_host, void* stream) {
+  if (!c || !actions_host || !obs_host || !reward_host || !terminated_host || !truncated_host) return fail(SO100_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  int rc = ensure_staging(c);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t od = (size_t)c->obs_dim;
+  const bool want_term = terminal_obs_host || ep_return_host || ep_len_host;
+  c->tick += 1;
+  const void* key[5] = {actions_host, obs_host, reward_host, terminated_host, truncated_host};
+  so100_ctx::HostGraph* g = nullptr;
+  for (auto& x : c->graphs)
+    if (x.exec && x.want_term == want_term && memcmp(x.key, key, sizeof key) == 0) { g = &x; break; }
+  if (!g && is_pinned(actions_host) && is_pinned(obs_host) && is_pinned(reward_host) && is_pinned(terminated_host) && is_pinned(truncated_host)) {
+    // pinned buffers: record the pipeline once per buffer set (pageable memory cannot be captured)
+    so100_ctx::HostGraph* slot = &c->graphs[0];
+    for (auto& x : c->graphs) {
+      if (!x.exec) { slot = &x; break; }
+      if (x.last_use < slot->last_use) slot = &x;
+    }
+    if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const int64_t launches_before = c->launches;
+    CU(cudaStreamBeginCapture(c->cap, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_host_pipeline(c, c->cap, actions_host, obs_host, reward_host, terminated_host, truncated_host, want_term, true);
+    cudaError_t ce = cudaStreamEndCapture(c->cap, &graph);
+    c->launches = launches_before;  // recording is not launching
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(SO100_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&slot->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { slot->exec = nullptr; return fail(SO100_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+    memcpy(slot->key, key, sizeof key);
+    slot->want_term = want_term;
+    g = slot;
+  }
+  if (g) {
+    *c->p_tick = (unsigned)c->tick;
+    g->last_use = ++c->graph_launches;
+    CU(cudaGraphLaunch(g->exec, st));
+    int nchunk = c->n >= 4 * 4096 ? c->n_chunks : 1;
+    int per = ((c->n + nchunk - 1) / nchunk + kBlock - 1) / kBlock * kBlock;
+    c->launches += (c->n + per - 1) / per;  // step_kernel launches inside the graph
+  } else {
+    rc = enqueue_host_pipeline(c, st, actions_host, obs_host, reward_host, terminated_host, truncated_host, want_term, false);
+    if (rc) return rc;
+  }
   CU(cudaStreamSynchronize(st));
   if (want_term && *c->p_any_done) {  // the terminal rows are only meaningful for envs that finished: copy them only then
     size_t n = (size_t)c->n;
@@ -1037,6 +1144,20 @@ int so100_host_constants(const so100_model* m, double* out) {
   int rc = build_host_model(*m, H);
   if (rc) return rc;
   flatten_dyn(H.dyn, out);
+  return SO100_OK;
+}
+
+int so100_host_solver_constants(const so100_model* m, float* out, int n_out) {
+  if (!m || !out) return fail(SO100_ERR_ARG, "null argument");
+  if (m->struct_size != (int)sizeof(so100_model)) return fail(SO100_ERR_ARG, "so100_model.struct_size mismatch");
+  if (n_out != kNSolverConstants) return fail(SO100_ERR_ARG, "n_out must be SO100_N_SOLVER_CONSTANTS");
+  HostModel H;
+  int rc = build_host_model(*m, H);
+  if (rc) return rc;
+  ConC<float> K;
+  ActC<float> A;
+  solver_constants_f32(*m, H, K, A);
+  flatten_solver(K, A, out);
   return SO100_OK;
 }
 

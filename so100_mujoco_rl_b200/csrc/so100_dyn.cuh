@@ -22,10 +22,28 @@
 
 #define SO_NJ 6
 
+struct SoTrue { static constexpr bool value = true; };
+struct SoFalse { static constexpr bool value = false; };
+
 SO_HD float so_fma(float a, float b, float c) { return fmaf(a, b, c); }
 SO_HD double so_fma(double a, double b, double c) { return a * b + c; }
 template <typename T>
 SO_HD T so_fma(T a, T b, T c) { return a * b + c; }
+
+// sin/cos of a joint angle inside the substep loop.  Device fp32: MUFU.SIN / MUFU.COS (|err| <= 2^-21.2 on [-pi, pi],
+// CUDA C Programming Guide table of intrinsics; joint ranges of this model stay inside +-3.1416).  A 4e-7 error in
+// sin/cos moves a gravity torque of <= 1 N m by 4e-7 N m, i.e. the servo's equilibrium by 1e-8 rad; the task
+// kinematics (end-effector / camera pose) by < 3e-7 m.  -DSO100_ACCURATE_SINCOS restores sincosf().
+SO_HD void so_sincos(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__) && !defined(SO100_ACCURATE_SINCOS)
+  __sincosf(x, s, c);
+#elif defined(__CUDA_ARCH__)
+  sincosf(x, s, c);
+#else
+  *s = std::sin(x); *c = std::cos(x);
+#endif
+}
+SO_HD void so_sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
 
 template <typename T>
 struct LinkC {
@@ -208,6 +226,14 @@ struct ConC {
   T lo[SO_NJ], hi[SO_NJ];                      // joint range
   T lim_B[SO_NJ], lim_K[SO_NJ], invw[SO_NJ];   // limit row: aref = -B*(J qd) - K*imp*dist, R = (1-imp)/imp*invw
   T imp0[SO_NJ], imp1[SO_NJ], imp_w[SO_NJ], imp_mid[SO_NJ], imp_pow[SO_NJ];
+  T imp_rw[SO_NJ], imp_rmid[SO_NJ], imp_r1mid[SO_NJ];  // 1/width, 1/mid, 1/(1-mid): no divisions on the device
+};
+
+// Position servo + integrator constants (MuJoCo actuator gainprm/biasprm, ctrlrange, forcerange)
+template <typename T>
+struct ActC {
+  T kp[SO_NJ], kv[SO_NJ], ctrl_lo[SO_NJ], ctrl_hi[SO_NJ], frc_lo[SO_NJ], frc_hi[SO_NJ];
+  T h;  // timestep
 };
 
 template <typename T>
@@ -222,12 +248,12 @@ SO_HD T so_pow(T x, T p) {
 template <typename T>
 SO_HD T impedance(const ConC<T>& K, int j, T dist) {  // MuJoCo getimpedance with margin 0
   if (K.imp0[j] == K.imp1[j] || K.imp_w[j] <= T(1e-15)) return T(0.5) * (K.imp0[j] + K.imp1[j]);
-  T x = (dist < 0 ? -dist : dist) / K.imp_w[j];
+  T x = (dist < 0 ? -dist : dist) * K.imp_rw[j];
   if (x >= T(1)) return K.imp1[j];
   if (x <= T(0)) return K.imp0[j];
   T y, p = K.imp_pow[j], mid = K.imp_mid[j];
   if (p == T(1)) y = x;
-  else if (p == T(2)) y = (x <= mid) ? x * x / mid : T(1) - (T(1) - x) * (T(1) - x) / (T(1) - mid);
+  else if (p == T(2)) y = (x <= mid) ? x * x * K.imp_rmid[j] : T(1) - (T(1) - x) * (T(1) - x) * K.imp_r1mid[j];
   else if (x <= mid) y = so_pow(x, p) / so_pow(mid, p - T(1));
   else y = T(1) - so_pow(T(1) - x, p) / so_pow(T(1) - mid, p - T(1));
   return K.imp0[j] + y * (K.imp1[j] - K.imp0[j]);
@@ -311,11 +337,10 @@ SO_HD T solve_qacc(const ConC<T>& K, const T* M, const T* b, const T* q, const T
 #pragma unroll
   for (int j = 0; j < SO_NJ; j++) { T ax = a[j] < T(0) ? -a[j] : a[j]; amax = ax > amax ? ax : amax; }
   const T tol = T(1e-3) * amax;  // scale from the warm start
-#pragma unroll 1
-  for (int sw = 0; sw < sweeps + 6; sw++) {
-    // fixed schedule, then (rare, per-lane) extra sweeps while the last one still moved qacc by > 1e-3 relative
-    if (sw >= sweeps && !(last > tol)) break;
-    last = T(0);
+  // one Gauss-Seidel sweep; TRACK: also return the largest coordinate update
+  auto sweep = [&](auto track) -> T {
+    constexpr bool TRACK = decltype(track)::value;
+    T big = T(0);
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {
       // c_j = b_j - sum_{k != j} M_jk a_k, as two independent chains
@@ -334,13 +359,23 @@ SO_HD T solve_qacc(const ConC<T>& K, const T* M, const T* b, const T* q, const T
         T x2 = solve1(m + Dl, rm2[j], kap2[j], cc + Dl * xl[j], af[j], K.fr_loss[j]);
         x = sDl[j] * (x - xl[j]) < T(0) ? x2 : x;
       }
-      if (sw >= sweeps - 1) {  // only the last scheduled sweep (and the extra ones) feed the convergence test
+      if (TRACK) {
         T d = x - a[j];
         d = d < T(0) ? -d : d;
-        last = d > last ? d : last;
+        big = d > big ? d : big;
       }
       a[j] = x;
     }
+    return big;
+  };
+  // fixed schedule: sweeps-1 plain sweeps, then the last scheduled one with bookkeeping, then (rare, per-lane) extra
+  // sweeps while the last one still moved qacc by > 1e-3 relative
+#pragma unroll 1
+  for (int sw = 0; sw < sweeps - 1; sw++) sweep(SoFalse());
+#pragma unroll 1
+  for (int sw = 0; sw < 7; sw++) {
+    last = sweep(SoTrue());
+    if (!(last > tol)) break;
   }
   return last;
 }

@@ -322,8 +322,53 @@ def host_constants():
     return list(out)
 
 
+N_SOLVER = 16 * NJ + 6 * NJ + 1
+CON_FIELDS = ["fr_D", "fr_B", "fr_loss", "lo", "hi", "lim_B", "lim_K", "invw", "imp0", "imp1", "imp_w", "imp_mid", "imp_pow",
+              "imp_rw", "imp_rmid", "imp_r1mid"]
+ACT_FIELDS = ["kp", "kv", "ctrl_lo", "ctrl_hi", "frc_lo", "frc_hi"]
+
+
+def host_solver_constants():
+    """fp32 solver / servo constants in the ConC<float> + ActC<float> layout (so100_host_solver_constants)."""
+    from so100_mujoco_rl_b200 import _native
+    from so100_mujoco_rl_b200.model import load_model
+    L = _native.lib()
+    m = load_model().to_ctypes()
+    out = (ctypes.c_float * N_SOLVER)()
+    L.so100_host_solver_constants.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
+    _native.check(L.so100_host_solver_constants(ctypes.byref(m), out, N_SOLVER))
+    return [float(x) for x in out]
+
+
+def f32lit(x: float) -> str:
+    return float(np.float32(x)).hex() + "f"
+
+
+def render_solver(sflat):
+    rows = lambda k: "{" + ", ".join(f32lit(v) for v in sflat[k * NJ:(k + 1) * NJ]) + "}"  # noqa: E731
+    con = ",\n      ".join(f"/* {name} */ {rows(k)}" for k, name in enumerate(CON_FIELDS))
+    act = ",\n      ".join(f"/* {name} */ {rows(len(CON_FIELDS) + k)}" for k, name in enumerate(ACT_FIELDS))
+    hexs = ",\n    ".join(", ".join(f32lit(x) for x in sflat[i:i + 6]) for i in range(0, N_SOLVER, 6))
+    return f"""
+// fp32 solver / servo constants (ConC<float> then ActC<float>, so100_host_solver_constants layout); compared exactly too.
+#define SO100_GEN_NS {N_SOLVER}
+static const float kGenSolverConstants[SO100_GEN_NS] = {{
+    {hexs}}};
+
+// The same numbers as literals: after unrolling they become immediates of the solver / servo instructions.
+SO_HD void so100_gen_solver_constants(ConC<float>& K, ActC<float>& A) {{
+  K = ConC<float>{{
+      {con}}};
+  A = ActC<float>{{
+      {act},
+      /* h */ {f32lit(sflat[-1])}}};
+}}
+"""
+
+
 def render():
     flat = host_constants()
+    sflat = host_solver_constants()
     g, outs, planar = build(flat)
     lines, nop = emit(g, outs)
     hexd = ",\n    ".join(", ".join(float(x).hex() for x in flat[i:i + 4]) for i in range(0, 141, 4))
@@ -343,7 +388,7 @@ static const double kGenDynConstants[SO100_GEN_N] = {{
 template <typename T>
 SO_HD void dyn_bias_mass_so100(const T* s, const T* c, const T* qd, T* bias, T* M) {{
 """
-    return hdr + "\n".join(lines) + "\n}\n", nop
+    return hdr + "\n".join(lines) + "\n}\n" + render_solver(sflat), nop
 
 
 def main():
