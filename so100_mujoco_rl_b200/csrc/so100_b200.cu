@@ -86,7 +86,6 @@ struct StepIO {
   unsigned tick;
   int env_lo, env_hi;   // this launch covers envs [env_lo, env_hi) (the host path pipelines chunks)
   int* any_done;        // optional: set to 1 if any env of the launch finished an episode
-  const unsigned* tick_dev;  // optional: the tick is read from device memory (replayed CUDA graphs of the host path)
 };
 
 // ------------------------------------------------------------------------------------------------ device helpers
@@ -348,7 +347,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
   const TaskC& t = C.t;
   const int n = t.n, base = io.env_lo + blockIdx.x * kBlock, hi = io.env_hi;
   const bool live = base + (int)threadIdx.x < hi;
-  const unsigned tick = io.tick_dev ? __ldg(io.tick_dev) : io.tick;
+  const unsigned tick = io.tick;
   const int i = live ? base + (int)threadIdx.x : hi - 1;  // tail threads shadow the last env (they must reach every barrier); nothing they compute is stored
   // coalesced load of the CTA's action rows through shared memory
   for (int k = threadIdx.x; k < kBlock * SO_NJ; k += kBlock) {
@@ -777,21 +776,15 @@ struct so100_ctx {
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_tobs = nullptr, *h_epr = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
   int* h_epl = nullptr;
-  // host path pipeline: chunks of envs on helper streams so that H2D, kernel and D2H overlap; with pinned host buffers
-  // the whole pipeline is a cached CUDA graph (one cudaGraphLaunch per step instead of ~7 API calls per chunk)
-  static constexpr int kMaxChunks = 16, kMaxGraphs = 16;
+  // host path.  Pinned host buffers: the kernel reads the actions and writes obs / reward / flags straight through
+  // the host link (zero-copy), one launch per step.  Pageable buffers: chunks of envs on helper streams so that H2D,
+  // kernel and D2H overlap.
+  static constexpr int kMaxChunks = 16;
   int n_chunks = 4;
-  cudaStream_t hs[kMaxChunks] = {}, cap = nullptr;
+  bool zero_copy = true;
+  cudaStream_t hs[kMaxChunks] = {};
   cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {};
-  int *d_any_done = nullptr, *p_any_done = nullptr;  // device flag + pinned host copy
-  unsigned *d_tick = nullptr, *p_tick = nullptr;     // tick as the graph's kernels read it + pinned source
-  struct HostGraph {
-    const void* key[5] = {};
-    bool want_term = false;
-    cudaGraphExec_t exec = nullptr;
-    int64_t last_use = 0;
-  } graphs[kMaxGraphs];
-  int64_t graph_launches = 0;
+  int *d_any_done = nullptr, *p_any_done = nullptr;  // device flag + pinned host copy (the zero-copy path writes the latter)
 };
 
 static void free_ctx(so100_ctx* c) {
@@ -802,10 +795,6 @@ static void free_ctx(so100_ctx* c) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (c->d_any_done) cudaFree(c->d_any_done);
   if (c->p_any_done) cudaFreeHost(c->p_any_done);
-  if (c->d_tick) cudaFree(c->d_tick);
-  if (c->p_tick) cudaFreeHost(c->p_tick);
-  for (auto& g : c->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
-  if (c->cap) cudaStreamDestroy(c->cap);
   for (int k = 0; k < so100_ctx::kMaxChunks; k++) {
     if (c->hs[k]) cudaStreamDestroy(c->hs[k]);
     if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
@@ -954,7 +943,7 @@ int so100_step(so100_ctx* c, const float* actions_dev, float* obs_dev, float* re
   CU(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   c->tick += 1;
-  StepIO io{actions_dev, obs_dev, reward_dev, terminal_obs_dev, ep_return_dev, terminated_dev, truncated_dev, ep_len_dev, (unsigned)c->tick, 0, c->n, nullptr, nullptr};
+  StepIO io{actions_dev, obs_dev, reward_dev, terminal_obs_dev, ep_return_dev, terminated_dev, truncated_dev, ep_len_dev, (unsigned)c->tick, 0, c->n, nullptr};
   return launch_step(c, io, st);
 }
 
@@ -971,9 +960,7 @@ static int ensure_staging(so100_ctx* c) {
   CU(cudaMalloc((void**)&c->h_trunc, n));
   CU(cudaMalloc((void**)&c->d_any_done, sizeof(int)));
   CU(cudaMallocHost((void**)&c->p_any_done, sizeof(int)));
-  CU(cudaMalloc((void**)&c->d_tick, sizeof(unsigned)));
-  CU(cudaMallocHost((void**)&c->p_tick, sizeof(unsigned)));
-  CU(cudaStreamCreateWithFlags(&c->cap, cudaStreamNonBlocking));
+  if (const char* e = getenv("SO100_HOST_ZEROCOPY")) c->zero_copy = atoi(e) != 0;  // A/B knob (default on)
   if (const char* e = getenv("SO100_HOST_CHUNKS")) {  // tuning knob of the host path (default 4: measured best of 1..16, profiles/r1_e2e_chunks.txt)
     int v = atoi(e);
     if (v >= 1 && v <= so100_ctx::kMaxChunks) c->n_chunks = v;
@@ -999,16 +986,14 @@ int so100_reset_host(so100_ctx* c, float* obs_host, void* stream) {
   return SO100_OK;
 }
 
-// Enqueue the chunked H2D -> step_kernel -> D2H pipeline: forks from `st` onto the helper streams and joins back.
-// Runs either live on the caller's stream or under stream capture (st == c->cap) to build the cached graph.
+// Pageable host buffers: chunked H2D -> step_kernel -> D2H pipeline, forked from `st` onto the helper streams.
 static int enqueue_host_pipeline(so100_ctx* c, cudaStream_t st, const float* actions_host, float* obs_host, float* reward_host,
-                                 uint8_t* terminated_host, uint8_t* truncated_host, bool want_term, bool tick_from_dev) {
+                                 uint8_t* terminated_host, uint8_t* truncated_host, bool want_term) {
   const size_t od = (size_t)c->obs_dim;
   // chunks are multiples of the CTA size; small batches are not worth splitting
   int nchunk = c->n >= 4 * 4096 ? c->n_chunks : 1;
   int per = ((c->n + nchunk - 1) / nchunk + kBlock - 1) / kBlock * kBlock;
   CU(cudaMemsetAsync(c->d_any_done, 0, sizeof(int), st));
-  if (tick_from_dev) CU(cudaMemcpyAsync(c->d_tick, c->p_tick, sizeof(unsigned), cudaMemcpyHostToDevice, st));
   CU(cudaEventRecord(c->ev_start, st));
   for (int k = 0; k < nchunk; k++) {
     int lo = k * per, hi = lo + per < c->n ? lo + per : c->n;
@@ -1018,7 +1003,7 @@ static int enqueue_host_pipeline(so100_ctx* c, cudaStream_t st, const float* act
     CU(cudaStreamWaitEvent(hs, c->ev_start, 0));
     CU(cudaMemcpyAsync(c->h_act + (size_t)lo * SO_NJ, actions_host + (size_t)lo * SO_NJ, cnt * SO_NJ * 4, cudaMemcpyHostToDevice, hs));
     StepIO io{c->h_act, c->h_obs, c->h_rew, want_term ? c->h_tobs : nullptr, want_term ? c->h_epr : nullptr, c->h_term, c->h_trunc,
-              want_term ? c->h_epl : nullptr, (unsigned)c->tick, lo, hi, c->d_any_done, tick_from_dev ? c->d_tick : nullptr};
+              want_term ? c->h_epl : nullptr, (unsigned)c->tick, lo, hi, c->d_any_done};
     int rc = launch_step(c, io, hs);
     if (rc) return rc;
     CU(cudaMemcpyAsync(obs_host + (size_t)lo * od, c->h_obs + (size_t)lo * od, cnt * od * 4, cudaMemcpyDeviceToHost, hs));
@@ -1032,10 +1017,12 @@ static int enqueue_host_pipeline(so100_ctx* c, cudaStream_t st, const float* act
   return SO100_OK;
 }
 
-static bool is_pinned(const void* p) {
+// device-visible alias of a pinned (page-locked, mapped) host pointer, or nullptr for pageable memory
+static void* mapped_alias(const void* host) {
   cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return a.type == cudaMemoryTypeHost;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+  return a.devicePointer;
 }
 
 int so100_step_host(so100_ctx* c, const float* actions_host, float* obs_host, float* reward_host, uint8_t* terminated_host,
@@ -1048,44 +1035,20 @@ int so100_step_host(so100_ctx* c, const float* actions_host, float* obs_host, fl
   const size_t od = (size_t)c->obs_dim;
   const bool want_term = terminal_obs_host || ep_return_host || ep_len_host;
   c->tick += 1;
-  const void* key[5] = {actions_host, obs_host, reward_host, terminated_host, truncated_host};
-  so100_ctx::HostGraph* g = nullptr;
-  for (auto& x : c->graphs)
-    if (x.exec && x.want_term == want_term && memcmp(x.key, key, sizeof key) == 0) { g = &x; break; }
-  if (!g && is_pinned(actions_host) && is_pinned(obs_host) && is_pinned(reward_host) && is_pinned(terminated_host) && is_pinned(truncated_host)) {
-    // pinned buffers: record the pipeline once per buffer set (pageable memory cannot be captured)
-    so100_ctx::HostGraph* slot = &c->graphs[0];
-    for (auto& x : c->graphs) {
-      if (!x.exec) { slot = &x; break; }
-      if (x.last_use < slot->last_use) slot = &x;
-    }
-    if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
-    cudaGraph_t graph = nullptr;
-    const int64_t launches_before = c->launches;
-    CU(cudaStreamBeginCapture(c->cap, cudaStreamCaptureModeThreadLocal));
-    rc = enqueue_host_pipeline(c, c->cap, actions_host, obs_host, reward_host, terminated_host, truncated_host, want_term, true);
-    cudaError_t ce = cudaStreamEndCapture(c->cap, &graph);
-    c->launches = launches_before;  // recording is not launching
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (ce != cudaSuccess) return fail(SO100_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
-    ce = cudaGraphInstantiate(&slot->exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) { slot->exec = nullptr; return fail(SO100_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
-    memcpy(slot->key, key, sizeof key);
-    slot->want_term = want_term;
-    g = slot;
-  }
-  if (g) {
-    *c->p_tick = (unsigned)c->tick;
-    g->last_use = ++c->graph_launches;
-    CU(cudaGraphLaunch(g->exec, st));
-    int nchunk = c->n >= 4 * 4096 ? c->n_chunks : 1;
-    int per = ((c->n + nchunk - 1) / nchunk + kBlock - 1) / kBlock * kBlock;
-    c->launches += (c->n + per - 1) / per;  // step_kernel launches inside the graph
+  const float* za = c->zero_copy ? (const float*)mapped_alias(actions_host) : nullptr;
+  float *zo = za ? (float*)mapped_alias(obs_host) : nullptr, *zr = zo ? (float*)mapped_alias(reward_host) : nullptr;
+  uint8_t *zt = zr ? (uint8_t*)mapped_alias(terminated_host) : nullptr, *zc = zt ? (uint8_t*)mapped_alias(truncated_host) : nullptr;
+  if (zc) {
+    // zero-copy: ONE launch; each CTA pulls its action rows over the host link and posts its obs / reward / flag
+    // rows back as coalesced stores, so the transfers of one CTA overlap the arithmetic of the others
+    *c->p_any_done = 0;
+    StepIO io{za, zo, zr, want_term ? c->h_tobs : nullptr, want_term ? c->h_epr : nullptr, zt, zc,
+              want_term ? c->h_epl : nullptr, (unsigned)c->tick, 0, c->n, (int*)mapped_alias(c->p_any_done)};
+    rc = launch_step(c, io, st);
   } else {
-    rc = enqueue_host_pipeline(c, st, actions_host, obs_host, reward_host, terminated_host, truncated_host, want_term, false);
-    if (rc) return rc;
+    rc = enqueue_host_pipeline(c, st, actions_host, obs_host, reward_host, terminated_host, truncated_host, want_term);
   }
+  if (rc) return rc;
   CU(cudaStreamSynchronize(st));
   if (want_term && *c->p_any_done) {  // the terminal rows are only meaningful for envs that finished: copy them only then
     size_t n = (size_t)c->n;
