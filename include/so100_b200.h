@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SO100_ABI_VERSION 1
+#define SO100_ABI_VERSION 2
 #define SO100_NJ 6            /* arm hinges incl. the jaw */
 #define SO100_MAX_START 64    /* rows available for Env01 start poses (reference: 36) */
 
@@ -59,6 +59,7 @@ extern "C" {
 #define SO100_FLAG_FRESH_FK_ON_RESET 1u /* run kinematics in reset (the reference does not: SURVEY Q2) */
 #define SO100_FLAG_CLIP_ACTIONS 2u      /* clip actions to [-1,1] on device (the reference env does not) */
 #define SO100_FLAG_GENERIC_KERNEL 4u    /* never use the model-specialised kernel (tests: generic vs specialised) */
+#define SO100_FLAG_STATIC_BLOCK 8u      /* hold the Env01/02/06 block at its spawn pose: no gravity, no floor contact (round-1 behaviour) */
 
 /*
  * Model constants as they stand in the MJCF (so_arm100_camera.xml + env01.xml), nothing derived.
@@ -99,6 +100,16 @@ typedef struct so100_model {
   double cam_pos[3];
   double cam_quat[4];
   double cam_fovy_deg;       /* 120 */
+  /* block <-> floor contact (env01.xml:29-34, :39): a free box on the z = 0 plane, all contact parameters default.
+     The arm cannot reach the block's spawn annulus with a colliding body (env01.xml:42-49 excludes the others), so
+     the block only ever moves along z: see DESIGN.md "Block-floor contact". */
+  double block_half_z;       /* box half-size along z, 0.01 (env01.xml:32) */
+  double block_mass;         /* 0.008 = default density 1000 x 0.02^3 (inertiafromgeom="true", env01.xml:2) */
+  double block_friction;     /* sliding friction of the geom pair (max of the two geoms) = 1 */
+  double contact_solref[2];  /* 0.02 1 */
+  double contact_solimp[5];  /* 0.9 0.95 0.001 0.5 2 */
+  int32_t block_ncon;        /* contact points of MuJoCo's plane-box collider for a flat box: 4; 0 = the pair does not collide */
+  int32_t _pad1;
 } so100_model;
 
 /* Task constants: the literals of envs/utils.py, env03_v1.py, env05_v1.py, env_base_02.py, __init__.py. */
@@ -137,7 +148,7 @@ typedef struct so100_state_view {
   float *qvel;          /* [6][N] */
   float *qacc_warm;     /* [6][N]  previous substep's qacc (solver warm start, mjData.qacc_warmstart) */
   float *qpos_comp;     /* [6][N]  compensation term of the fp32 qpos integration: qpos_exact ~ qpos - qpos_comp */
-  float *block;         /* [3][N]  block position (qpos[6:9] of the reference) */
+  float *block;         /* [4][N]  block position (qpos[6:9] of the reference) and its z velocity (qvel[8]) */
   float *snap;          /* [12][N] stale kinematics snapshot: Env01/02 end_pos(0..2), wrist_z(3), block_xpos(4..6);
                                     Env05 cam_xpos(0..2), cam_xmat(3..11 row-major) */
   float *aux;           /* [24][N] task scalars: Env02 block_pos(0..2), last_block_pos(3..5); Env05 cmd(0..5),
@@ -221,9 +232,9 @@ int so100_host_constants(const so100_model *model, double *out /*[141]*/);
 /*
  * The fp32 constraint-solver and servo constants the kernels consume (host only): friction-loss rows (D, B, loss),
  * joint ranges, limit rows (B, K, invweight0, solimp and its reciprocals), then kp, kv, ctrlrange, forcerange, timestep.
- * 16 x 6 + 6 x 6 + 1 floats.  tools/gen_so100_dyn.py bakes them into csrc/so100_dyn_gen.cuh as literals.
+ * then the block-floor contact constants (13).  16 x 6 + 6 x 6 + 1 + 13 floats.  tools/gen_so100_dyn.py bakes them into csrc/so100_dyn_gen.cuh as literals.
  */
-#define SO100_N_SOLVER_CONSTANTS 133
+#define SO100_N_SOLVER_CONSTANTS 146
 int so100_host_solver_constants(const so100_model *model, float *out, int n_out /* = SO100_N_SOLVER_CONSTANTS */);
 
 /* Which step kernel this ctx launches: 0 = generic (constants at run time), 1 = specialised to the baked so100 model. */

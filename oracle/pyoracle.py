@@ -30,6 +30,7 @@ class OrcEnvState(ctypes.Structure):
     _fields_ = [
         ("qpos", ctypes.c_double * NJ), ("qvel", ctypes.c_double * NJ), ("qacc_warm", ctypes.c_double * NJ),
         ("ctrl", ctypes.c_double * NJ), ("time", ctypes.c_double), ("block", ctypes.c_double * 3),
+        ("block_vz", ctypes.c_double),
         ("end_pos", ctypes.c_double * 3), ("wrist_pos", ctypes.c_double * 3), ("block_xpos", ctypes.c_double * 3),
         ("cam_xpos", ctypes.c_double * 3), ("cam_xmat", ctypes.c_double * 9),
         ("task_block_pos", ctypes.c_double * 3), ("last_block_pos", ctypes.c_double * 3),
@@ -74,6 +75,7 @@ def lib():
         L.orc_forward.argtypes = [ctypes.c_void_p, dp, dp, dp, dp, dp, dp, dp, i32p]
         L.orc_substeps.argtypes = [ctypes.c_void_p, dp, dp, dp, dp, ctypes.c_int]
         L.orc_energy.argtypes = [ctypes.c_void_p, dp, dp, dp, dp]
+        L.orc_block_substeps.argtypes = [ctypes.c_void_p, dp, dp, ctypes.c_double, ctypes.c_int]
         L.orc_reset.argtypes = [ctypes.c_void_p, u8p, fp, ctypes.c_int]
         L.orc_step.argtypes = [ctypes.c_void_p, fp, fp, dp, u8p, u8p, fp, dp, i32p, ctypes.c_int]
         L.orc_philox.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
@@ -166,6 +168,12 @@ class Oracle:
         c = np.ascontiguousarray(ctrl, dtype=np.float64)
         self._L.orc_substeps(self._h, _d(q), _d(v), _d(w), _d(c), int(n))
         return q, v, w
+
+    def block_substeps(self, z: float, vz: float, n: int, fz_applied: float = 0.0):
+        """n mj_step substeps of the free block's z coordinate (gravity + applied force + floor contact)."""
+        zz, vv = ctypes.c_double(z), ctypes.c_double(vz)
+        self._L.orc_block_substeps(self._h, ctypes.byref(zz), ctypes.byref(vv), float(fz_applied), int(n))
+        return zz.value, vv.value
 
     def energy(self, qpos, qvel):
         q = np.ascontiguousarray(qpos, dtype=np.float64)

@@ -434,9 +434,46 @@ void orc_forward(const orc_sim *s, const double *qpos, const double *qvel, const
   forward_from_kin(s, &k, qpos, qvel, ctrl, qacc_warm, qacc, qacc_smooth, qfrc_constraint, niter_out);
 }
 
-/* n x mj_step on the arm; if kin_last != NULL it receives the kinematics computed in the LAST substep */
+/* ------------------------------------------------------------------ block <-> floor contact
+ * The Env01/02/06 block is a free box (env01.xml:29-34) spawned with its centre ON the floor plane (env01_v1.py:51-52,
+ * env02_v1.py:61-62: z = 0.0, i.e. penetrating by its half-size), so MuJoCo's soft contact pushes it up until it rests
+ * ~0.1 mm inside the plane.  Nothing else can touch it (env01.xml:42-49 excludes every arm body that can reach the
+ * spawn annulus), it starts axis-aligned with zero velocity, and teleports only rewrite qpos[0:3]; by symmetry the
+ * unique minimiser of MuJoCo's convex constraint problem then has no tangential or angular component, and the
+ * block's 6-dof dynamics reduce EXACTLY to its z coordinate.  What MuJoCo 3.3.1 does for that coordinate [3P, restated
+ * from knowledge of mjc_PlaneBox, mj_instantiateContact and mj_makeImpedance; no source in the container]:
+ *   - plane-box collision makes one contact per bottom corner (4), each with dist = z - half_z, included while dist <= 0;
+ *   - condim 3 + pyramidal cone (the scene's default <option>): 4 rows per contact, J = n +- mu t_k, so J_z = 1, J.v = vz;
+ *   - every row: pos = dist, aref = -B vz - K imp(dist) dist with (K, B) from solref as for the limit rows;
+ *   - regularisation: diagApprox = (1 + mu^2) body_invweight0_trans = (1 + mu^2)/m, R0 = (1-imp)/imp diagApprox,
+ *     every pyramid row R = 2 mu_reg^2 R0, mu_reg = mu / sqrt(impratio) = mu (impratio 1);
+ *   - row force = -min(0, J a - aref) / R.  With all 16 rows identical:  m a = m g + f_applied + (16/R) max(0, aref - a).
+ * For mu = 1 the total stiffness 16/R equals that of 4 elliptic-cone normal rows, as MuJoCo's scaling intends. */
+static double block_accel(const orc_sim *s, double z, double vz, double fz_applied) {
+  const orc_model *m = &s->m;
+  double a_free = m->gravity[2] + fz_applied / m->block_mass;
+  double dist = z - m->block_half_z;
+  if (m->block_ncon <= 0 || dist > 0) return a_free;
+  double K, B, imp = impedance(m->contact_solimp, dist), mu = m->block_friction;
+  kb_from_solref(m->contact_solref, m->contact_solimp, m->timestep, &K, &B);
+  double R0 = fmax(MJMINVAL, (1 - imp) / imp * (1 + mu * mu) / m->block_mass);
+  double R = fmax(MJMINVAL, 2 * mu * mu * R0);
+  double D = 4.0 * m->block_ncon / R;
+  double aref = -B * vz - K * imp * dist;
+  if (a_free >= aref) return a_free; /* J a - aref >= 0: the rows carry no force */
+  return (m->block_mass * a_free + D * aref) / (m->block_mass + D);
+}
+void orc_block_substeps(const orc_sim *s, double *z, double *vz, double fz_applied, int n) {
+  for (int t = 0; t < n; t++) {
+    *vz += s->m.timestep * block_accel(s, *z, *vz, fz_applied);
+    *z += s->m.timestep * *vz;
+  }
+}
+
+/* n x mj_step on the arm (and the free block's z when blk != NULL); if kin_last != NULL it receives the kinematics
+   computed in the LAST substep and blk_xpos the block position of that same instant */
 static void substeps_kin(const orc_sim *s, double *qpos, double *qvel, double *warm, const double *ctrl, int n,
-                         orc_kin *kin_last) {
+                         orc_kin *kin_last, double *blk, double *blk_vz, double *blk_xpos) {
   double h = s->m.timestep;
   for (int t = 0; t < n; t++) {
     orc_kin k;
@@ -449,10 +486,14 @@ static void substeps_kin(const orc_sim *s, double *qpos, double *qvel, double *w
       warm[j] = qacc[j];
     }
     if (kin_last && t == n - 1) *kin_last = k;
+    if (blk) {
+      if (blk_xpos && t == n - 1) memcpy(blk_xpos, blk, 3 * sizeof(double));
+      if (blk_vz) orc_block_substeps(s, &blk[2], blk_vz, 0.0, 1);
+    }
   }
 }
 void orc_substeps(const orc_sim *s, double *qpos, double *qvel, double *qacc_warm, const double *ctrl, int n) {
-  substeps_kin(s, qpos, qvel, qacc_warm, ctrl, n, NULL);
+  substeps_kin(s, qpos, qvel, qacc_warm, ctrl, n, NULL, NULL, NULL, NULL);
 }
 
 /* ------------------------------------------------------------------ construction */
@@ -548,7 +589,6 @@ static void snapshot(orc_env_state *e, const orc_kin *k) {
   memcpy(e->wrist_pos, k->wrist_pos, sizeof e->wrist_pos);
   memcpy(e->cam_xpos, k->cam_xpos, sizeof e->cam_xpos);
   memcpy(e->cam_xmat, k->cam_xmat, sizeof e->cam_xmat);
-  memcpy(e->block_xpos, e->block, sizeof e->block_xpos);
 }
 
 /* MujocoEnv.reset = mj_resetData + reset_model (no mj_forward: kinematics stay zero) */
@@ -558,7 +598,7 @@ static void reset_env(const orc_sim *s, orc_env_state *e, int env, int stream, f
   uint32_t raw[4];
   memset(e->qpos, 0, sizeof e->qpos); memset(e->qvel, 0, sizeof e->qvel);
   memset(e->qacc_warm, 0, sizeof e->qacc_warm); memset(e->ctrl, 0, sizeof e->ctrl);
-  e->time = 0; e->elapsed_steps = 0; e->ep_return = 0;
+  e->time = 0; e->elapsed_steps = 0; e->ep_return = 0; e->block_vz = 0; /* mj_resetData zeroes qvel */
   memset(e->end_pos, 0, sizeof e->end_pos); memset(e->wrist_pos, 0, sizeof e->wrist_pos);
   memset(e->block_xpos, 0, sizeof e->block_xpos);
   memset(e->cam_xpos, 0, sizeof e->cam_xpos); memset(e->cam_xmat, 0, sizeof e->cam_xmat);
@@ -589,6 +629,7 @@ static void reset_env(const orc_sim *s, orc_env_state *e, int env, int stream, f
     orc_kin k;
     orc_fk(s, e->qpos, &k);
     snapshot(e, &k);
+    memcpy(e->block_xpos, e->block, sizeof e->block_xpos);
   }
   if (c->task == 5) obs_env05(s, e, env, STREAM_RESET_NOISE, obs); else obs_env0102(e, obs);
 }
@@ -664,7 +705,9 @@ static void step_env(const orc_sim *s, orc_env_state *e, int env, const float *a
         memcpy(e->task_block_pos, e->block, sizeof e->task_block_pos);
       }
     }
-    substeps_kin(s, e->qpos, e->qvel, e->qacc_warm, e->ctrl, s->m.nsubstep, &kin);
+    /* SO100_FLAG_STATIC_BLOCK (8): the block is held at its spawn pose (no gravity, no contact) */
+    substeps_kin(s, e->qpos, e->qvel, e->qacc_warm, e->ctrl, s->m.nsubstep, &kin, e->block,
+                 (c->flags & 8u) ? NULL : &e->block_vz, e->block_xpos);
     snapshot(e, &kin);
     obs_env0102(e, obs);
   } else {
@@ -695,7 +738,8 @@ static void step_env(const orc_sim *s, orc_env_state *e, int env, const float *a
     }
     double newcmd[NJ];
     for (int j = 0; j < NJ; j++) { newcmd[j] = e->cmd[j] + a[j] * c->joint_step_scale; e->ctrl[j] = newcmd[j]; }
-    substeps_kin(s, e->qpos, e->qvel, e->qacc_warm, e->ctrl, s->m.nsubstep, &kin);
+    /* Env05's block is scripted: repositioned, its velocity zeroed and gravity cancelled every env step (:95-122) */
+    substeps_kin(s, e->qpos, e->qvel, e->qacc_warm, e->ctrl, s->m.nsubstep, &kin, e->block, NULL, e->block_xpos);
     snapshot(e, &kin);
     obs_env05(s, e, env, STREAM_NOISE, obs);
     if (obs[6] == -1.0f && obs[7] == -1.0f) { /* :152-164 */

@@ -40,6 +40,8 @@ typedef struct orc_model {
   double act_kp[ORC_NJ], act_dampratio[ORC_NJ], act_kv[ORC_NJ], act_ctrlrange[ORC_NJ][2], act_forcerange[ORC_NJ][2];
   int32_t ee_body, wrist_body, cam_body, _pad0;
   double ee_offset[3], cam_pos[3], cam_quat[4], cam_fovy_deg;
+  double block_half_z, block_mass, block_friction, contact_solref[2], contact_solimp[5];
+  int32_t block_ncon, _pad1;
 } orc_model;
 
 typedef struct orc_task_cfg {
@@ -68,6 +70,7 @@ typedef struct orc_env_state {
   double qpos[ORC_NJ], qvel[ORC_NJ], qacc_warm[ORC_NJ], ctrl[ORC_NJ];
   double time;
   double block[3];
+  double block_vz; /* qvel[8] of the reference: the free block only ever moves along z (floor contact) */
   /* stale kinematics as left by the last mj_step (all zero after mj_resetData) */
   double end_pos[3], wrist_pos[3], block_xpos[3], cam_xpos[3], cam_xmat[9];
   /* task state */
@@ -98,6 +101,8 @@ void orc_bias(const orc_sim *s, const double *qpos, const double *qvel, double *
 /* one mj_forward on the arm: returns qacc; optional outputs may be NULL. niter_out = Newton iterations used. */
 void orc_forward(const orc_sim *s, const double *qpos, const double *qvel, const double *ctrl,
                  const double *qacc_warm, double *qacc, double *qacc_smooth, double *qfrc_constraint, int *niter_out);
+/* n mj_step substeps of the free block's z coordinate (gravity + applied force fz + floor contact), in place */
+void orc_block_substeps(const orc_sim *s, double *z, double *vz, double fz_applied, int n);
 /* n mj_step substeps on raw arrays (qpos,qvel,warm updated in place) */
 void orc_substeps(const orc_sim *s, double *qpos, double *qvel, double *qacc_warm, const double *ctrl, int n);
 /* total mechanical energy (kinetic incl. armature, potential) for invariants */

@@ -77,7 +77,7 @@ def lib() -> ctypes.CDLL:
     for name in EXPORTS:
         if name not in ("so100_last_error", "so100_destroy"):
             getattr(L, name).restype = ci
-    if L.so100_abi_version() != 1:
+    if L.so100_abi_version() != 2:
         raise ImportError("libso100_b200.so has an unexpected ABI version; rebuild it")
     _lib = L
     return L

@@ -140,7 +140,7 @@ class BatchedSo100Env:
 
     # ---- state access (parity tests, checkpoints)
     _STATE_FIELDS = {"qpos": (6, torch.float32), "qvel": (6, torch.float32), "qacc_warm": (6, torch.float32), "qpos_comp": (6, torch.float32),
-                     "block": (3, torch.float32), "snap": (12, torch.float32), "aux": (24, torch.float32),
+                     "block": (4, torch.float32), "snap": (12, torch.float32), "aux": (24, torch.float32),
                      "counters": (4, torch.int32), "ep_return": (1, torch.float32)}
 
     def get_state(self) -> dict:

@@ -58,6 +58,7 @@ struct TaskC {
   long long env_offset;
   float dt_env, step_scale;
   ActC<float> act;                     // servo gains, clamps, timestep
+  BlkC<float> blk;                     // block <-> floor contact
   float pen_lo[SO_NJ], pen_hi[SO_NJ];  // joint-penalty thresholds, env_base_01.py:155-156
   float rest[SO_NJ], start05[SO_NJ];
   float dist_lo, dist_hi, theta_half, reach;
@@ -109,7 +110,7 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 struct EnvRegs {  // everything one env carries through a step, in registers
   float q[SO_NJ], v[SO_NJ], w[SO_NJ];
   float qc[SO_NJ];  // Kahan compensation of the qpos integration (qpos = q - qc to ~2^-48)
-  float blk[3];
+  float blk[3], bvz;  // block position, z velocity
   float snap[kSnap];
   float aux[kAux];
   int elapsed, flags, miss, t0step;
@@ -122,6 +123,7 @@ __device__ __forceinline__ void load_env(const Bufs& B, int n, int i, EnvRegs& e
   for (int j = 0; j < SO_NJ; j++) { e.q[j] = B.qpos[j * n + i]; e.v[j] = B.qvel[j * n + i]; e.w[j] = B.warm[j * n + i]; e.qc[j] = B.qcomp[j * n + i]; }
 #pragma unroll
   for (int k = 0; k < 3; k++) e.blk[k] = B.block[k * n + i];
+  e.bvz = TASK == 5 ? 0.0f : B.block[3 * n + i];
   constexpr int ns = TASK == 5 ? 12 : 7, na = TASK == 5 ? 18 : ((TASK == 2 || TASK == 6) ? 6 : 0);
 #pragma unroll
   for (int k = 0; k < ns; k++) e.snap[k] = B.snap[k * n + i];
@@ -137,6 +139,7 @@ __device__ __forceinline__ void store_env(const Bufs& B, int n, int i, const Env
   for (int j = 0; j < SO_NJ; j++) { B.qpos[j * n + i] = e.q[j]; B.qvel[j * n + i] = e.v[j]; B.warm[j * n + i] = e.w[j]; B.qcomp[j * n + i] = e.qc[j]; }
 #pragma unroll
   for (int k = 0; k < 3; k++) B.block[k * n + i] = e.blk[k];
+  if (TASK != 5) B.block[3 * n + i] = e.bvz;
   constexpr int ns = TASK == 5 ? 12 : 7, na = TASK == 5 ? 18 : ((TASK == 2 || TASK == 6) ? 6 : 0);
 #pragma unroll
   for (int k = 0; k < ns; k++) B.snap[k * n + i] = e.snap[k];
@@ -217,7 +220,7 @@ __device__ __forceinline__ void reset_env(const Consts& C, const Bufs& B, EnvReg
   for (int j = 0; j < SO_NJ; j++) { e.q[j] = 0.0f; e.v[j] = 0.0f; e.w[j] = 0.0f; e.qc[j] = 0.0f; }
 #pragma unroll
   for (int k = 0; k < kSnap; k++) e.snap[k] = 0.0f;
-  e.elapsed = 0; e.ep_ret = 0.0f;
+  e.elapsed = 0; e.ep_ret = 0.0f; e.bvz = 0.0f;  // mj_resetData zeroes qvel
   if (TASK == 1) {  // env01_v1.py:39-63
     uint4 r = draw(t, env, tick, stream);
     place_block(t, r, e.blk);
@@ -290,9 +293,12 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
   // SPEC: the solver / servo constants of the so100 MJCF are literals (immediates after unrolling), not constant-bank loads
   ConC<float> Kg;
   ActC<float> Ag;
-  if (SPEC) so100_gen_solver_constants(Kg, Ag);
+  BlkC<float> Bg;
+  if (SPEC) so100_gen_solver_constants(Kg, Ag, Bg);
   const ConC<float>& K = SPEC ? Kg : C.con;
   const ActC<float>& A = SPEC ? Ag : t.act;
+  const BlkC<float>& Kb = SPEC ? Bg : t.blk;
+  const bool block_moves = TASK != 5 && !(t.flags & SO100_FLAG_STATIC_BLOCK);  // Env05 scripts its block (env03_v1.py:95-122)
   float cc[SO_NJ], cl[SO_NJ];
 #pragma unroll
   for (int j = 0; j < SO_NJ; j++) {
@@ -334,6 +340,7 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
       e.q[j] = s1;
     }
     unconverged |= d > 2e-3f * amax;
+    if (block_moves) block_substep<float>(Kb, A.h, e.blk[2], e.bvz);  // after the snapshot: xpos is of the substep's start
   }
   // the last sweep's largest update bounds the error BEFORE that sweep; the sweep itself contracts it ~100x more
   if (unconverged && live) atomicAdd(&B.stats[0], 1ULL);
@@ -728,7 +735,7 @@ int build_host_model(const so100_model& m, HostModel& H) {
 }
 
 // fp32 solver / servo constants exactly as the kernels consume them (also what so100_dyn_gen.cuh bakes in)
-void solver_constants_f32(const so100_model& m, const HostModel& H, ConC<float>& K, ActC<float>& A) {
+void solver_constants_f32(const so100_model& m, const HostModel& H, ConC<float>& K, ActC<float>& A, BlkC<float>& Bk) {
 #define CASTF(f) cast_arr(H.con.f, K.f, SO_NJ)
   CASTF(fr_D); CASTF(fr_B); CASTF(fr_loss); CASTF(lo); CASTF(hi); CASTF(lim_B); CASTF(lim_K); CASTF(invw);
   CASTF(imp0); CASTF(imp1); CASTF(imp_w); CASTF(imp_mid); CASTF(imp_pow); CASTF(imp_rw); CASTF(imp_rmid); CASTF(imp_r1mid);
@@ -739,12 +746,30 @@ void solver_constants_f32(const so100_model& m, const HostModel& H, ConC<float>&
     A.frc_lo[j] = (float)m.act_forcerange[j][0]; A.frc_hi[j] = (float)m.act_forcerange[j][1];
   }
   A.h = (float)m.timestep;
+  // block <-> floor contact (csrc/so100_dyn.cuh:block_substep; MuJoCo semantics in DESIGN.md "Block-floor contact")
+  {
+    double tc = m.contact_solref[0], dr = m.contact_solref[1], dmax = m.contact_solimp[1], Kc, Bc;
+    if (tc > 0) {
+      if (tc < 2 * m.timestep) tc = 2 * m.timestep;  // refsafe
+      Kc = 1.0 / std::fmax(1e-15, dmax * dmax * tc * tc * dr * dr);
+      Bc = 2.0 / std::fmax(1e-15, dmax * tc);
+    } else { Kc = -m.contact_solref[0] / (dmax * dmax); Bc = -m.contact_solref[1] / dmax; }
+    const double mu = m.block_friction, rows = 4.0 * (m.block_ncon > 0 ? m.block_ncon : 0);
+    const double* si = m.contact_solimp;
+    Bk.half_z = (float)m.block_half_z; Bk.gz = (float)m.gravity[2]; Bk.K = (float)Kc; Bk.B = (float)Bc;
+    Bk.lam_scale = (float)(mu > 0 ? rows / (2 * mu * mu * (1 + mu * mu)) : 0.0);
+    Bk.imp0 = (float)si[0]; Bk.imp1 = (float)si[1]; Bk.imp_w = (float)si[2]; Bk.imp_mid = (float)si[3]; Bk.imp_pow = (float)si[4];
+    Bk.imp_rw = (float)(si[2] > 1e-15 ? 1.0 / si[2] : 0.0);
+    Bk.imp_rmid = (float)(si[3] > 0 ? 1.0 / si[3] : 0.0);
+    Bk.imp_r1mid = (float)(si[3] < 1 ? 1.0 / (1.0 - si[3]) : 0.0);
+  }
 }
-static_assert(sizeof(ConC<float>) == 16 * SO_NJ * 4 && sizeof(ActC<float>) == (6 * SO_NJ + 1) * 4, "flat float layout");
-constexpr int kNSolverConstants = 16 * SO_NJ + 6 * SO_NJ + 1;
-void flatten_solver(const ConC<float>& K, const ActC<float>& A, float* out) {
+static_assert(sizeof(ConC<float>) == 16 * SO_NJ * 4 && sizeof(ActC<float>) == (6 * SO_NJ + 1) * 4 && sizeof(BlkC<float>) == 13 * 4, "flat float layout");
+constexpr int kNSolverConstants = 16 * SO_NJ + 6 * SO_NJ + 1 + 13;
+void flatten_solver(const ConC<float>& K, const ActC<float>& A, const BlkC<float>& Bk, float* out) {
   memcpy(out, &K, sizeof K);
   memcpy(out + 16 * SO_NJ, &A, sizeof A);
+  memcpy(out + 16 * SO_NJ + 6 * SO_NJ + 1, &Bk, sizeof Bk);
 }
 
 }  // namespace
@@ -824,6 +849,7 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
   if (cfg->max_episode_steps <= 0) return fail(SO100_ERR_ARG, "max_episode_steps must be positive");
   if (cfg->task == SO100_TASK_ENV01 && (cfg->n_start <= 0 || cfg->n_start > kMaxStart)) return fail(SO100_ERR_ARG, "n_start out of range");
   if (m->nsubstep <= 0 || !(m->timestep > 0)) return fail(SO100_ERR_MODEL, "nsubstep / timestep must be positive");
+  if (!(m->block_mass > 0) || !(m->block_half_z > 0) || m->block_ncon < 0) return fail(SO100_ERR_MODEL, "block mass / half size must be positive");
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(SO100_ERR_ARG, "no such CUDA device");
@@ -838,9 +864,10 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
     flatten_dyn(c->H.dyn, flat);
     ConC<float> K;
     ActC<float> A;
+    BlkC<float> Bk;
     float sflat[kNSolverConstants];
-    solver_constants_f32(*m, c->H, K, A);
-    flatten_solver(K, A, sflat);
+    solver_constants_f32(*m, c->H, K, A, Bk);
+    flatten_solver(K, A, Bk, sflat);
     static_assert(SO100_GEN_NS == kNSolverConstants, "so100_dyn_gen.cuh is stale: run tools/gen_so100_dyn.py");
     c->specialised = memcmp(flat, kGenDynConstants, sizeof flat) == 0 && memcmp(sflat, kGenSolverConstants, sizeof sflat) == 0 &&
                      !(cfg->flags & SO100_FLAG_GENERIC_KERNEL);
@@ -864,7 +891,7 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
   t.seed_lo = (unsigned)(cfg->seed & 0xFFFFFFFFull); t.seed_hi = (unsigned)(cfg->seed >> 32);
   t.env_offset = cfg->env_offset;
   t.dt_env = (float)(m->timestep * m->nsubstep); t.step_scale = (float)cfg->joint_step_scale;
-  solver_constants_f32(*m, c->H, C.con, t.act);
+  solver_constants_f32(*m, c->H, C.con, t.act, t.blk);
   for (int j = 0; j < SO_NJ; j++) {
     double lo = m->jnt_range[j][0], hi = m->jnt_range[j][1];
     t.pen_lo[j] = (float)(lo + 0.05 * (hi - lo)); t.pen_hi[j] = (float)(hi - 0.05 * (hi - lo));
@@ -883,7 +910,7 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
     return cudaMemset(*p, 0, bytes) == cudaSuccess;
   };
   bool ok = alloc((void**)&c->B.qpos, 6 * n * 4) && alloc((void**)&c->B.qvel, 6 * n * 4) && alloc((void**)&c->B.warm, 6 * n * 4) && alloc((void**)&c->B.qcomp, 6 * n * 4) &&
-            alloc((void**)&c->B.block, 3 * n * 4) && alloc((void**)&c->B.snap, kSnap * n * 4) && alloc((void**)&c->B.aux, kAux * n * 4) &&
+            alloc((void**)&c->B.block, 4 * n * 4) && alloc((void**)&c->B.snap, kSnap * n * 4) && alloc((void**)&c->B.aux, kAux * n * 4) &&
             alloc((void**)&c->B.ep_return, n * 4) && alloc((void**)&c->B.cnt, kCnt * n * 4) && alloc((void**)&c->B.stats, 2 * 8) &&
             alloc((void**)&c->start_tab, kMaxStart * SO_NJ * 4);
   if (!ok) { std::string e = cudaGetErrorString(cudaGetLastError()); free_ctx(c); return fail(SO100_ERR_CUDA, "cudaMalloc: " + e); }
@@ -1067,7 +1094,7 @@ static int copy_state(so100_ctx* c, const so100_state_view* v, void* stream, boo
   size_t n = (size_t)c->n;
   struct { void* ext; void* in; size_t bytes; } f[] = {
       {v->qpos, c->B.qpos, 6 * n * 4}, {v->qvel, c->B.qvel, 6 * n * 4}, {v->qacc_warm, c->B.warm, 6 * n * 4}, {v->qpos_comp, c->B.qcomp, 6 * n * 4},
-      {v->block, c->B.block, 3 * n * 4}, {v->snap, c->B.snap, kSnap * n * 4}, {v->aux, c->B.aux, kAux * n * 4},
+      {v->block, c->B.block, 4 * n * 4}, {v->snap, c->B.snap, kSnap * n * 4}, {v->aux, c->B.aux, kAux * n * 4},
       {v->counters, c->B.cnt, kCnt * n * 4}, {v->ep_return, c->B.ep_return, n * 4}};
   for (auto& x : f) {
     if (!x.ext) continue;
@@ -1119,8 +1146,9 @@ int so100_host_solver_constants(const so100_model* m, float* out, int n_out) {
   if (rc) return rc;
   ConC<float> K;
   ActC<float> A;
-  solver_constants_f32(*m, H, K, A);
-  flatten_solver(K, A, out);
+  BlkC<float> Bk;
+  solver_constants_f32(*m, H, K, A, Bk);
+  flatten_solver(K, A, Bk, out);
   return SO100_OK;
 }
 

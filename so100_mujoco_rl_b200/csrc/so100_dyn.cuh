@@ -236,6 +236,16 @@ struct ActC {
   T h;  // timestep
 };
 
+// Free block resting on the floor plane, reduced to its z coordinate (exact by symmetry: DESIGN.md "Block-floor
+// contact", which restates the MuJoCo contact semantics this folds).  All contact rows are identical, so the
+// constrained acceleration is closed form:  a = (g + lam aref) / (1 + lam),  lam = lam_scale * imp / (1 - imp),
+// lam_scale = rows / (2 mu^2 (1 + mu^2)) = 4 for 4 corner contacts x 4 pyramid rows at mu = 1.
+template <typename T>
+struct BlkC {
+  T half_z, gz, K, B, lam_scale;
+  T imp0, imp1, imp_w, imp_rw, imp_mid, imp_rmid, imp_r1mid, imp_pow;
+};
+
 template <typename T>
 SO_HD T so_pow(T x, T p) {
 #ifdef __CUDA_ARCH__
@@ -245,18 +255,23 @@ SO_HD T so_pow(T x, T p) {
 #endif
 }
 
+// MuJoCo getimpedance with margin 0: d0 at dist 0 rising to d1 at |dist| >= width along a power-law sigmoid
 template <typename T>
-SO_HD T impedance(const ConC<T>& K, int j, T dist) {  // MuJoCo getimpedance with margin 0
-  if (K.imp0[j] == K.imp1[j] || K.imp_w[j] <= T(1e-15)) return T(0.5) * (K.imp0[j] + K.imp1[j]);
-  T x = (dist < 0 ? -dist : dist) * K.imp_rw[j];
-  if (x >= T(1)) return K.imp1[j];
-  if (x <= T(0)) return K.imp0[j];
-  T y, p = K.imp_pow[j], mid = K.imp_mid[j];
+SO_HD T impedance_f(T d0, T d1, T w, T rw, T mid, T rmid, T r1mid, T p, T dist) {
+  if (d0 == d1 || w <= T(1e-15)) return T(0.5) * (d0 + d1);
+  T x = (dist < 0 ? -dist : dist) * rw;
+  if (x >= T(1)) return d1;
+  if (x <= T(0)) return d0;
+  T y;
   if (p == T(1)) y = x;
-  else if (p == T(2)) y = (x <= mid) ? x * x * K.imp_rmid[j] : T(1) - (T(1) - x) * (T(1) - x) * K.imp_r1mid[j];
+  else if (p == T(2)) y = (x <= mid) ? x * x * rmid : T(1) - (T(1) - x) * (T(1) - x) * r1mid;
   else if (x <= mid) y = so_pow(x, p) / so_pow(mid, p - T(1));
   else y = T(1) - so_pow(T(1) - x, p) / so_pow(T(1) - mid, p - T(1));
-  return K.imp0[j] + y * (K.imp1[j] - K.imp0[j]);
+  return d0 + y * (d1 - d0);
+}
+template <typename T>
+SO_HD T impedance(const ConC<T>& K, int j, T dist) {
+  return impedance_f(K.imp0[j], K.imp1[j], K.imp_w[j], K.imp_rw[j], K.imp_mid[j], K.imp_rmid[j], K.imp_r1mid[j], K.imp_pow[j], dist);
 }
 
 #ifdef __CUDACC__
@@ -287,6 +302,20 @@ SO_HD float so_rcp(float x) {
 }
 template <typename T>
 SO_HD T so_rcp(T x) { return T(1) / x; }
+
+// One mj_step of the block's z coordinate: soft floor contact + gravity, semi-implicit Euler.
+template <typename T>
+SO_HD void block_substep(const BlkC<T>& Kb, T h, T& z, T& vz) {
+  T a = Kb.gz, dist = z - Kb.half_z;
+  if (!(dist > T(0))) {  // mjc_PlaneBox keeps the corner contacts while dist <= margin = 0
+    T imp = impedance_f(Kb.imp0, Kb.imp1, Kb.imp_w, Kb.imp_rw, Kb.imp_mid, Kb.imp_rmid, Kb.imp_r1mid, Kb.imp_pow, dist);
+    T aref = -Kb.B * vz - Kb.K * imp * dist;
+    T lam = Kb.lam_scale * imp * so_rcp(T(1) - imp);
+    if (Kb.gz < aref) a = (Kb.gz + lam * aref) * so_rcp(T(1) + lam);  // rows active iff J a - aref < 0
+  }
+  vz += h * a;
+  z += h * vz;
+}
 
 // Exact minimiser over x of  m x^2/2 - c x + huber_f(x - af)   (friction-loss row only), closed form:
 //   t = c - m af;  F = clamp(t * D/(m+D), -loss, loss);  x = af + (t - F)/m          (rm = 1/m, kap = D/(m+D))

@@ -104,6 +104,13 @@ class So100Model(ctypes.Structure):
         ("cam_pos", ctypes.c_double * 3),
         ("cam_quat", ctypes.c_double * 4),
         ("cam_fovy_deg", ctypes.c_double),
+        ("block_half_z", ctypes.c_double),
+        ("block_mass", ctypes.c_double),
+        ("block_friction", ctypes.c_double),
+        ("contact_solref", ctypes.c_double * 2),
+        ("contact_solimp", ctypes.c_double * 5),
+        ("block_ncon", ctypes.c_int32),
+        ("_pad1", ctypes.c_int32),
     ]
 
 
@@ -142,6 +149,13 @@ class ModelSpec:
     cam_pos: np.ndarray = field(default_factory=lambda: np.zeros(3))
     cam_quat: np.ndarray = field(default_factory=lambda: np.array([1.0, 0, 0, 0]))
     cam_fovy_deg: float = 45.0
+    # block <-> floor contact (env01.xml:29-34, :39): MuJoCo defaults unless the scene overrides them
+    block_half_z: float = 0.01
+    block_mass: float = 0.008
+    block_friction: float = 1.0
+    contact_solref: np.ndarray = field(default_factory=lambda: np.array(_DEF_SOLREF))
+    contact_solimp: np.ndarray = field(default_factory=lambda: np.array(_DEF_SOLIMP))
+    block_ncon: int = 4  # bottom corners of a flat box on a plane (mjc_PlaneBox); 0 = the pair does not collide
     joint_names: list = field(default_factory=lambda: list(JOINT_NAMES))
     source: str = ""
 
@@ -152,6 +166,8 @@ class ModelSpec:
         m.timestep = float(self.timestep)
         m.ee_body, m.wrist_body, m.cam_body = int(self.ee_body), int(self.wrist_body), int(self.cam_body)
         m.cam_fovy_deg = float(self.cam_fovy_deg)
+        m.block_half_z, m.block_mass, m.block_friction = float(self.block_half_z), float(self.block_mass), float(self.block_friction)
+        m.block_ncon = int(self.block_ncon)
 
         def put(dst, src):
             src = np.asarray(src, dtype=np.float64)
@@ -167,7 +183,7 @@ class ModelSpec:
                      "body_mass", "body_inertia", "jnt_axis", "jnt_range", "jnt_armature", "jnt_frictionloss",
                      "jnt_solref_limit", "jnt_solimp_limit", "dof_solref_friction", "dof_solimp_friction",
                      "act_kp", "act_dampratio", "act_kv", "act_ctrlrange", "act_forcerange", "ee_offset",
-                     "cam_pos", "cam_quat"):
+                     "cam_pos", "cam_quat", "contact_solref", "contact_solimp"):
             put(getattr(m, name), getattr(self, name))
         return m
 
@@ -373,7 +389,56 @@ def load_model(path: str | None = None) -> ModelSpec:
             spec.act_forcerange[k] = _floats(aa["forcerange"]) if aa.get("forcerange") else (-np.inf, np.inf)
     if seen != set(range(NJ)):
         raise ValueError("every arm joint needs one <position> actuator")
+    _read_block(root, spec)
     return spec
+
+
+def _read_block(root, spec: ModelSpec) -> None:
+    """The free block and the floor plane of the SCENE file (env01.xml:29-39): box half-size, mass, contact parameters.
+
+    MuJoCo rules applied: `inertiafromgeom="true"` makes the box geom (default density 1000) define the mass and
+    overrides the `<inertial>`; a contact pair takes the larger friction and, for equal priority and solmix, the
+    mean of solref / solimp; the pair collides iff (contype1 & conaffinity2) | (contype2 & conaffinity1)."""
+    comp = root.find("compiler")
+    from_geom = comp is not None and comp.get("inertiafromgeom", "auto") == "true"
+    blk = None
+    for wb in root.findall("worldbody"):
+        found = _find_body(wb, "block_a")
+        blk = found if found is not None else blk
+    floor = None
+    for wb in root.findall("worldbody"):
+        for g in wb.findall("geom"):
+            if g.get("type") == "plane":
+                floor = g
+    if blk is None or floor is None:
+        spec.block_ncon = 0
+        return
+    geom = blk.find("geom")
+    if geom is None or geom.get("type") != "box":
+        raise ValueError("block_a needs one box geom")
+    size = _floats(geom.get("size"))
+    if any(abs(v) > 0 for v in _floats(geom.get("pos", "0 0 0"))) or any(abs(v) > 0 for v in _floats(floor.get("pos", "0 0 0"))):
+        raise ValueError("block geom / floor offsets are not supported")
+    spec.block_half_z = size[2]
+    inert = blk.find("inertial")
+    if from_geom or inert is None:
+        spec.block_mass = float(geom.get("density", "1000")) * 8.0 * size[0] * size[1] * size[2]
+    else:
+        spec.block_mass = float(inert.get("mass"))
+
+    def par(g, name, default):
+        v = _floats(g.get(name)) if g.get(name) else []
+        return np.array(v + list(default[len(v):]))
+
+    fr = max(par(geom, "friction", (1.0, 0.005, 0.0001))[0], par(floor, "friction", (1.0, 0.005, 0.0001))[0])
+    spec.block_friction = float(fr)
+    spec.contact_solref = 0.5 * (par(geom, "solref", _DEF_SOLREF) + par(floor, "solref", _DEF_SOLREF))
+    spec.contact_solimp = 0.5 * (par(geom, "solimp", _DEF_SOLIMP) + par(floor, "solimp", _DEF_SOLIMP))
+    ct = lambda g, k: int(g.get(k, "1"))  # noqa: E731
+    collide = (ct(geom, "contype") & ct(floor, "conaffinity")) | (ct(floor, "contype") & ct(geom, "conaffinity"))
+    if int(geom.get("condim", "3")) != 3 or int(floor.get("condim", "3")) != 3:
+        raise ValueError("only condim 3 block / floor contacts are supported")
+    spec.block_ncon = 4 if collide else 0
 
 
 def reference_scene_path() -> str | None:

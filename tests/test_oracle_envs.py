@@ -157,7 +157,8 @@ def test_env06_gripper_reward_and_no_relocation():
     o.reset()
     b0 = o.gather("block").copy()
     _, r1, *_ = o.step(zeros(4))
-    assert np.array_equal(o.gather("block"), b0)                       # env06_v1.py:38: relocation is commented out
+    assert np.array_equal(o.gather("block")[:, :2], b0[:, :2])          # env06_v1.py:38: relocation is commented out
+    assert (o.gather("block")[:, 2] > 0.004).all()                      # ... the floor contact is already lifting it
     jn = np.clip((0.0 + 0.2) / 2.2, 0, 1)                                # REST_POSITION jaw = 0
     grip = 100.0 / (1.0 + np.exp(-10 * (jn - 0.3)))
     lo, hi = np.array([-2.2, -3.14158, 0, -2.0, -3.14158, -0.2]), np.array([2.2, 0.2, 3.14158, 1.8, 3.14158, 2.0])

@@ -172,3 +172,85 @@ def test_against_real_mujoco_if_available(orc):
         for k in range(per - 1):
             q, v, w = orc.substeps(q, v, w, g["ctrl"][e * per + k], 1)
             assert np.abs(q - g["qpos"][e * per + k + 1]).max() < 1e-7
+        if "block_z" in g:  # the block-floor contact restatement against MuJoCo's own 6-dof box
+            z, vz = float(g["block_z"][e * per]), float(g["block_vz"][e * per])
+            for k in range(per - 1):
+                z, vz = orc.block_substeps(z, vz, 1)
+                assert abs(z - g["block_z"][e * per + k + 1]) < 1e-7
+
+
+# ------------------------------------------------------------------------------------------ block <-> floor contact
+def _block_constants(spec):
+    """(K, B, lam(imp)) of the 16 identical pyramid rows; see oracle/so100_oracle.c:block_accel."""
+    d0, d1, w, mid, p = spec.contact_solimp
+    tc, dr = spec.contact_solref
+    K, B = 1 / (d1 * d1 * tc * tc * dr * dr), 2 / (d1 * tc)
+
+    def imp(dist):
+        x = min(abs(dist) / w, 1.0)
+        y = x ** p / mid ** (p - 1) if x <= mid else 1 - (1 - x) ** p / (1 - mid) ** (p - 1)
+        return d0 + y * (d1 - d0)
+
+    mu = spec.block_friction
+    lam = lambda i: 4 * spec.block_ncon / (2 * mu * mu * (1 + mu * mu)) * i / (1 - i)  # noqa: E731
+    return K, B, imp, lam
+
+
+def test_block_pops_out_of_the_floor_and_rests_at_the_force_balance(spec):
+    """Spawned with its centre on the plane (env01_v1.py:51-52) the box is pushed up without overshoot and comes to
+    rest where gravity equals the 16 soft rows: g + lam(imp) * (-K imp dist) = 0."""
+    o = make_oracle(1, 1)
+    z, v, zs = 0.0, 0.0, []
+    for _ in range(2000):
+        z, v = o.block_substeps(z, v, 1)
+        zs.append(z)
+    zs = np.array(zs)
+    assert (np.diff(zs) > -1e-15).all() and zs.max() < spec.block_half_z        # critically damped: monotone, never leaves
+    assert 0.009 < zs[3 * 16 - 1] < 0.0099                                       # ~3 env steps to get within 1 mm
+    K, B, imp, lam = _block_constants(spec)
+    dist = z - spec.block_half_z
+    i = imp(dist)
+    assert abs(spec.gravity[2] + lam(i) * (-K * i * dist)) < 1e-6 and abs(v) < 1e-9
+    assert abs(dist + 1.078e-4) < 2e-6                                           # rests 0.108 mm inside the plane
+
+
+def test_block_above_the_floor_is_in_free_fall_and_contact_rows_only_push(spec):
+    o = make_oracle(1, 1)
+    h, g = spec.timestep, spec.gravity[2]
+    z, v = o.block_substeps(0.05, 0.0, 10)
+    assert np.isclose(v, 10 * h * g) and np.isclose(z, 0.05 + h * h * g * 55)    # semi-implicit Euler: sum_{k<=10} k = 55
+    # moving up fast enough the reference acceleration drops below gravity: the rows carry no force (unilateral)
+    K, B, imp, lam = _block_constants(spec)
+    z0, v0 = spec.block_half_z - 1e-5, 1.0
+    assert -B * v0 - K * imp(-1e-5) * (-1e-5) < g
+    z1, v1 = o.block_substeps(z0, v0, 1)
+    assert np.isclose(v1, v0 + h * g)
+    # an applied force that cancels gravity (env03_v1.py:118-122) leaves a block at rest on the surface untouched
+    z2, v2 = o.block_substeps(spec.block_half_z, 0.0, 16, fz_applied=-spec.block_mass * g)
+    assert z2 == spec.block_half_z and v2 == 0.0
+
+
+def test_block_one_substep_matches_the_closed_form(spec):
+    o = make_oracle(1, 1)
+    K, B, imp, lam = _block_constants(spec)
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        z0, v0 = rng.uniform(0.0, 0.0102), rng.uniform(-0.3, 0.3)
+        dist, g = z0 - spec.block_half_z, spec.gravity[2]
+        a = g
+        if dist <= 0:
+            i = imp(dist)
+            aref = -B * v0 - K * i * dist
+            if g < aref:
+                a = (g + lam(i) * aref) / (1 + lam(i))
+        z1, v1 = o.block_substeps(z0, v0, 1)
+        assert np.isclose(v1, v0 + spec.timestep * a, rtol=1e-12, atol=1e-15)
+        assert np.isclose(z1, z0 + spec.timestep * v1, rtol=1e-12, atol=1e-15)
+
+
+def test_static_block_flag_restores_the_held_block(spec):
+    from so100_mujoco_rl_b200.tasks import make_task_cfg  # noqa: F401
+    o = make_oracle(2, 3, seed=4, flags=8)
+    o.reset()
+    o.step(np.zeros((3, 6), dtype=np.float32))
+    assert (o.gather("block")[:, 2] == 0.0).all() and (o.gather("block_vz") == 0.0).all()

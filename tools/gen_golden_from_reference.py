@@ -10,7 +10,8 @@ What is real and what is stubbed
     re-projection, lost-cube termination.
   * STUBBED (not installable offline): `mujoco`, `gymnasium`, `ultralytics`, `glfw`.  The stub `mujoco.mj_step`
     advances the arm with the repo's fp64 oracle physics (n-1 substeps, kinematics, 1 substep: so xpos/xmat are one
-    substep stale exactly as MuJoCo leaves them); `mj_resetData` zero-fills like MuJoCo; `MujocoEnv.reset` is
+    substep stale exactly as MuJoCo leaves them) and the free block along z with the oracle's floor-contact restatement;
+    `mj_resetData` zero-fills like MuJoCo; `MujocoEnv.reset` is
     gymnasium's (`mj_resetData` + `reset_model`); TimeLimit / auto-reset follow gymnasium + SB3 DummyVecEnv.
     => these fixtures pin the TASK LOGIC (the part the reference itself owns); the physics stays "parity unpinned".
   * RNG: the reference draws from the global np.random; here np.random.uniform / randint are patched to serve the
@@ -163,13 +164,16 @@ def _kinematics(d):
 
 
 def mj_step(model, d, nstep=1):
-    """nstep x mj_step for this scene, contact-free: arm = oracle physics; the block is held (Env01/02: declared
-    deviation D1; Env05: gravity is cancelled by qfrc_applied and its velocity is zeroed by the task, so it is exact)."""
-    q, v, w = PHYS.substeps(d.qpos[:6], d.qvel[:6], d.warm, d.ctrl, nstep - 1)
-    d.qpos[:6], d.qvel[:6], d.warm[:] = q, v, w
+    """nstep x mj_step for this scene: arm = oracle physics; block = the oracle's free-box-on-a-plane restatement
+    (gravity + qfrc_applied + soft floor contact along z; Env05 cancels gravity and zeroes the velocity itself)."""
+    def advance(n):
+        q, v, w = PHYS.substeps(d.qpos[:6], d.qvel[:6], d.warm, d.ctrl, n)
+        d.qpos[:6], d.qvel[:6], d.warm[:] = q, v, w
+        d.qpos[8], d.qvel[8] = PHYS.block_substeps(d.qpos[8], d.qvel[8], n, fz_applied=d.qfrc_applied[8])
+
+    advance(nstep - 1)
     _kinematics(d)  # forward quantities of the LAST substep are computed before its integration
-    q, v, w = PHYS.substeps(d.qpos[:6], d.qvel[:6], d.warm, d.ctrl, 1)
-    d.qpos[:6], d.qvel[:6], d.warm[:] = q, v, w
+    advance(1)
     d.time += nstep * model.opt.timestep
 
 

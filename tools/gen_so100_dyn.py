@@ -322,10 +322,11 @@ def host_constants():
     return list(out)
 
 
-N_SOLVER = 16 * NJ + 6 * NJ + 1
+N_SOLVER = 16 * NJ + 6 * NJ + 1 + 13
 CON_FIELDS = ["fr_D", "fr_B", "fr_loss", "lo", "hi", "lim_B", "lim_K", "invw", "imp0", "imp1", "imp_w", "imp_mid", "imp_pow",
               "imp_rw", "imp_rmid", "imp_r1mid"]
 ACT_FIELDS = ["kp", "kv", "ctrl_lo", "ctrl_hi", "frc_lo", "frc_hi"]
+BLK_FIELDS = ["half_z", "gz", "K", "B", "lam_scale", "imp0", "imp1", "imp_w", "imp_rw", "imp_mid", "imp_rmid", "imp_r1mid", "imp_pow"]
 
 
 def host_solver_constants():
@@ -348,6 +349,7 @@ def render_solver(sflat):
     rows = lambda k: "{" + ", ".join(f32lit(v) for v in sflat[k * NJ:(k + 1) * NJ]) + "}"  # noqa: E731
     con = ",\n      ".join(f"/* {name} */ {rows(k)}" for k, name in enumerate(CON_FIELDS))
     act = ",\n      ".join(f"/* {name} */ {rows(len(CON_FIELDS) + k)}" for k, name in enumerate(ACT_FIELDS))
+    blk = ", ".join(f"/* {name} */ {f32lit(sflat[22 * NJ + 1 + k])}" for k, name in enumerate(BLK_FIELDS))
     hexs = ",\n    ".join(", ".join(f32lit(x) for x in sflat[i:i + 6]) for i in range(0, N_SOLVER, 6))
     return f"""
 // fp32 solver / servo constants (ConC<float> then ActC<float>, so100_host_solver_constants layout); compared exactly too.
@@ -356,12 +358,13 @@ static const float kGenSolverConstants[SO100_GEN_NS] = {{
     {hexs}}};
 
 // The same numbers as literals: after unrolling they become immediates of the solver / servo instructions.
-SO_HD void so100_gen_solver_constants(ConC<float>& K, ActC<float>& A) {{
+SO_HD void so100_gen_solver_constants(ConC<float>& K, ActC<float>& A, BlkC<float>& Bk) {{
   K = ConC<float>{{
       {con}}};
   A = ActC<float>{{
       {act},
-      /* h */ {f32lit(sflat[-1])}}};
+      /* h */ {f32lit(sflat[22 * NJ])}}};
+  Bk = BlkC<float>{{{blk}}};
 }}
 """
 
