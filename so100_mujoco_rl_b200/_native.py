@@ -21,6 +21,9 @@ EXPORTS = [
     "so100_get_tick", "so100_set_tick", "so100_forward_dynamics", "so100_host_forward", "so100_get_derived",
     "so100_get_stats", "so100_bench_fp32_peak", "so100_host_constants", "so100_kernel_variant",
     "so100_host_solver_constants",
+    # include/so100_ppo.h
+    "so100_ppo_param_count", "so100_ppo_workspace_floats", "so100_ppo_act", "so100_ppo_post_step", "so100_ppo_gae",
+    "so100_ppo_grad", "so100_ppo_adam",
 ]
 
 
@@ -74,9 +77,18 @@ def lib() -> ctypes.CDLL:
     L.so100_get_derived.argtypes = [vp, dp, dp, dp]
     L.so100_get_stats.argtypes = [vp, i64p, i64p, i64p]
     L.so100_bench_fp32_peak.argtypes = [ci, ci, dp]
+    cf, u32, u64, i64 = ctypes.c_float, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int64
+    L.so100_ppo_param_count.argtypes = [ci]
+    L.so100_ppo_workspace_floats.argtypes = [ci]
+    L.so100_ppo_act.argtypes = [ci, vp, vp, ci, u64, i64, u32, ci, vp, vp, vp, vp, vp, vp]
+    L.so100_ppo_post_step.argtypes = [ci, vp, ci, vp, vp, vp, vp, vp, vp, cf, vp, vp, vp, vp]
+    L.so100_ppo_gae.argtypes = [vp, vp, vp, vp, ci, ci, cf, cf, vp, vp, vp]
+    L.so100_ppo_grad.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, ci, cf, cf, cf, ci, vp, vp, vp, vp]
+    L.so100_ppo_adam.argtypes = [ci, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, vp]
     for name in EXPORTS:
         if name not in ("so100_last_error", "so100_destroy"):
             getattr(L, name).restype = ci
+    L.so100_ppo_workspace_floats.restype = i64
     if L.so100_abi_version() != 2:
         raise ImportError("libso100_b200.so has an unexpected ABI version; rebuild it")
     _lib = L

@@ -20,6 +20,7 @@
 #include <string>
 
 #include "../../include/so100_b200.h"
+#include "../../include/so100_ppo.h"
 #include "so100_dyn.cuh"
 #define SO100_GEN_N SO100_N_DYN_CONSTANTS
 #include "so100_dyn_gen.cuh"  // model-specialised straight-line dynamics (tools/gen_so100_dyn.py)
@@ -1244,3 +1245,5 @@ int so100_bench_fp32_peak(int device, int iters, double* tflops_out) {
 }
 
 }  // extern "C"
+
+#include "so100_ppo_kernels.cuh"  // fused PPO learner kernels + their C ABI (include/so100_ppo.h)

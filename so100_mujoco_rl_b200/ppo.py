@@ -10,6 +10,14 @@ orthogonal init, Adam 3e-4 eps 1e-5, gamma 0.99, lambda 0.95, clip 0.2, vf_coef 
 batch geometry differs (n_steps x num_envs samples per rollout, large minibatches).  `state_dict_sb3()` exports the
 weights under SB3's parameter names so that `PPO.load`-style tooling can consume them.
 
+Two learners share the hyper-parameters, the rollout geometry and the `learn()` loop:
+  * `PPO`       — plain PyTorch fp32 (autograd, torch.optim.Adam, optionally replayed as a CUDA graph).  It is the
+                  numerical REFERENCE of the fused path and the only one that runs on CPU tensors (host-logic tests).
+  * `FusedPPO`  — the product path on a GPU: hand-written kernels behind include/so100_ppo.h do the rollout inference
+                  (`so100_ppo_act`), the TimeLimit bootstrap + statistics (`so100_ppo_post_step`), GAE, one fused
+                  forward + loss + backward per minibatch (`so100_ppo_grad`) and clip + Adam (`so100_ppo_adam`); torch only
+                  owns the buffers, draws the minibatch permutation and runs the NCCL all-reduce.
+
 Data parallel: one process per GPU, each with its own env shard; gradients are averaged with ONE flat all-reduce per
 minibatch (NCCL over NVLink; ~10 k fp32 values, latency bound).  The env step path itself has no collective.
 """
@@ -91,6 +99,37 @@ def compute_gae(rewards, values, dones, last_value, gamma: float, lam: float):
     return adv, adv + values
 
 
+def param_layout(obs_dim: int, act_dim: int = 6, hidden: int = 64):
+    """(name, shape) in the order of the flat parameter vector of include/so100_ppo.h."""
+    out = []
+    for tower, nout in (("pi", act_dim), ("vf", 1)):
+        out += [(f"{tower}.W1", (hidden, obs_dim)), (f"{tower}.b1", (hidden,)), (f"{tower}.W2", (hidden, hidden)),
+                (f"{tower}.b2", (hidden,)), (f"{tower}.W3", (nout, hidden)), (f"{tower}.b3", (nout,))]
+    return out + [("log_std", (act_dim,))]
+
+
+def _policy_tensors(policy: "MlpPolicy"):
+    return [policy.pi[0].weight, policy.pi[0].bias, policy.pi[2].weight, policy.pi[2].bias, policy.action_net.weight,
+            policy.action_net.bias, policy.vf[0].weight, policy.vf[0].bias, policy.vf[2].weight, policy.vf[2].bias,
+            policy.value_net.weight, policy.value_net.bias, policy.log_std]
+
+
+def pack_params(policy: "MlpPolicy") -> torch.Tensor:
+    """MlpPolicy -> flat float32 vector in the layout of include/so100_ppo.h."""
+    return torch.cat([t.detach().reshape(-1).float() for t in _policy_tensors(policy)])
+
+
+def unpack_params(flat: torch.Tensor, policy: "MlpPolicy") -> "MlpPolicy":
+    o = 0
+    with torch.no_grad():
+        for t in _policy_tensors(policy):
+            k = t.numel()
+            t.copy_(flat[o:o + k].view_as(t))
+            o += k
+    assert o == flat.numel()
+    return policy
+
+
 @dataclass
 class PPOConfig:
     n_steps: int = 32
@@ -117,7 +156,35 @@ class PPOStats:
     history: list = field(default_factory=list)  # per iteration: dict(mean_step_reward, ep_return_mean, ep_len_mean, ...)
 
 
-class PPO:
+class _LearnLoop:
+    def _sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+
+    def learn(self, total_samples: int, log_every: int = 10, callback=None) -> PPOStats:
+        per_iter = self.cfg.n_steps * self.env.num_envs * self.world
+        while self.stats.samples < total_samples:
+            self._sync(); t0 = time.perf_counter()
+            adv, ret = self.collect()
+            self._sync(); t1 = time.perf_counter()
+            info = self.update(adv, ret)
+            self._sync(); t2 = time.perf_counter()
+            s = self.stats
+            s.iterations += 1; s.samples += per_iter; s.rollout_s += t1 - t0; s.update_s += t2 - t1
+            raw, ers, els, cnt = (float(x) for x in self._acc.tolist())
+            self._acc.zero_()
+            rec = {"iter": s.iterations, "samples": s.samples, "mean_step_reward": raw / (self.cfg.n_steps * self.env.num_envs),
+                   "ep_return_mean": ers / cnt if cnt else None, "ep_len_mean": els / cnt if cnt else None,
+                   "episodes": int(cnt), "log_std_mean": self._log_std_mean(), **info}
+            s.history.append(rec)
+            if callback is not None:
+                callback(rec)
+            elif log_every and s.iterations % log_every == 0:
+                print(rec, flush=True)
+        return self.stats
+
+
+class PPO(_LearnLoop):
     """`env` is a BatchedSo100Env-like object: .num_envs, .obs_dim, .act_dim, .device, reset() -> obs [N, od],
     step(actions [N, 6]) -> object with obs, reward, terminated, truncated, terminal_obs, ep_return, ep_len."""
 
@@ -247,28 +314,108 @@ class PPO:
         pg, vl, kl = self._last_info.tolist()
         return {"pg_loss": pg, "v_loss": vl, "approx_kl": kl}
 
-    def _sync(self):
-        if self.device.type == "cuda":
-            torch.cuda.synchronize(self.device)
+    def _log_std_mean(self) -> float:
+        return float(self.policy.log_std.mean())
 
-    def learn(self, total_samples: int, log_every: int = 10, callback=None) -> PPOStats:
-        per_iter = self.cfg.n_steps * self.env.num_envs * self.world
-        while self.stats.samples < total_samples:
-            self._sync(); t0 = time.perf_counter()
-            adv, ret = self.collect()
-            self._sync(); t1 = time.perf_counter()
-            info = self.update(adv, ret)
-            self._sync(); t2 = time.perf_counter()
-            s = self.stats
-            s.iterations += 1; s.samples += per_iter; s.rollout_s += t1 - t0; s.update_s += t2 - t1
-            raw, ers, els, cnt = (float(x) for x in self._acc.tolist())
-            self._acc.zero_()
-            rec = {"iter": s.iterations, "samples": s.samples, "mean_step_reward": raw / (self.cfg.n_steps * self.env.num_envs),
-                   "ep_return_mean": ers / cnt if cnt else None, "ep_len_mean": els / cnt if cnt else None,
-                   "episodes": int(cnt), "log_std_mean": float(self.policy.log_std.mean()), **info}
-            s.history.append(rec)
-            if callback is not None:
-                callback(rec)
-            elif log_every and s.iterations % log_every == 0:
-                print(rec, flush=True)
-        return self.stats
+
+class FusedPPO(_LearnLoop):
+    """PPO on the hand-written kernels of include/so100_ppo.h; same interface and hyper-parameters as `PPO`.
+
+    `env` must be a `BatchedSo100Env` (CUDA tensors with stable addresses: the kernels read `env.obs` etc. in place).
+    Initial weights are those `PPO` would start from for the same seed (torch's orthogonal init), so the two learners
+    can be compared step by step."""
+
+    def __init__(self, env, cfg: PPOConfig | None = None, env_offset: int = 0):
+        import ctypes
+
+        from . import _native
+        self.env, self.cfg = env, cfg or PPOConfig()
+        self.device = env.device
+        if self.device.type != "cuda":
+            raise ValueError("FusedPPO runs on CUDA devices only (use PPO for CPU tensors)")
+        self._L, self._check, self._ct = _native.lib(), _native.check, ctypes
+        self.od, n, T = env.obs_dim, env.num_envs, self.cfg.n_steps
+        self.n_params = self._check(self._L.so100_ppo_param_count(self.od))
+        torch.manual_seed(self.cfg.seed)
+        self.params = pack_params(MlpPolicy(self.od, env.act_dim)).to(self.device)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if self.world > 1:
+            dist.broadcast(self.params, src=0)
+        f = dict(device=self.device, dtype=torch.float32)
+        self.exp_avg, self.exp_avg_sq = torch.zeros(self.n_params, **f), torch.zeros(self.n_params, **f)
+        self.grad = torch.zeros(self.n_params, **f)
+        self.step_count = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self.workspace = torch.zeros(int(self._L.so100_ppo_workspace_floats(self.od)), **f)
+        self.loss = torch.zeros(3, **f)
+        self.buf = {"obs": torch.zeros((T, n, self.od), **f), "act": torch.zeros((T, n, env.act_dim), **f), "logp": torch.zeros((T, n), **f),
+                    "val": torch.zeros((T, n), **f), "rew": torch.zeros((T, n), **f), "done": torch.zeros((T, n), **f)}
+        self.adv, self.ret = torch.zeros((T, n), **f), torch.zeros((T, n), **f)
+        self.act_clip, self.last_val = torch.zeros((n, env.act_dim), **f), torch.zeros(n, **f)
+        self._acc = torch.zeros(4, device=self.device, dtype=torch.float64)
+        self.env_offset, self.tick = int(env_offset), 0
+        self.obs = env.reset()
+        self.stats = PPOStats()
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def act(self, obs: torch.Tensor, deterministic: bool = False):
+        """Policy inference on arbitrary observations [n, od] -> (raw action, clipped action, log-prob, value)."""
+        n = obs.shape[0]
+        f = dict(device=self.device, dtype=torch.float32)
+        a, c, lp, v = torch.empty((n, 6), **f), torch.empty((n, 6), **f), torch.empty(n, **f), torch.empty(n, **f)
+        self.tick += 1
+        self._check(self._L.so100_ppo_act(self.od, self.params.data_ptr(), obs.contiguous().data_ptr(), n, self.cfg.seed, self.env_offset,
+                                          self.tick, int(deterministic), a.data_ptr(), c.data_ptr(), lp.data_ptr(), v.data_ptr(), None,
+                                          self._stream()))
+        return a, c, lp, v
+
+    @torch.no_grad()
+    def collect(self):
+        cfg, b, L, st, P = self.cfg, self.buf, self._L, self._stream(), self.params.data_ptr()
+        n = self.env.num_envs
+        for t in range(cfg.n_steps):
+            self.tick += 1
+            self._check(L.so100_ppo_act(self.od, P, self.obs.data_ptr(), n, cfg.seed, self.env_offset, self.tick, 0, b["act"][t].data_ptr(),
+                                        self.act_clip.data_ptr(), b["logp"][t].data_ptr(), b["val"][t].data_ptr(), b["obs"][t].data_ptr(), st))
+            r = self.env.step(self.act_clip)  # SB3 clips Box actions before env.step (the log-prob is of the raw action)
+            self._check(L.so100_ppo_post_step(self.od, P, n, r.reward.data_ptr(), r.terminated.data_ptr(), r.truncated.data_ptr(),
+                                              r.terminal_obs.data_ptr(), r.ep_return.data_ptr(), r.ep_len.data_ptr(), cfg.gamma,
+                                              b["rew"][t].data_ptr(), b["done"][t].data_ptr(), self._acc.data_ptr(), st))
+            self.obs = r.obs
+        self._check(L.so100_ppo_act(self.od, P, self.obs.data_ptr(), n, cfg.seed, self.env_offset, self.tick, 1, None, None, None,
+                                    self.last_val.data_ptr(), None, st))
+        self._check(L.so100_ppo_gae(b["rew"].data_ptr(), b["val"].data_ptr(), b["done"].data_ptr(), self.last_val.data_ptr(), cfg.n_steps, n,
+                                    cfg.gamma, cfg.gae_lambda, self.adv.data_ptr(), self.ret.data_ptr(), st))
+        return self.adv, self.ret
+
+    def minibatch_step(self, idx: torch.Tensor, adv: torch.Tensor, ret: torch.Tensor):
+        """One optimiser step on the samples idx (int64, device) of the flattened rollout buffers."""
+        cfg, b, L, st = self.cfg, self.buf, self._L, self._stream()
+        self._check(L.so100_ppo_grad(self.od, self.params.data_ptr(), b["obs"].data_ptr(), b["act"].data_ptr(), b["logp"].data_ptr(),
+                                     adv.data_ptr(), ret.data_ptr(), idx.data_ptr(), idx.numel(), cfg.clip_range, cfg.vf_coef, cfg.ent_coef,
+                                     int(cfg.normalize_advantage), self.workspace.data_ptr(), self.grad.data_ptr(), self.loss.data_ptr(), st))
+        if self.world > 1:
+            dist.all_reduce(self.grad)  # ~10^4 floats over NVLink: latency bound
+        self._check(L.so100_ppo_adam(self.n_params, self.params.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                     self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(), 1.0 / self.world, cfg.max_grad_norm, cfg.lr,
+                                     0.9, 0.999, 1e-5, st))
+
+    def update(self, adv, ret):
+        cfg = self.cfg
+        total = adv.numel()
+        mb = total // cfg.n_minibatches
+        for _ in range(cfg.n_epochs):
+            perm = torch.randperm(total, device=self.device)
+            for k in range(cfg.n_minibatches):
+                self.minibatch_step(perm[k * mb:(k + 1) * mb], adv, ret)
+        pg, vl, kl = self.loss.tolist()
+        return {"pg_loss": pg, "v_loss": vl, "approx_kl": kl}
+
+    def _log_std_mean(self) -> float:
+        return float(self.params[-6:].mean())
+
+    @property
+    def policy(self) -> MlpPolicy:
+        """The current weights as a torch MlpPolicy (export, evaluation, tests)."""
+        return unpack_params(self.params, MlpPolicy(self.od, 6).to(self.device))

@@ -1,4 +1,4 @@
-"""The C-ABI library loads on a CPU-only machine and exports every symbol include/so100_b200.h declares."""
+"""The C-ABI library loads on a CPU-only machine and exports every symbol include/*.h declares."""
 import ctypes
 import os
 import re
@@ -9,9 +9,12 @@ from conftest import ROOT
 
 
 def _header_symbols():
-    src = open(os.path.join(ROOT, "include", "so100_b200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(so100_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for h in ("so100_b200.h", "so100_ppo.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(so100_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_symbols_are_exported(native_lib):

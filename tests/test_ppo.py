@@ -100,3 +100,18 @@ def test_truncation_bootstraps_with_terminal_value():
     r_env = algo.buf["rew"][1]
     assert (algo.buf["done"][1] == 1).all()
     assert ((r_env - 0.99 * 3.0) <= 1e-6).all()  # raw toy rewards are <= 0
+
+
+def test_flat_parameter_layout_matches_the_c_abi(native_lib):
+    """pack_params / unpack_params / param_layout agree with so100_ppo_param_count (include/so100_ppo.h)."""
+    from so100_mujoco_rl_b200.ppo import pack_params, param_layout, unpack_params
+    for od, expect in ((15, 10829), (8, 9933)):
+        assert native_lib.so100_ppo_param_count(od) == expect
+        assert sum(int(np.prod(s)) for _, s in param_layout(od)) == expect
+        p = MlpPolicy(od, 6)
+        flat = pack_params(p)
+        assert flat.numel() == expect and torch.equal(flat[-6:], p.log_std.detach())
+        assert torch.equal(flat[:64 * od].view(64, od), p.pi[0].weight.detach())
+        q = unpack_params(flat * 2, MlpPolicy(od, 6))
+        assert torch.equal(q.value_net.weight, 2 * p.value_net.weight) and torch.equal(q.pi[2].bias, 2 * p.pi[2].bias)
+    assert native_lib.so100_ppo_param_count(17) < 0 and native_lib.so100_ppo_workspace_floats(15) == 1024 * 10833 + 8

@@ -28,12 +28,13 @@ def main():
     ap.add_argument("--epochs", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--max-episode-steps", type=int, default=0)
+    ap.add_argument("--learner", default="fused", choices=["fused", "torch"], help="fused = include/so100_ppo.h kernels; torch = the PyTorch reference learner")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out"))
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
     from so100_mujoco_rl_b200.batched_env import BatchedSo100Env
-    from so100_mujoco_rl_b200.ppo import PPO, PPOConfig
+    from so100_mujoco_rl_b200.ppo import PPO, FusedPPO, PPOConfig
     from so100_mujoco_rl_b200.sharding import dist_env
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
@@ -42,7 +43,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     env = BatchedSo100Env(args.env, args.num_envs, device=local_rank, seed=args.seed, env_offset=rank * args.num_envs,
                           max_episode_steps=args.max_episode_steps or None)
-    algo = PPO(env, PPOConfig(n_steps=args.n_steps, n_minibatches=args.minibatches, n_epochs=args.epochs, seed=args.seed))
+    cfg = PPOConfig(n_steps=args.n_steps, n_minibatches=args.minibatches, n_epochs=args.epochs, seed=args.seed)
+    algo = FusedPPO(env, cfg, env_offset=rank * args.num_envs) if args.learner == "fused" else PPO(env, cfg)
     hist = []
 
     def cb(rec):
@@ -52,7 +54,7 @@ def main():
     t0 = time.time()
     st = algo.learn(int(args.samples), log_every=0, callback=cb)
     wall = time.time() - t0
-    graphed = algo._graph is not None
+    graphed = getattr(algo, "_graph", None) is not None
     if world > 1:
         # a captured CUDA graph holds NCCL kernels: drop it and drain the device before tearing the group down
         # (destroying the communicator under a live graph can hang at exit)
@@ -62,12 +64,12 @@ def main():
     if rank != 0:
         sys.stdout.flush()
         os._exit(0)
-    out = {"env": args.env, "num_envs": args.num_envs, "n_gpus": world, "cuda_graph_update": graphed, "n_steps": args.n_steps, "samples": st.samples, "wall_s": wall,
+    out = {"env": args.env, "learner": args.learner, "num_envs": args.num_envs, "n_gpus": world, "cuda_graph_update": graphed, "n_steps": args.n_steps, "samples": st.samples, "wall_s": wall,
            "rollout_s": st.rollout_s, "update_s": st.update_s, "samples_per_s": st.samples / wall,
            "rollout_env_steps_per_s": st.samples / st.rollout_s, "history": hist[:: max(1, len(hist) // 200)] + hist[-1:],
            "kernel_variant": env.kernel_variant, "stats": env.stats()}
     os.makedirs(args.out, exist_ok=True)
-    path = os.path.join(args.out, f"ppo_{args.env}_s{args.seed}" + (f"_{world}gpu" if world > 1 else "") + ".json")
+    path = os.path.join(args.out, f"ppo_{args.env}_{args.learner}_s{args.seed}" + (f"_{world}gpu" if world > 1 else "") + ".json")
     json.dump(out, open(path, "w"), indent=1)
     print("wrote", path, {k: out[k] for k in ("n_gpus", "samples", "wall_s", "rollout_s", "update_s", "samples_per_s", "cuda_graph_update")})
     if world > 1:
