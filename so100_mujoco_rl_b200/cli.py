@@ -36,8 +36,16 @@ def cli(ctx, algorithm, model_path):
 @click.option("--n-steps", default=32, show_default=True)
 @click.option("--seed", default=0, show_default=True)
 @click.option("--out", default="models", show_default=True, help="output folder (reference: models/<Env>_<Algo>/)")
+@click.option("--learner", "learner_kind", type=click.Choice(["fused", "torch"]), default="fused", show_default=True,
+              help="fused = hand-written PPO kernels (include/so100_ppo.h); torch = the PyTorch reference learner")
+@click.option("--eval-freq", default=2_000_000, show_default=True, help="samples between evaluations (main.py:221 uses 20000 for its single env)")
+@click.option("--eval-envs", default=64, show_default=True, help="envs of the evaluation simulator (0 = no evaluation)")
+@click.option("--eval-steps", default=4000, show_default=True, help="env steps per evaluation (one Env01 episode)")
+@click.option("--save-freq", default=4_000_000, show_default=True, help="samples between checkpoints (main.py:228 uses 40000 for its single env)")
+@click.option("--tensorboard-log", default="logs", show_default=True, help="TensorBoard folder (main.py:30, :62); empty = off")
 @click.pass_context
-def train(ctx, environment, num_envs, device, trainer, total_timesteps, n_steps, seed, out):
+def train(ctx, environment, num_envs, device, trainer, total_timesteps, n_steps, seed, out, learner_kind, eval_freq, eval_envs,
+          eval_steps, save_freq, tensorboard_log):
     algo = ctx.obj["ALGORITHM_NAME"]
     folder = os.path.join(out, f"{environment}_{algo}")
     os.makedirs(folder, exist_ok=True)
@@ -54,17 +62,36 @@ def train(ctx, environment, num_envs, device, trainer, total_timesteps, n_steps,
         raise click.UsageError("the native trainer implements PPO; use --trainer sb3 for other algorithms")
     import torch
     from .batched_env import BatchedSo100Env
-    from .ppo import PPO, PPOConfig
+    from .callbacks import TrainCallbacks
+    from .ppo import PPO, FusedPPO, PPOConfig
     env = BatchedSo100Env(environment, num_envs, device=device, seed=seed)
-    learner = PPO(env, PPOConfig(n_steps=n_steps, seed=seed))
+    cfg = PPOConfig(n_steps=n_steps, seed=seed)
+    learner = FusedPPO(env, cfg) if learner_kind == "fused" else PPO(env, cfg)
     if ctx.obj["MODEL_PATH"]:
-        learner.policy.load_state_dict(torch.load(ctx.obj["MODEL_PATH"], map_location=env.device)["policy"])
+        learner.load_policy(_load_policy(ctx.obj["MODEL_PATH"], env.obs_dim, env.device))
+    # main.py:211-232: EvalCallback(eval_freq=20000) + reward threshold 6000 + no-improvement stop, CheckpointCallback(40000)
+    eval_env = BatchedSo100Env(environment, eval_envs, device=device, seed=seed + 1) if eval_envs > 0 else None
+    cb = TrainCallbacks(learner, folder, f"{environment}_{algo}", eval_env=eval_env, eval_freq=eval_freq, eval_steps=eval_steps,
+                        save_freq=save_freq, tensorboard_dir=tensorboard_log or None)
     t0 = time.time()
-    stats = learner.learn(total_timesteps, log_every=10)
-    torch.save({"policy": learner.policy.state_dict(), "sb3_policy_state_dict": learner.policy.state_dict_sb3(),
-                "env": environment, "history": stats.history}, os.path.join(folder, "final_model.pt"))
-    click.echo(json.dumps({"samples": stats.samples, "wall_s": time.time() - t0, "rollout_s": stats.rollout_s,
-                           "update_s": stats.update_s, "last": stats.history[-1] if stats.history else None}))
+    stats = learner.learn(total_timesteps, log_every=0, callback=cb)
+    cb.save("final_model")
+    cb.close()
+    click.echo(json.dumps({"samples": stats.samples, "wall_s": time.time() - t0, "rollout_s": stats.rollout_s, "update_s": stats.update_s,
+                           "best_eval": cb.best, "stopped": cb.stop_reason, "last": stats.history[-1] if stats.history else None}))
+
+
+def _load_policy(path, obs_dim, device):
+    """A policy saved by this package (.pt) or a Stable-Baselines3 style archive (.zip, policy.pth inside)."""
+    import torch
+    from .callbacks import load_sb3_zip
+    from .ppo import MlpPolicy
+    policy = MlpPolicy(obs_dim, 6)
+    if path.endswith(".zip"):
+        policy.load_state_dict_sb3(load_sb3_zip(path))
+    else:
+        policy.load_state_dict(torch.load(path, map_location="cpu")["policy"])
+    return policy.to(device)
 
 
 def _evaluate(ctx, environment, num_envs, device, steps):
@@ -74,8 +101,7 @@ def _evaluate(ctx, environment, num_envs, device, steps):
     if not ctx.obj["MODEL_PATH"]:
         raise click.UsageError("-m/--model is required")
     env = BatchedSo100Env(environment, num_envs, device=device, seed=123)
-    policy = MlpPolicy(env.obs_dim, env.act_dim).to(env.device)
-    policy.load_state_dict(torch.load(ctx.obj["MODEL_PATH"], map_location=env.device)["policy"])
+    policy = _load_policy(ctx.obj["MODEL_PATH"], env.obs_dim, env.device)
     obs, total = env.reset(), torch.zeros(num_envs, device=env.device)
     with torch.no_grad():
         for _ in range(steps):

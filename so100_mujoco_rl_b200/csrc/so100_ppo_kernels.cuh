@@ -283,33 +283,22 @@ __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rew,
 }
 
 // ------------------------------------------------------------------------------------------------ minibatch gradient
-// mean and 1 / (unbiased std + 1e-8) of adv[idx[0..mb)]  (single CTA, fp64 accumulation, two passes)
-__global__ void __launch_bounds__(1024) adv_stats_kernel(const float* __restrict__ adv, const int64_t* __restrict__ idx, int mb, float* stats) {
-  __shared__ double red[32];
-  __shared__ double s_mean;
+// Per-CTA partial sums (fp64) of adv[idx] and its square over the minibatch; the gradient kernel combines the partials in
+// a fixed order (deterministic) into mean and 1 / (unbiased std + 1e-8).
+constexpr int kStatCtas = 128;
+__global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict__ adv, const int64_t* __restrict__ idx, int mb, double* part) {
+  __shared__ double red[2][8];
   const int tid = threadIdx.x;
-  auto block_sum = [&](double v) -> double {
+  double s = 0.0, q = 0.0;
+  for (int e = blockIdx.x * 256 + tid; e < mb; e += gridDim.x * 256) { const double a = (double)adv[idx[e]]; s += a; q += a * a; }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((tid & 31) == 0) red[tid >> 5] = v;
-    __syncthreads();
-    double s = 0.0;
-    for (int w = 0; w < 32; w++) s += red[w];
-    return s;
-  };
-  double s = 0.0;
-  for (int e = tid; e < mb; e += 1024) s += (double)adv[idx[e]];
-  s = block_sum(s);
-  if (tid == 0) s_mean = s / mb;
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((tid & 31) == 0) { red[0][tid >> 5] = s; red[1][tid >> 5] = q; }
   __syncthreads();
-  const double mean = s_mean;
-  double q = 0.0;
-  for (int e = tid; e < mb; e += 1024) { const double d = (double)adv[idx[e]] - mean; q += d * d; }
-  q = block_sum(q);
-  if (tid == 0) {
-    stats[0] = (float)mean;
-    stats[1] = (float)(1.0 / (sqrt(q / (mb > 1 ? mb - 1 : 1)) + 1e-8));
+  if (tid < 2) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += red[tid][w];
+    part[2 * blockIdx.x + tid] = t;
   }
 }
 
@@ -322,7 +311,7 @@ constexpr int kGradSmemFloats = 2 * tower_floats(true)  // weights of both tower
 
 __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __restrict__ P, const float* __restrict__ obs, const float* __restrict__ act,
                                                     const float* __restrict__ logp_old, const float* __restrict__ adv, const float* __restrict__ ret,
-                                                    const int64_t* __restrict__ idx, int mb, const float* __restrict__ adv_stats, float clip,
+                                                    const int64_t* __restrict__ idx, int mb, const double* __restrict__ adv_part, float clip,
                                                     float vf_coef, float ent_coef, int normalize, float* __restrict__ gpart) {
   extern __shared__ __align__(16) float sm[];
   TowerS T[2];
@@ -352,7 +341,14 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
   load_tower(L, P, 0, T[0], true);
   load_tower(L, P, 1, T[1], true);
   if (tid < ACT) ls[tid] = P[L.log_std + tid];
-  const float a_mean = normalize ? adv_stats[0] : 0.0f, a_rstd = normalize ? adv_stats[1] : 1.0f;
+  float a_mean = 0.0f, a_rstd = 1.0f;
+  if (normalize) {  // every thread combines the partials in the same order: identical values everywhere
+    double s1 = 0.0, s2 = 0.0;
+    for (int c = 0; c < kStatCtas; c++) { s1 += adv_part[2 * c]; s2 += adv_part[2 * c + 1]; }
+    const double mean = s1 / mb, var = fmax(s2 - s1 * mean, 0.0) / (mb > 1 ? mb - 1 : 1);
+    a_mean = (float)mean;
+    a_rstd = (float)(1.0 / (sqrt(var) + 1e-8));
+  }
   const float inv_mb = 1.0f / (float)mb;
 
   // gradient accumulators, persistent over the CTA's tiles; each thread owns fixed parameters of both towers
@@ -601,7 +597,7 @@ int so100_ppo_param_count(int obs_dim) {
 }
 int64_t so100_ppo_workspace_floats(int obs_dim) {
   const int n = so100_ppo_param_count(obs_dim);
-  return n < 0 ? n : (int64_t)SO100_PPO_MAX_CTAS * (n + 4) + 8;
+  return n < 0 ? n : (int64_t)SO100_PPO_MAX_CTAS * (n + 4) + 4 * ppo::kStatCtas;
 }
 
 static int ppo_smem_optin(const void* fn, int floats) {  // per device; the call is cheap, so it is simply repeated
@@ -661,8 +657,9 @@ int so100_ppo_grad(int obs_dim, const float* params, const float* obs, const flo
   int grid = ntiles < sms ? ntiles : sms;  // persistent: one CTA per SM
   if (grid > SO100_PPO_MAX_CTAS) grid = SO100_PPO_MAX_CTAS;
   cudaStream_t st = (cudaStream_t)stream;
-  float* stats = workspace + (size_t)SO100_PPO_MAX_CTAS * (L.total + 4);
-  if (normalize) ppo::adv_stats_kernel<<<1, 1024, 0, st>>>(adv, idx, mb, stats);
+  // fp64 partials behind the gradient partials; (total + 4) * MAX_CTAS floats is a multiple of 8 bytes
+  double* stats = reinterpret_cast<double*>(workspace + (size_t)SO100_PPO_MAX_CTAS * (L.total + 4));
+  if (normalize) ppo::adv_stats_kernel<<<ppo::kStatCtas, 256, 0, st>>>(adv, idx, mb, stats);
   ppo::grad_kernel<<<grid, ppo::NT, ppo::kGradSmemFloats * 4, st>>>(L, params, obs, act, logp_old, adv, ret, idx, mb, stats, clip_range, vf_coef,
                                                                    ent_coef, normalize, workspace);
   ppo::reduce_kernel<<<(L.total + 3 + 255) / 256, 256, 0, st>>>(workspace, grid, L.total, mb, grad, loss_out);

@@ -71,6 +71,19 @@ class MlpPolicy(nn.Module):
         entropy = (0.5 + 0.5 * math.log(2 * math.pi) + log_std).sum(-1).expand(obs.shape[0])
         return self.value(obs), self.log_prob(mean, log_std, actions), entropy
 
+    def load_state_dict_sb3(self, sd: dict) -> "MlpPolicy":
+        """Inverse of state_dict_sb3: accepts a stable_baselines3 ActorCriticPolicy state dict (policy.pth of a .zip)."""
+        with torch.no_grad():
+            self.log_std.copy_(sd["log_std"])
+            for name, seq in (("policy_net", self.pi), ("value_net", self.vf)):
+                for idx in (0, 2):
+                    seq[idx].weight.copy_(sd[f"mlp_extractor.{name}.{idx}.weight"])
+                    seq[idx].bias.copy_(sd[f"mlp_extractor.{name}.{idx}.bias"])
+            for name, lin in (("action_net", self.action_net), ("value_net", self.value_net)):
+                lin.weight.copy_(sd[f"{name}.weight"])
+                lin.bias.copy_(sd[f"{name}.bias"])
+        return self
+
     def state_dict_sb3(self) -> dict:
         """Weights under stable_baselines3.common.policies.ActorCriticPolicy's parameter names."""
         sd = {"log_std": self.log_std.detach().clone()}
@@ -179,6 +192,8 @@ class _LearnLoop:
             s.history.append(rec)
             if callback is not None:
                 callback(rec)
+                if getattr(callback, "stop", False):  # callbacks.TrainCallbacks: reward threshold / no improvement
+                    break
             elif log_every and s.iterations % log_every == 0:
                 print(rec, flush=True)
         return self.stats
@@ -317,6 +332,9 @@ class PPO(_LearnLoop):
     def _log_std_mean(self) -> float:
         return float(self.policy.log_std.mean())
 
+    def load_policy(self, policy: MlpPolicy) -> None:
+        self.policy.load_state_dict(policy.state_dict())
+
 
 class FusedPPO(_LearnLoop):
     """PPO on the hand-written kernels of include/so100_ppo.h; same interface and hyper-parameters as `PPO`.
@@ -414,6 +432,11 @@ class FusedPPO(_LearnLoop):
 
     def _log_std_mean(self) -> float:
         return float(self.params[-6:].mean())
+
+    def load_policy(self, policy: MlpPolicy) -> None:
+        """Continue from the weights of a torch MlpPolicy (Adam moments restart)."""
+        self.params.copy_(pack_params(policy).to(self.device))
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.step_count.zero_()
 
     @property
     def policy(self) -> MlpPolicy:

