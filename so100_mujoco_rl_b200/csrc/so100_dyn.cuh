@@ -317,14 +317,8 @@ SO_HD void block_substep(const BlkC<T>& Kb, T h, T& z, T& vz) {
   z += h * vz;
 }
 
-// Exact minimiser over x of  m x^2/2 - c x + huber_f(x - af)   (friction-loss row only), closed form:
-//   t = c - m af;  F = clamp(t * D/(m+D), -loss, loss);  x = af + (t - F)/m          (rm = 1/m, kap = D/(m+D))
-template <typename T>
-SO_HD T solve1(T m, T rm, T kap, T c, T af, T loss) {
-  T t = c - m * af;
-  T F = so_clamp(t * kap, -loss, loss);
-  return af + (t - F) * rm;
-}
+// Friction-loss row on one dof: the exact minimiser over x of  m x^2/2 - c x + huber_f(x - af)  is closed form,
+//   t = c - m af;  F = clamp(t * D/(m+D), -loss, loss);  x = af + (t - F)/m        (used inline in solve_qacc)
 
 // Joint j is outside its range: one unilateral limit row (MuJoCo mj_instantiateLimit) joins the friction row on this
 // dof.  Evaluated ONCE per substep; the sweeps only see (xl, sDl, rm2, kap2).  With random actions the arm sits on
@@ -351,16 +345,22 @@ SO_HD void limit_row(const ConC<T>& K, int j, T m, T q, T qc, T qd, T& xl, T& sD
 // qc[] is the compensation term of the fp32 position integration (zeros when T = double).
 template <typename T>
 SO_HD T solve_qacc(const ConC<T>& K, const T* M, const T* b, const T* q, const T* qc, const T* qd, T* a, int sweeps) {
-  T af[SO_NJ], rm[SO_NJ], kap[SO_NJ], xl[SO_NJ], sDl[SO_NJ], rm2[SO_NJ], kap2[SO_NJ];
+  // per-dof constants of this substep.  Friction row only:  t = c - m af,  x = af + (t - clamp(t kap, +-loss)) / m
+  //   = (af + t rm) - clamp(t kr, +-lr)   with kr = kap rm, lr = loss rm;  bp = b - m af folds "- m af" into the sum.
+  T af[SO_NJ], rm[SO_NJ], kr[SO_NJ], lr[SO_NJ], bp[SO_NJ], xl[SO_NJ], sDl[SO_NJ], rm2[SO_NJ], kap2[SO_NJ], dl[SO_NJ];
 #pragma unroll
   for (int j = 0; j < SO_NJ; j++) {
     T m = M[midx(j, j)];
     af[j] = -K.fr_B[j] * qd[j];
     rm[j] = so_rcp(m);
-    kap[j] = K.fr_D[j] * so_rcp(m + K.fr_D[j]);
-    xl[j] = T(0); sDl[j] = T(0); rm2[j] = T(0); kap2[j] = T(0);
-    if ((q[j] - K.lo[j]) - qc[j] < T(0) || (K.hi[j] - q[j]) + qc[j] < T(0))
+    kr[j] = K.fr_D[j] * so_rcp(m + K.fr_D[j]) * rm[j];
+    lr[j] = K.fr_loss[j] * rm[j];
+    bp[j] = b[j] - m * af[j];
+    xl[j] = T(0); sDl[j] = T(0); rm2[j] = T(0); kap2[j] = T(0); dl[j] = T(0);
+    if ((q[j] - K.lo[j]) - qc[j] < T(0) || (K.hi[j] - q[j]) + qc[j] < T(0)) {
       limit_row(K, j, m, q[j], qc[j], qd[j], xl[j], sDl[j], rm2[j], kap2[j]);
+      dl[j] = (sDl[j] < T(0) ? -sDl[j] : sDl[j]) * (xl[j] - af[j]);  // t with the limit row active = t + Dl (xl - af)
+    }
   }
   T last = T(0), amax = T(1);
 #pragma unroll
@@ -372,20 +372,20 @@ SO_HD T solve_qacc(const ConC<T>& K, const T* M, const T* b, const T* q, const T
     T big = T(0);
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {
-      // c_j = b_j - sum_{k != j} M_jk a_k, as two independent chains
-      T m = M[midx(j, j)], c0 = b[j], c1 = T(0);
+      // t = bp_j - sum_{k != j} M_jk a_k; the coordinate updated last (j - 1) enters last: one fma on the critical path
+      constexpr int NJ = SO_NJ;
+      const int prev = (j + NJ - 1) % NJ;
+      T t = bp[j];
 #pragma unroll
       for (int k = 0; k < SO_NJ; k++) {
-        if (k == j) continue;
-        T mjk = k < j ? M[midx(j, k)] : M[midx(k, j)];
-        if (k & 1) c1 -= mjk * a[k];
-        else c0 -= mjk * a[k];
+        if (k == j || k == prev) continue;
+        t -= (k < j ? M[midx(j, k)] : M[midx(k, j)]) * a[k];
       }
-      T cc = c0 + c1;
-      T x = solve1(m, rm[j], kap[j], cc, af[j], K.fr_loss[j]);
+      t -= (prev < j ? M[midx(j, prev)] : M[midx(prev, j)]) * a[prev];
+      T x = so_fma(t, rm[j], af[j]) - so_clamp(t * kr[j], -lr[j], lr[j]);
       if (sDl[j] != T(0)) {  // limit row present: active iff the limit-free minimiser violates it
-        T Dl = sDl[j] < T(0) ? -sDl[j] : sDl[j];
-        T x2 = solve1(m + Dl, rm2[j], kap2[j], cc + Dl * xl[j], af[j], K.fr_loss[j]);
+        T t2 = t + dl[j];
+        T x2 = af[j] + (t2 - so_clamp(t2 * kap2[j], -K.fr_loss[j], K.fr_loss[j])) * rm2[j];
         x = sDl[j] * (x - xl[j]) < T(0) ? x2 : x;
       }
       if (TRACK) {
