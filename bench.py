@@ -279,8 +279,10 @@ def main():
             threads = os.cpu_count() or 1
             ncpu = args.cpu_envs or 256 * threads
             rate, k, dt = cpu_oracle_rate(task, ncpu, 12.0, threads)
+            one, k1, dt1 = cpu_oracle_rate(task, 1, 2.0, 1)  # BASELINE config 1: ONE env on one core, as the reference steps it
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"{ncpu} envs x {k} steps ({dt:.1f} s) of the same workload on the fp64 C oracle"}
+                                    "sample": f"{ncpu} envs x {k} steps ({dt:.1f} s) of the same workload on the fp64 C oracle",
+                                    "per_core": rate / threads, "single_env_single_core": one}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
