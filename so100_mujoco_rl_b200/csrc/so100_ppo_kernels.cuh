@@ -6,20 +6,25 @@
 // 2x64 tanh towers (pi: od -> 64 -> 64 -> 6, vf: od -> 64 -> 64 -> 1) and a state-independent log_std.
 //
 // Gradient kernel: persistent CTAs (one per SM, 256 threads), each looping over tiles of 64 samples.  Both towers'
-// weights stay in shared memory for the whole kernel (77 KB); a tile's activations live in shared memory in two
+// weights stay in shared memory for the whole kernel (88 KB); a tile's activations live in shared memory in two
 // layouts, [feature][sample] for the forward / back-propagation products and [sample][feature] for the weight-gradient
-// products, so that every product is a 64x64 register-tiled GEMM (4x4 outputs per thread) fed by 16-byte shared loads
-// of which one operand is a warp broadcast.  Weight gradients accumulate in REGISTERS across all tiles of the CTA
-// (each thread owns a fixed set of parameters) and leave the SM once, as per-CTA partials; a second kernel adds the
-// partials in a fixed order, so the result is deterministic.  fp32 CUDA cores throughout: K = 64 products with exact
-// fp32 parity against torch's autograd are the contract here (a tcgen05 TF32 variant is the next step).
+// products, so that every product is a 64x64x64 GEMM with both operands K-major.  The GEMMs run on the tensor cores
+// as warp-level m16n8k8 TF32 MMAs with the 3xTF32 split (x = hi + lo, D += lo*hi + hi*lo + hi*hi, fp32 accumulate),
+// which keeps fp32-level parity against torch's autograd; each warp owns a 16x32 slab of the output, and every
+// fragment load is a conflict-free 4-byte shared load (row stride 72 = 8 mod 32).  The first version of this kernel did
+// the same products on the FP32 pipes with 4x4 register tiles and was bound by shared-memory bandwidth (one 16-byte
+// load per 8 FMAs; profiles/r1_ppo_grad_ncu_raw.csv); the MMA path moves 5x fewer bytes per flop.  Weight gradients
+// accumulate in REGISTERS (MMA accumulator fragments) across all tiles of the CTA and leave the SM once, as per-CTA
+// partials; a second kernel adds the partials in a fixed order, so the result is deterministic.  A tcgen05 / TMEM
+// version is the step after this one.
 #pragma once
 
 namespace ppo {
 
 constexpr int HID = SO100_PPO_HIDDEN, ACT = SO100_PPO_ACT, TB = SO100_PPO_TILE, NT = 256, K1 = 16;
-constexpr int LDT = 68;  // row stride of the [sample][feature] copies (16-byte aligned, de-phases the banks)
-constexpr int LDX = 20;  // row stride of the [sample][input feature] copy
+constexpr int LD = 72;    // row stride of every K-major 64-column matrix in shared memory: 72 = 8 (mod 32) makes the MMA
+                          // fragment loads (4 k-rows x 8 consecutive columns per warp) hit 32 distinct banks
+constexpr int LDXT = 24;  // same property for the [sample][input feature] copy (16 columns)
 constexpr float LOG_SQRT_2PI = 0.91893853320467274178f;
 
 struct Layout {  // offsets into the flat parameter vector
@@ -45,18 +50,18 @@ __host__ __device__ inline Layout make_layout(int od) {
 
 // shared-memory image of one tower's weights
 struct TowerS {
-  float* W1t;  // [K1][HID]   W1t[k][m] = W1[m][k], rows k >= od are zero
-  float* W2t;  // [HID][HID]  W2t[k][m] = W2[m][k]
-  float* W2n;  // [HID][HID]  W2 as stored, [out][in]
+  float* W1t;  // [K1][LD]    W1t[k][m] = W1[m][k], rows k >= od are zero
+  float* W2t;  // [HID][LD]   W2t[k][m] = W2[m][k]
+  float* W2n;  // [HID][LD]   W2 as stored, [out][in]
   float* W3;   // [nout][HID]
   float *b1, *b2, *b3;
 };
-constexpr int tower_floats(bool with_w2n) { return K1 * HID + HID * HID + (with_w2n ? HID * HID : 0) + 8 * HID + HID + HID + 8; }
+constexpr int tower_floats(bool with_w2n) { return K1 * LD + HID * LD + (with_w2n ? HID * LD : 0) + 8 * HID + HID + HID + 8; }
 
 __device__ inline float* carve_tower(float* p, TowerS& T, bool with_w2n) {
-  T.W1t = p; p += K1 * HID;
-  T.W2t = p; p += HID * HID;
-  T.W2n = with_w2n ? p : nullptr; p += with_w2n ? HID * HID : 0;
+  T.W1t = p; p += K1 * LD;
+  T.W2t = p; p += HID * LD;
+  T.W2n = with_w2n ? p : nullptr; p += with_w2n ? HID * LD : 0;
   T.W3 = p; p += 8 * HID;
   T.b1 = p; p += HID;
   T.b2 = p; p += HID;
@@ -65,62 +70,96 @@ __device__ inline float* carve_tower(float* p, TowerS& T, bool with_w2n) {
 }
 __device__ inline void load_tower(const Layout& L, const float* P, int t, TowerS& T, bool with_w2n) {
   const int od = L.od, nout = t == 0 ? ACT : 1, tid = threadIdx.x, nt = blockDim.x;
-  for (int e = tid; e < K1 * HID; e += nt) { int k = e / HID, m = e % HID; T.W1t[e] = k < od ? P[L.W1[t] + m * od + k] : 0.0f; }
+  for (int e = tid; e < K1 * HID; e += nt) { int k = e / HID, m = e % HID; T.W1t[k * LD + m] = k < od ? P[L.W1[t] + m * od + k] : 0.0f; }
   for (int e = tid; e < HID * HID; e += nt) {
     int k = e / HID, m = e % HID;
-    T.W2t[e] = P[L.W2[t] + m * HID + k];
-    if (with_w2n) T.W2n[e] = P[L.W2[t] + e];
+    T.W2t[k * LD + m] = P[L.W2[t] + m * HID + k];
+    if (with_w2n) T.W2n[k * LD + m] = P[L.W2[t] + e];
   }
   for (int e = tid; e < 8 * HID; e += nt) T.W3[e] = e < nout * HID ? P[L.W3[t] + e] : 0.0f;
   for (int e = tid; e < HID; e += nt) { T.b1[e] = P[L.b1[t] + e]; T.b2[e] = P[L.b2[t] + e]; }
   for (int e = tid; e < 8; e += nt) T.b3[e] = e < nout ? P[L.b3[t] + e] : 0.0f;
 }
 
-// acc[i][j] += sum_k At[k][r0 + i] * Bm[k][c0 + j]   (both operands K-major in shared memory)
-template <int K>
-__device__ __forceinline__ void gemm44(const float* __restrict__ At, int lda, const float* __restrict__ Bm, int ldb, int r0, int c0,
-                                       float (&acc)[4][4]) {
-#pragma unroll 8
-  for (int k = 0; k < K; k++) {
-    const float4 a = *reinterpret_cast<const float4*>(At + k * lda + r0);
-    const float4 b = *reinterpret_cast<const float4*>(Bm + k * ldb + c0);
-    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+// ---- warp-level tensor-core tile: D(16 x 8*NTILE) += A(16 x K) B(K x 8*NTILE), both operands K-major in shared memory
+// (At[k][m], Bm[k][n]).  Lane (g = lane / 4, t = lane % 4) owns rows m0 + g + 8 i (i = 0, 1) and, in n-tile j, columns
+// n0 + 8 j + 2 t + e (e = 0, 1): acc[j][2 i + e]  (PTX ISA, mma.m16n8k8 .tf32 fragment layouts).
+struct Own {
+  int m0, n0, g, t;
+  __device__ __forceinline__ int row(int i) const { return m0 + g + 8 * i; }
+  __device__ __forceinline__ int col(int j, int e) const { return n0 + 8 * j + 2 * t + e; }
+};
+__device__ __forceinline__ Own own_64x64() {  // 8 warps: 4 along M x 2 along N, each 16 x 32
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  return Own{16 * (w & 3), 32 * (w >> 2), lane >> 2, lane & 3};
+}
+// 3xTF32 operand split.  The tensor core reads only the upper 19 bits of an fp32 operand (sign, exponent, 10 mantissa
+// bits), so "hi" is x itself as far as the MMA is concerned; lo = x - trunc19(x) is exact in fp32 (two instructions;
+// cvt.rna.tf32 is emulated with ~8 on this architecture) and is itself truncated by the hardware to 11 significant bits:
+// the neglected terms are O(2^-21) relative per product.
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x);
+  lo = __float_as_uint(x - __uint_as_float(hi & 0xFFFFE000u));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <int K, int NTILE, int lda, int ldb>
+__device__ __forceinline__ void gemm_mma(const float* __restrict__ At, const float* __restrict__ Bm, const Own& o, float (&acc)[NTILE][4]) {
+#pragma unroll 2
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    const float* ap = At + (k0 + o.t) * lda + o.m0 + o.g;
+    uint32_t ah[4], al[4];
+    split_tf32(ap[0], ah[0], al[0]);
+    split_tf32(ap[8], ah[1], al[1]);
+    split_tf32(ap[4 * lda], ah[2], al[2]);
+    split_tf32(ap[4 * lda + 8], ah[3], al[3]);
+    const float* bp = Bm + (k0 + o.t) * ldb + o.n0 + o.g;
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    for (int j = 0; j < NTILE; j++) {
+      uint32_t bh[2], bl[2];
+      split_tf32(bp[8 * j], bh[0], bl[0]);
+      split_tf32(bp[4 * ldb + 8 * j], bh[1], bl[1]);
+      mma_tf32(acc[j], al, bh);  // small terms first
+      mma_tf32(acc[j], ah, bl);
+      mma_tf32(acc[j], ah, bh);
+    }
   }
 }
-__device__ __forceinline__ void zero44(float (&a)[4][4]) {
+template <int NTILE>
+__device__ __forceinline__ void zero_acc(float (&a)[NTILE][4]) {
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int j = 0; j < NTILE; j++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) a[i][j] = 0.0f;
+    for (int q = 0; q < 4; q++) a[j][q] = 0.0f;
 }
-// h = tanh(acc + bias[row]) -> H[row][col] ([feature][sample], ld TB) and, if HT, HT[col][row] ([sample][feature], ld LDT)
-__device__ __forceinline__ void store_tanh(const float (&acc)[4][4], const float* bias, int r0, int c0, float* H, float* HT) {
-  float h[4][4];
+// h = tanh(acc + bias[row]) -> H[row][col] ([feature][sample]) and, if HT, HT[col][row] ([sample][feature]); both ld = LD
+__device__ __forceinline__ void store_tanh(const float (&acc)[4][4], const float* bias, const Own& o, float* H, float* HT) {
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < 2; i++) {
+    const int r = o.row(i);
+    const float bi = bias[r];
 #pragma unroll
-    for (int j = 0; j < 4; j++) h[i][j] = tanhf(acc[i][j] + bias[r0 + i]);
-#pragma unroll
-  for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(H + (r0 + i) * TB + c0) = make_float4(h[i][0], h[i][1], h[i][2], h[i][3]);
-  if (HT) {
-#pragma unroll
-    for (int j = 0; j < 4; j++) *reinterpret_cast<float4*>(HT + (c0 + j) * LDT + r0) = make_float4(h[0][j], h[1][j], h[2][j], h[3][j]);
+    for (int j = 0; j < 4; j++) {
+      const float h0 = tanhf(acc[j][2 * i] + bi), h1 = tanhf(acc[j][2 * i + 1] + bi);
+      const int c = o.col(j, 0);
+      *reinterpret_cast<float2*>(H + r * LD + c) = make_float2(h0, h1);
+      if (HT) { HT[c * LD + r] = h0; HT[(c + 1) * LD + r] = h1; }
+    }
   }
 }
-// two hidden layers of one tower on the tile in X ([K1][TB]); leaves H1, H2 (and the transposed copies when given)
-__device__ __forceinline__ void tower_forward(const TowerS& T, const float* X, float* H1, float* H1T, float* H2, float* H2T, int r0, int c0) {
+// two hidden layers of one tower on the tile in X ([K1][LD]); leaves H1, H2 (and the transposed copies when given)
+__device__ __forceinline__ void tower_forward(const TowerS& T, const float* X, float* H1, float* H1T, float* H2, float* H2T, const Own& o) {
   float acc[4][4];
-  zero44(acc);
-  gemm44<K1>(T.W1t, HID, X, TB, r0, c0, acc);
-  store_tanh(acc, T.b1, r0, c0, H1, H1T);
+  zero_acc(acc);
+  gemm_mma<K1, 4, LD, LD>(T.W1t, X, o, acc);
+  store_tanh(acc, T.b1, o, H1, H1T);
   __syncthreads();
-  zero44(acc);
-  gemm44<HID>(T.W2t, HID, H1, TB, r0, c0, acc);
-  store_tanh(acc, T.b2, r0, c0, H2, H2T);
+  zero_acc(acc);
+  gemm_mma<HID, 4, LD, LD>(T.W2t, H1, o, acc);
+  store_tanh(acc, T.b2, o, H2, H2T);
   __syncthreads();
 }
 // out[o][s] = b3[o] + sum_k W3[o][k] H2[k][s].  The 64-long sums are split over four thread groups (16 k each, NOUT
@@ -133,7 +172,7 @@ __device__ __forceinline__ void head_forward(const TowerS& T, const float* H2, f
   for (int o = 0; o < NOUT; o++) acc[o] = 0.0f;
 #pragma unroll
   for (int k = 16 * kg; k < 16 * kg + 16; k++) {
-    const float h = H2[k * TB + s];
+    const float h = H2[k * LD + s];
 #pragma unroll
     for (int o = 0; o < NOUT; o++) acc[o] = fmaf(T.W3[o * HID + k], h, acc[o]);
   }
@@ -148,7 +187,7 @@ __device__ __forceinline__ void head_forward(const TowerS& T, const float* H2, f
 }
 
 // ------------------------------------------------------------------------------------------------ rollout inference
-constexpr int kActSmemFloats = 2 * tower_floats(false) + K1 * TB + 2 * HID * TB + 8 * TB + 32 * TB + 8;
+constexpr int kActSmemFloats = 2 * tower_floats(false) + K1 * LD + 2 * HID * LD + 8 * TB + 32 * TB + 8;
 
 __global__ void __launch_bounds__(NT) act_kernel(Layout L, const float* __restrict__ P, const float* __restrict__ obs, int n, unsigned seed_lo,
                                                  unsigned seed_hi, long long env_offset, unsigned tick, int deterministic, float* act_raw,
@@ -157,9 +196,9 @@ __global__ void __launch_bounds__(NT) act_kernel(Layout L, const float* __restri
   TowerS T[2];
   float* p = carve_tower(sm, T[0], false);
   p = carve_tower(p, T[1], false);
-  float* X = p; p += K1 * TB;
-  float* H1 = p; p += HID * TB;
-  float* H2 = p; p += HID * TB;
+  float* X = p; p += K1 * LD;
+  float* H1 = p; p += HID * LD;
+  float* H2 = p; p += HID * LD;
   float* out = p; p += 8 * TB;
   float* scratch = p; p += 32 * TB;
   float* ls = p;
@@ -167,7 +206,8 @@ __global__ void __launch_bounds__(NT) act_kernel(Layout L, const float* __restri
   load_tower(L, P, 0, T[0], false);
   load_tower(L, P, 1, T[1], false);
   if (tid < ACT) ls[tid] = P[L.log_std + tid];
-  const int r0 = 4 * (tid >> 4), c0 = 4 * (tid & 15), ntiles = (n + TB - 1) / TB;
+  const Own o = own_64x64();
+  const int ntiles = (n + TB - 1) / TB;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {  // persistent: the weights are staged once per CTA
     const int base = tile * TB;
     __syncthreads();
@@ -178,12 +218,12 @@ __global__ void __launch_bounds__(NT) act_kernel(Layout L, const float* __restri
         v = obs[(size_t)g * od + f];
         if (obs_copy) obs_copy[(size_t)g * od + f] = v;
       }
-      X[f * TB + s] = v;
+      X[f * LD + s] = v;
     }
     __syncthreads();
-    tower_forward(T[1], X, H1, nullptr, H2, nullptr, r0, c0);
+    tower_forward(T[1], X, H1, nullptr, H2, nullptr, o);
     head_forward<1>(T[1], H2, out + 7 * TB, scratch);  // value in row 7
-    tower_forward(T[0], X, H1, nullptr, H2, nullptr, r0, c0);
+    tower_forward(T[0], X, H1, nullptr, H2, nullptr, o);
     head_forward<ACT>(T[0], H2, out, scratch);
     if (tid < TB && base + tid < n) {
       const int g = base + tid;
@@ -303,9 +343,9 @@ __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict_
 }
 
 constexpr int kGradSmemFloats = 2 * tower_floats(true)  // weights of both towers
-                                + K1 * TB + TB * LDX     // X, XT
-                                + 2 * HID * TB           // H1, H2 ([feature][sample]; H2 is overwritten by dZ2)
-                                + 4 * TB * LDT           // H1T, H2T, dZ2T, dZ1T ([sample][feature])
+                                + K1 * LD + TB * LDXT    // X, XT
+                                + 2 * HID * LD           // H1, H2 ([feature][sample]; H2 is overwritten by dZ2)
+                                + 4 * TB * LD            // H1T, H2T, dZ2T, dZ1T ([sample][feature])
                                 + 8 * TB + 8 * TB        // head outputs, head gradients
                                 + 6 * TB + 4 * TB + 32 * TB + 16;  // actions, (logp_old, adv, ret, valid), head scratch, log_std
 
@@ -317,14 +357,14 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
   TowerS T[2];
   float* p = carve_tower(sm, T[0], true);
   p = carve_tower(p, T[1], true);
-  float* X = p; p += K1 * TB;
-  float* XT = p; p += TB * LDX;
-  float* H1 = p; p += HID * TB;
-  float* H2 = p; p += HID * TB;
-  float* H1T = p; p += TB * LDT;
-  float* H2T = p; p += TB * LDT;
-  float* dZ2T = p; p += TB * LDT;
-  float* dZ1T = p; p += TB * LDT;
+  float* X = p; p += K1 * LD;
+  float* XT = p; p += TB * LDXT;
+  float* H1 = p; p += HID * LD;
+  float* H2 = p; p += HID * LD;
+  float* H1T = p; p += TB * LD;
+  float* H2T = p; p += TB * LD;
+  float* dZ2T = p; p += TB * LD;
+  float* dZ1T = p; p += TB * LD;
   float* out = p; p += 8 * TB;
   float* dOut = p; p += 8 * TB;
   float* sAct = p; p += 6 * TB;
@@ -336,7 +376,8 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
   float* ls = p;
 
   const int tid = threadIdx.x, od = L.od;
-  const int ty = tid >> 4, tx = tid & 15, r0 = 4 * ty, c0 = 4 * tx;
+  const Own o = own_64x64();                                  // 64 x 64 products: 16 x 32 per warp
+  const Own o1{o.m0, 8 * (tid >> 7), o.g, o.t};               // dW1 (64 x 16): 16 x 8 per warp
   const int sg = tid >> 6, fk = tid & 63;  // (sample group, feature) mapping of the reductions over a tile's samples
   load_tower(L, P, 0, T[0], true);
   load_tower(L, P, 1, T[1], true);
@@ -352,15 +393,14 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
   const float inv_mb = 1.0f / (float)mb;
 
   // gradient accumulators, persistent over the CTA's tiles; each thread owns fixed parameters of both towers
-  //   gW2 / gW1: the thread's 4x4 (4x1) block of dW2 (dW1);  gW3p / gb2p / gb1p: partial sums over the thread's 16-sample
-  //   group (combined across the 4 groups at the end);  gOut / gLs / loss sums: per sample slot (threads 0..63)
-  float gW2[2][4][4], gW1[2][4], gW3p[ACT + 1], gb2p[2] = {0, 0}, gb1p[2] = {0, 0}, gOut[ACT + 1], gLs[ACT];
+  //   gW2 / gW1: the thread's MMA accumulator fragments of dW2 (dW1);  gW3p / gb2p / gb1p: partial sums over the thread's
+  //   16-sample group (combined across the 4 groups at the end);  gOut / gLs / loss sums: per sample slot (threads 0..63)
+  float gW2[2][4][4], gW1[2][1][4], gW3p[ACT + 1], gb2p[2] = {0, 0}, gb1p[2] = {0, 0}, gOut[ACT + 1], gLs[ACT];
   float sPg = 0.0f, sV = 0.0f, sKl = 0.0f;
 #pragma unroll
   for (int t = 0; t < 2; t++) {
-    zero44(gW2[t]);
-#pragma unroll
-    for (int i = 0; i < 4; i++) gW1[t][i] = 0.0f;
+    zero_acc(gW2[t]);
+    zero_acc(gW1[t]);
   }
 #pragma unroll
   for (int o = 0; o < ACT + 1; o++) { gW3p[o] = 0.0f; gOut[o] = 0.0f; }
@@ -374,8 +414,8 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
       const int s = e / K1, f = e % K1, g = tile * TB + s;
       float v = 0.0f;
       if (g < mb && f < od) v = obs[(size_t)idx[g] * od + f];
-      X[f * TB + s] = v;
-      XT[s * LDX + f] = v;
+      X[f * LD + s] = v;
+      XT[s * LDXT + f] = v;
     }
     if (tid < TB) {
       const int g = tile * TB + tid;
@@ -393,7 +433,7 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
     for (int t = 0; t < 2; t++) {  // unrolled: the accumulators of both towers stay in registers
       const TowerS& W = T[t];
       const int nout = t == 0 ? ACT : 1;
-      tower_forward(W, X, H1, H1T, H2, H2T, r0, c0);
+      tower_forward(W, X, H1, H1T, H2, H2T, o);
       if (t == 0) head_forward<ACT>(W, H2, out, scratch);
       else head_forward<1>(W, H2, out, scratch);
       // ---- loss and its gradient with respect to the head outputs (one thread per sample)
@@ -437,64 +477,71 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
       __syncthreads();
       // ---- back through the head and the second tanh: dZ2 = (W3^T dOut) * (1 - H2^2), written over H2 and to dZ2T
       {
-        float acc[4][4];
-        zero44(acc);
-        for (int o = 0; o < nout; o++) {
-          const float4 w = *reinterpret_cast<const float4*>(W.W3 + o * HID + r0);
-          const float4 g = *reinterpret_cast<const float4*>(dOut + o * TB + c0);
-          const float wv[4] = {w.x, w.y, w.z, w.w}, gv[4] = {g.x, g.y, g.z, g.w};
+        float w3[2][ACT];
 #pragma unroll
-          for (int i = 0; i < 4; i++)
+        for (int i = 0; i < 2; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j] = fmaf(wv[i], gv[j], acc[i][j]);
+          for (int q = 0; q < ACT; q++) w3[i][q] = q < nout ? W.W3[q * HID + o.row(i)] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int c = o.col(j, 0);
+          float d[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
+#pragma unroll
+          for (int q = 0; q < ACT; q++) {
+            if (q >= nout) break;
+            const float2 g2 = *reinterpret_cast<const float2*>(dOut + q * TB + c);
+#pragma unroll
+            for (int i = 0; i < 2; i++) { d[i][0] = fmaf(w3[i][q], g2.x, d[i][0]); d[i][1] = fmaf(w3[i][q], g2.y, d[i][1]); }
+          }
+#pragma unroll
+          for (int i = 0; i < 2; i++) {
+            const int r = o.row(i);
+            float2 h = *reinterpret_cast<const float2*>(H2 + r * LD + c);  // each element is owned by exactly one thread
+            h.x = d[i][0] * (1.0f - h.x * h.x); h.y = d[i][1] * (1.0f - h.y * h.y);
+            *reinterpret_cast<float2*>(H2 + r * LD + c) = h;
+            dZ2T[c * LD + r] = h.x; dZ2T[(c + 1) * LD + r] = h.y;
+          }
         }
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          float4 h = *reinterpret_cast<const float4*>(H2 + (r0 + i) * TB + c0);
-          h.x = acc[i][0] * (1.0f - h.x * h.x); h.y = acc[i][1] * (1.0f - h.y * h.y);
-          h.z = acc[i][2] * (1.0f - h.z * h.z); h.w = acc[i][3] * (1.0f - h.w * h.w);
-          acc[i][0] = h.x; acc[i][1] = h.y; acc[i][2] = h.z; acc[i][3] = h.w;
-          *reinterpret_cast<float4*>(H2 + (r0 + i) * TB + c0) = h;  // each thread rewrites only its own 4x4 block
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) *reinterpret_cast<float4*>(dZ2T + (c0 + j) * LDT + r0) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
       }
       __syncthreads();
       // ---- dZ1 = (W2^T dZ2) * (1 - H1^2) -> dZ1T only (nothing propagates to the observations)
       {
         float acc[4][4];
-        zero44(acc);
-        gemm44<HID>(W.W2n, HID, H2, TB, r0, c0, acc);
+        zero_acc(acc);
+        gemm_mma<HID, 4, LD, LD>(W.W2n, H2, o, acc);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float4 h = *reinterpret_cast<const float4*>(H1 + (r0 + i) * TB + c0);
-          acc[i][0] *= 1.0f - h.x * h.x; acc[i][1] *= 1.0f - h.y * h.y; acc[i][2] *= 1.0f - h.z * h.z; acc[i][3] *= 1.0f - h.w * h.w;
+        for (int i = 0; i < 2; i++) {
+          const int r = o.row(i);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int c = o.col(j, 0);
+            const float2 h = *reinterpret_cast<const float2*>(H1 + r * LD + c);
+            dZ1T[c * LD + r] = acc[j][2 * i] * (1.0f - h.x * h.x);
+            dZ1T[(c + 1) * LD + r] = acc[j][2 * i + 1] * (1.0f - h.y * h.y);
+          }
         }
-#pragma unroll
-        for (int j = 0; j < 4; j++) *reinterpret_cast<float4*>(dZ1T + (c0 + j) * LDT + r0) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
       }
       __syncthreads();
-      // ---- weight gradients (inner dimension = the tile's samples), accumulated in registers
-      gemm44<TB>(dZ2T, LDT, H1T, LDT, r0, c0, gW2[t]);  // dW2[out][in] += dZ2[out][s] H1[in][s]
-#pragma unroll 8
-      for (int s = 0; s < TB; s++) {                     // dW1[out][in = tx] += dZ1[out][s] X[in][s]
-        const float4 a = *reinterpret_cast<const float4*>(dZ1T + s * LDT + r0);
-        const float x = XT[s * LDX + tx];
-        gW1[t][0] = fmaf(a.x, x, gW1[t][0]); gW1[t][1] = fmaf(a.y, x, gW1[t][1]);
-        gW1[t][2] = fmaf(a.z, x, gW1[t][2]); gW1[t][3] = fmaf(a.w, x, gW1[t][3]);
-      }
+      // ---- weight gradients (inner dimension = the tile's samples), accumulated in the persistent MMA fragments
+      gemm_mma<TB, 4, LD, LD>(dZ2T, H1T, o, gW2[t]);   // dW2[out][in] += dZ2[out][s] H1[in][s]
+      gemm_mma<TB, 1, LD, LDXT>(dZ1T, XT, o1, gW1[t]);   // dW1[out][in] += dZ1[out][s] X[in][s]
       // dW3[o][k = fk] and the hidden biases: partial sums over this thread's 16 samples, NOUT + 2 independent chains
 #pragma unroll
-      for (int s = 16 * sg; s < 16 * sg + 16; s++) {
-        const float h = H2T[s * LDT + fk];
-        if (t == 0) {
+      for (int s0 = 16 * sg; s0 < 16 * sg + 16; s0 += 4) {
+        float h[4];
 #pragma unroll
-          for (int o = 0; o < ACT; o++) gW3p[o] = fmaf(dOut[o * TB + s], h, gW3p[o]);
-        } else {
-          gW3p[ACT] = fmaf(dOut[s], h, gW3p[ACT]);
+        for (int i = 0; i < 4; i++) {
+          h[i] = H2T[(s0 + i) * LD + fk];
+          gb2p[t] += dZ2T[(s0 + i) * LD + fk];
+          gb1p[t] += dZ1T[(s0 + i) * LD + fk];
         }
-        gb2p[t] += dZ2T[s * LDT + fk];
-        gb1p[t] += dZ1T[s * LDT + fk];
+#pragma unroll
+        for (int q = 0; q < ACT; q++) {
+          if (q >= nout) break;
+          const float4 g4 = *reinterpret_cast<const float4*>(dOut + q * TB + s0);  // warp broadcast
+          float& acc = gW3p[t == 0 ? q : ACT];
+          acc = fmaf(g4.x, h[0], acc); acc = fmaf(g4.y, h[1], acc); acc = fmaf(g4.z, h[2], acc); acc = fmaf(g4.w, h[3], acc);
+        }
       }
       __syncthreads();  // the next tower (or tile) overwrites the activation buffers
     }
@@ -505,10 +552,13 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
 #pragma unroll
   for (int t = 0; t < 2; t++) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < 2; i++) {
 #pragma unroll
-      for (int j = 0; j < 4; j++) G[L.W2[t] + (r0 + i) * HID + c0 + j] = gW2[t][i][j];
-      if (tx < od) G[L.W1[t] + (r0 + i) * od + tx] = gW1[t][i];
+      for (int e = 0; e < 2; e++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) G[L.W2[t] + o.row(i) * HID + o.col(j, e)] = gW2[t][j][2 * i + e];
+        if (o1.col(0, e) < od) G[L.W1[t] + o1.row(i) * od + o1.col(0, e)] = gW1[t][0][2 * i + e];
+      }
     }
   }
   __syncthreads();

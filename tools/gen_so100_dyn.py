@@ -21,7 +21,6 @@ from __future__ import annotations
 import argparse
 import ctypes
 import os
-import struct
 import sys
 
 import numpy as np
