@@ -15,6 +15,7 @@ TASK_ENV01, TASK_ENV02, TASK_ENV05, TASK_ENV06 = 1, 2, 5, 6
 FLAG_FRESH_FK_ON_RESET = 1
 FLAG_CLIP_ACTIONS = 2
 FLAG_GENERIC_KERNEL = 4
+FLAG_STATIC_BLOCK = 8  # hold the Env01/02/06 block at its spawn pose (no gravity, no floor contact)
 
 JOINT_STEP_SCALE = 0.075  # envs/utils.py:9
 REST_POSITION = [0.0, -3.141, 3.117, 1.0, 0.0, 0.0]  # envs/utils.py:11

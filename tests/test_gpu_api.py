@@ -119,3 +119,47 @@ def test_vec_env_adapter_on_the_gpu_backend():
         if dones.all():
             assert all(i["TimeLimit.truncated"] and i["episode"]["l"] == 5 for i in infos)
     env.close()
+
+
+@pytest.mark.parametrize("n", [300, 16384 + 300])
+def test_pageable_host_buffers_take_the_copy_pipeline_and_agree_with_pinned(n):
+    """Pinned buffers: one zero-copy launch.  Pageable numpy arrays: chunked H2D -> kernel -> D2H.  Same results."""
+    import ctypes
+    from so100_mujoco_rl_b200 import _native
+    e1, e2 = _env(2, n, seed=9, max_episode_steps=5), _env(2, n, seed=9, max_episode_steps=5)
+    pinned = e1.alloc_host()
+    e1.reset_host(pinned)
+    od = e2.obs_dim
+    buf = {"actions": np.zeros((n, 6), np.float32), "obs": np.zeros((n, od), np.float32), "reward": np.zeros(n, np.float32),
+           "terminated": np.zeros(n, np.uint8), "truncated": np.zeros(n, np.uint8), "terminal_obs": np.zeros((n, od), np.float32),
+           "ep_return": np.zeros(n, np.float32), "ep_len": np.zeros(n, np.int32)}
+    p = lambda k: buf[k].ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    _native.check(e2._L.so100_reset_host(e2._h, p("obs"), None))
+    assert np.array_equal(buf["obs"], pinned["obs"].numpy())
+    rng = np.random.default_rng(2)
+    for t in range(7):  # crosses the 5-step TimeLimit: terminal rows travel on that step
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        pinned["actions"].copy_(torch.from_numpy(a)); buf["actions"][...] = a
+        e1.step_host(pinned)
+        _native.check(e2._L.so100_step_host(e2._h, p("actions"), p("obs"), p("reward"), p("terminated"), p("truncated"),
+                                            p("terminal_obs"), p("ep_return"), p("ep_len"), None))
+        for k in ("obs", "reward", "terminated", "truncated"):
+            assert np.array_equal(buf[k], pinned[k].numpy()), (t, k)
+        if t == 4:
+            assert buf["truncated"].all()
+            for k in ("terminal_obs", "ep_return", "ep_len"):
+                assert np.array_equal(buf[k], pinned[k].numpy()), k
+
+
+def test_static_block_flag_and_block_contact_state():
+    from so100_mujoco_rl_b200.tasks import FLAG_STATIC_BLOCK
+    moving, held = _env(1, 64, seed=3), _env(1, 64, seed=3, flags=FLAG_STATIC_BLOCK)
+    moving.reset(); held.reset()
+    a = torch.zeros((64, 6), device="cuda")
+    for _ in range(12):
+        om, oh = moving.step(a).obs.clone(), held.step(a).obs.clone()
+    bm, bh = moving.get_state()["block"].cpu().numpy(), held.get_state()["block"].cpu().numpy()
+    assert (bh[2] == 0).all() and (bh[3] == 0).all()                     # held at the spawn height
+    assert (np.abs(bm[2] - 0.009892) < 2e-6).all() and (np.abs(bm[3]) < 1e-5).all()   # resting 0.108 mm inside the plane
+    assert torch.equal(om[:, :6], oh[:, :6])                              # the arm does not feel the block
+    assert (np.abs((om - oh).cpu().numpy()[:, [8, 11]] - bm[2][:, None]) < 1e-6).all()  # obs z columns carry the lift

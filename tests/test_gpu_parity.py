@@ -268,3 +268,36 @@ def test_env02_scripted_reach_fires_relocations_mid_episode(spec):
         assert np.abs(env.get_state()["block"].cpu().numpy()[:3].T - blk).max() < 1e-6
     print(f"Env02 scripted reach: {reloc} mid-episode relocations in {steps} steps ({n // 2} scripted envs)")
     assert reloc >= 10
+
+
+def test_other_mjcf_numbers_run_on_the_generic_kernel_and_track_the_oracle(spec):
+    """A so100-shaped chain with different numbers (masses, gains, limits, solimp power, block contact) is not the model
+    baked into so100_dyn_gen.cuh: so100_create must pick the generic kernel, and that kernel must track the oracle."""
+    import copy
+    m = copy.deepcopy(spec)
+    m.body_mass = m.body_mass * np.array([1.3, 0.8, 1.1, 1.5, 0.7, 2.0])
+    m.body_inertia = m.body_inertia * 1.2
+    m.act_kp = m.act_kp * np.array([0.8, 1.2, 1.0, 0.6, 1.5, 1.0])
+    m.jnt_frictionloss = m.jnt_frictionloss * np.array([0.5, 1.0, 2.0, 1.0, 0.3, 1.0])
+    m.jnt_range = m.jnt_range * 0.9
+    m.jnt_solimp_limit = m.jnt_solimp_limit.copy(); m.jnt_solimp_limit[:, 4] = 3.0   # power 3: the general impedance path
+    m.contact_solref = np.array([0.03, 1.0]); m.block_friction = 0.7; m.block_half_z = 0.015
+    from so100_mujoco_rl_b200.batched_env import BatchedSo100Env
+    n, seed = 128, 21
+    env = BatchedSo100Env(2, n, device=0, seed=seed, model=m)
+    assert env.kernel_variant == "generic"
+    o = make_oracle(2, n, seed=seed, spec=m)
+    assert np.abs(env.reset().cpu().numpy() - o.reset()).max() < 1e-6
+    rng = np.random.default_rng(4)
+    worst = 0.0
+    for t in range(200):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        r = env.step(torch.from_numpy(a).cuda())
+        oo, ro, *_ = o.step(a)
+        worst = max(worst, float(np.abs(r.obs.cpu().numpy() - oo).max()))
+        assert np.abs(r.reward.cpu().numpy() - ro).max() < 2e-4
+    st = env.get_state()
+    assert worst < TOL_OBS and np.abs(st["qpos"].cpu().numpy() - _oracle_soa(o, "qpos")).max() < TOL_Q
+    blk = st["block"].cpu().numpy()
+    assert np.abs(blk[:3] - _oracle_soa(o, "block")).max() < 2e-7 and (blk[2] > 0.0145).all()   # rests on ITS half-size
+    env.close()
