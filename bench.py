@@ -87,9 +87,11 @@ class ClockSampler:
 def cpu_oracle_rate(task: int, n_envs: int, seconds: float, threads: int):
     """env-steps/s of the fp64 C oracle on `threads` host threads (bounded sample)."""
     import numpy as np
+    from oracle import pyoracle
     from oracle.pyoracle import Oracle
     from so100_mujoco_rl_b200.model import load_model
     from so100_mujoco_rl_b200.tasks import make_task_cfg
+    pyoracle.use_native_build()  # -O3 -march=native for the timed CPU leg (BASELINE.md §3)
     o = Oracle(load_model().to_ctypes(), make_task_cfg(task, n_envs, seed=0))
     o.reset(nthreads=threads)
     rng = np.random.default_rng(0)
@@ -110,9 +112,11 @@ def run_reference(args, rank: int):
     if rank != 0:
         return
     import numpy as np
+    from oracle import pyoracle
     from oracle.pyoracle import Oracle, lib
     from so100_mujoco_rl_b200.model import load_model
     from so100_mujoco_rl_b200.tasks import make_task_cfg, task_id
+    native = pyoracle.use_native_build()  # -O3 -march=native for the timed CPU leg
     task = task_id(args.task)
     threads = lib().orc_hw_threads()
     n = args.cpu_envs or 256 * threads
@@ -127,7 +131,7 @@ def run_reference(args, rank: int):
         o.step(acts[k % 8], nthreads=threads)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    sample = f"{n} envs x {args.steps} steps of the {args.envs_per_gpu}-env workload, fp64 C oracle (MuJoCo not installable here), {threads} threads"
+    sample = f"{n} envs x {args.steps} steps of the {args.envs_per_gpu}-env workload, fp64 C oracle{' -O3 -march=native' if native else ''} (MuJoCo not installable here), {threads} threads"
     line = {
         "impl": "reference", "metric": "so100 env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
