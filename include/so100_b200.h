@@ -187,7 +187,13 @@ int so100_step(so100_ctx *ctx, const float *actions_dev, float *obs_dev, float *
                uint8_t *terminated_dev, uint8_t *truncated_dev, float *terminal_obs_dev,
                float *ep_return_dev, int32_t *ep_len_dev, void *stream);
 
-/* Host-buffer variants (the reference-facing call): copies + kernel on `stream`, synchronised on return. */
+/*
+ * Host-buffer variants (the reference-facing call), synchronised on return.  Page-locked (pinned / registered) host
+ * buffers are read and written by the kernel directly over the host link (one launch per step, each CTA's transfers
+ * overlapping the others' arithmetic); pageable buffers go through chunked H2D copy -> kernel -> D2H copy on helper
+ * streams.  terminal_obs / ep_return / ep_len rows cross only on steps in which some episode ended.
+ * Environment knobs (experiments): SO100_HOST_ZEROCOPY=0 forces the copy pipeline, SO100_HOST_CHUNKS=1..16 its chunk count.
+ */
 int so100_reset_host(so100_ctx *ctx, float *obs_host, void *stream);
 int so100_step_host(so100_ctx *ctx, const float *actions_host, float *obs_host, float *reward_host,
                     uint8_t *terminated_host, uint8_t *truncated_host, float *terminal_obs_host,

@@ -806,7 +806,7 @@ struct so100_ctx {
   // the host link (zero-copy), one launch per step.  Pageable buffers: chunks of envs on helper streams so that H2D,
   // kernel and D2H overlap.
   static constexpr int kMaxChunks = 16;
-  int n_chunks = 4;
+  int n_chunks = 2;
   bool zero_copy = true;
   cudaStream_t hs[kMaxChunks] = {};
   cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {};
@@ -989,7 +989,7 @@ static int ensure_staging(so100_ctx* c) {
   CU(cudaMalloc((void**)&c->d_any_done, sizeof(int)));
   CU(cudaMallocHost((void**)&c->p_any_done, sizeof(int)));
   if (const char* e = getenv("SO100_HOST_ZEROCOPY")) c->zero_copy = atoi(e) != 0;  // A/B knob (default on)
-  if (const char* e = getenv("SO100_HOST_CHUNKS")) {  // tuning knob of the host path (default 4: measured best of 1..16, profiles/r1_e2e_chunks.txt)
+  if (const char* e = getenv("SO100_HOST_CHUNKS")) {  // tuning knob of the host path (default 2: measured best of 1..8, profiles/r1_e2e_chunks.txt)
     int v = atoi(e);
     if (v >= 1 && v <= so100_ctx::kMaxChunks) c->n_chunks = v;
   }
