@@ -342,45 +342,111 @@ __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict_
   }
 }
 
-constexpr int kGradSmemFloats = 2 * tower_floats(true)  // weights of both towers
-                                + K1 * LD + TB * LDXT    // X, XT
-                                + 2 * HID * LD           // H1, H2 ([feature][sample]; H2 is overwritten by dZ2)
-                                + 4 * TB * LD            // H1T, H2T, dZ2T, dZ1T ([sample][feature])
-                                + 8 * TB + 8 * TB        // head outputs, head gradients
-                                + 6 * TB + 4 * TB + 32 * TB + 16;  // actions, (logp_old, adv, ret, valid), head scratch, log_std
+// ---- geometry of the gradient kernel: tiles of GT = 32 samples so that TWO CTAs fit one SM (109 KB each) and overlap each
+// other's barriers, loss phases and epilogues; [feature][sample] matrices use row stride LDG = 40 (= 8 mod 32)
+constexpr int GT = 32, LDG = 40;
+constexpr int kGradSmemFloats = 2 * tower_floats(false)  // weights of both towers (W2 once: the back-prop product reads it row-major)
+                                + K1 * LDG               // X
+                                + 2 * HID * LDG          // H1 (later dZ2), H2   [feature][sample]
+                                + 3 * GT * LD            // H1T, dZ2T, dZ1T      [sample][feature]
+                                + 8 * GT + 8 * GT        // head outputs, head gradients
+                                + 6 * GT + 4 * GT + 32 * GT + 16;  // actions, (logp_old, adv, ret, valid), head scratch, log_std
+static_assert(kGradSmemFloats * 4 <= 113 * 1024, "two gradient CTAs must fit one SM");
 
-__global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __restrict__ P, const float* __restrict__ obs, const float* __restrict__ act,
+// A given row-major (A[m][k] at Ar[m * lda + k]) instead of K-major: same MMA, 2-way conflicted fragment loads
+template <int K, int NTILE, int lda, int ldb>
+__device__ __forceinline__ void gemm_mma_rowA(const float* __restrict__ Ar, const float* __restrict__ Bm, const Own& o, float (&acc)[NTILE][4]) {
+#pragma unroll 2
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    const float* ap = Ar + (o.m0 + o.g) * lda + k0 + o.t;
+    uint32_t ah[4], al[4];
+    split_tf32(ap[0], ah[0], al[0]);
+    split_tf32(ap[8 * lda], ah[1], al[1]);
+    split_tf32(ap[4], ah[2], al[2]);
+    split_tf32(ap[8 * lda + 4], ah[3], al[3]);
+    const float* bp = Bm + (k0 + o.t) * ldb + o.n0 + o.g;
+#pragma unroll
+    for (int j = 0; j < NTILE; j++) {
+      uint32_t bh[2], bl[2];
+      split_tf32(bp[8 * j], bh[0], bl[0]);
+      split_tf32(bp[4 * ldb + 8 * j], bh[1], bl[1]);
+      mma_tf32(acc[j], al, bh);
+      mma_tf32(acc[j], ah, bl);
+      mma_tf32(acc[j], ah, bh);
+    }
+  }
+}
+// h = tanh(acc + bias[row]) for a 16 x 16 warp slab -> H[row][col] (ld LDG) and, if HT, HT[col][row] (ld LD)
+__device__ __forceinline__ void store_tanh_g(const float (&acc)[2][4], const float* bias, const Own& o, float* H, float* HT) {
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const int r = o.row(i);
+    const float bi = bias[r];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const float h0 = tanhf(acc[j][2 * i] + bi), h1 = tanhf(acc[j][2 * i + 1] + bi);
+      const int c = o.col(j, 0);
+      *reinterpret_cast<float2*>(H + r * LDG + c) = make_float2(h0, h1);
+      if (HT) { HT[c * LD + r] = h0; HT[(c + 1) * LD + r] = h1; }
+    }
+  }
+}
+// out[o][s] = b3[o] + sum_k W3[o][k] H2[k][s] for GT samples: threads 0..127 = 4 k-groups x 32 samples; ends synchronised
+template <int NOUT>
+__device__ __forceinline__ void head_forward_g(const TowerS& T, const float* H2, float* out, float* scratch) {
+  const int kg = threadIdx.x >> 5, s = threadIdx.x & 31;
+  if (threadIdx.x < 4 * GT) {
+    float acc[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; o++) acc[o] = 0.0f;
+#pragma unroll
+    for (int k = 16 * kg; k < 16 * kg + 16; k++) {
+      const float h = H2[k * LDG + s];
+#pragma unroll
+      for (int o = 0; o < NOUT; o++) acc[o] = fmaf(T.W3[o * HID + k], h, acc[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < NOUT; o++) scratch[(kg * 8 + o) * GT + s] = acc[o];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NOUT * GT; e += NT) {
+    const int o = e / GT, c = e % GT;
+    out[e] = T.b3[o] + ((scratch[o * GT + c] + scratch[(8 + o) * GT + c]) + (scratch[(16 + o) * GT + c] + scratch[(24 + o) * GT + c]));
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT, 2) grad_kernel(Layout L, const float* __restrict__ P, const float* __restrict__ obs, const float* __restrict__ act,
                                                     const float* __restrict__ logp_old, const float* __restrict__ adv, const float* __restrict__ ret,
                                                     const int64_t* __restrict__ idx, int mb, const double* __restrict__ adv_part, float clip,
                                                     float vf_coef, float ent_coef, int normalize, float* __restrict__ gpart) {
   extern __shared__ __align__(16) float sm[];
   TowerS T[2];
-  float* p = carve_tower(sm, T[0], true);
-  p = carve_tower(p, T[1], true);
-  float* X = p; p += K1 * LD;
-  float* XT = p; p += TB * LDXT;
-  float* H1 = p; p += HID * LD;
-  float* H2 = p; p += HID * LD;
-  float* H1T = p; p += TB * LD;
-  float* H2T = p; p += TB * LD;
-  float* dZ2T = p; p += TB * LD;
-  float* dZ1T = p; p += TB * LD;
-  float* out = p; p += 8 * TB;
-  float* dOut = p; p += 8 * TB;
-  float* sAct = p; p += 6 * TB;
-  float* sOld = p; p += TB;
-  float* sAdv = p; p += TB;
-  float* sRet = p; p += TB;
-  float* sValid = p; p += TB;
-  float* scratch = p; p += 32 * TB;
+  float* p = carve_tower(sm, T[0], false);
+  p = carve_tower(p, T[1], false);
+  float* X = p; p += K1 * LDG;
+  float* H1 = p; p += HID * LDG;   // h1, then dZ2 ([feature][sample]) once the second layer has consumed it
+  float* H2 = p; p += HID * LDG;
+  float* H1T = p; p += GT * LD;
+  float* dZ2T = p; p += GT * LD;
+  float* dZ1T = p; p += GT * LD;
+  float* out = p; p += 8 * GT;
+  float* dOut = p; p += 8 * GT;
+  float* sAct = p; p += 6 * GT;
+  float* sOld = p; p += GT;
+  float* sAdv = p; p += GT;
+  float* sRet = p; p += GT;
+  float* sValid = p; p += GT;
+  float* scratch = p; p += 32 * GT;
   float* ls = p;
 
-  const int tid = threadIdx.x, od = L.od;
-  const Own o = own_64x64();                                  // 64 x 64 products: 16 x 32 per warp
-  const Own o1{o.m0, 8 * (tid >> 7), o.g, o.t};               // dW1 (64 x 16): 16 x 8 per warp
-  const int sg = tid >> 6, fk = tid & 63;  // (sample group, feature) mapping of the reductions over a tile's samples
-  load_tower(L, P, 0, T[0], true);
-  load_tower(L, P, 1, T[1], true);
+  const int tid = threadIdx.x, od = L.od, w = tid >> 5, lane = tid & 31;
+  const Own oA{16 * (w & 3), 16 * (w >> 2), lane >> 2, lane & 3};  // 64 features x 32 samples: 16 x 16 per warp
+  const Own oW{16 * (w & 3), 32 * (w >> 2), lane >> 2, lane & 3};  // dW2, 64 x 64: 16 x 32 per warp
+  const Own o1{0, 8 * w, lane >> 2, lane & 3};                     // dW1^T, 16 inputs x 64 outputs: 16 x 8 per warp
+  const int sg = tid >> 6, fk = tid & 63;  // (group of 8 samples, feature) mapping of the reductions over a tile's samples
+  load_tower(L, P, 0, T[0], false);
+  load_tower(L, P, 1, T[1], false);
   if (tid < ACT) ls[tid] = P[L.log_std + tid];
   float a_mean = 0.0f, a_rstd = 1.0f;
   if (normalize) {  // every thread combines the partials in the same order: identical values everywhere
@@ -393,8 +459,8 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
   const float inv_mb = 1.0f / (float)mb;
 
   // gradient accumulators, persistent over the CTA's tiles; each thread owns fixed parameters of both towers
-  //   gW2 / gW1: the thread's MMA accumulator fragments of dW2 (dW1);  gW3p / gb2p / gb1p: partial sums over the thread's
-  //   16-sample group (combined across the 4 groups at the end);  gOut / gLs / loss sums: per sample slot (threads 0..63)
+  //   gW2 / gW1: the thread's MMA accumulator fragments of dW2 (dW1^T);  gW3p / gb2p / gb1p: partial sums over the thread's
+  //   8-sample group (combined across the 4 groups at the end);  gOut / gLs / loss sums: per sample slot (threads 0..31)
   float gW2[2][4][4], gW1[2][1][4], gW3p[ACT + 1], gb2p[2] = {0, 0}, gb1p[2] = {0, 0}, gOut[ACT + 1], gLs[ACT];
   float sPg = 0.0f, sV = 0.0f, sKl = 0.0f;
 #pragma unroll
@@ -407,22 +473,21 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
 #pragma unroll
   for (int o = 0; o < ACT; o++) gLs[o] = 0.0f;
 
-  const int ntiles = (mb + TB - 1) / TB;
+  const int ntiles = (mb + GT - 1) / GT;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     __syncthreads();  // the previous tile's buffers are free (also orders the weight loads before first use)
-    for (int e = tid; e < TB * K1; e += NT) {
-      const int s = e / K1, f = e % K1, g = tile * TB + s;
+    for (int e = tid; e < GT * K1; e += NT) {
+      const int s = e / K1, f = e % K1, g = tile * GT + s;
       float v = 0.0f;
       if (g < mb && f < od) v = obs[(size_t)idx[g] * od + f];
-      X[f * LD + s] = v;
-      XT[s * LDXT + f] = v;
+      X[f * LDG + s] = v;
     }
-    if (tid < TB) {
-      const int g = tile * TB + tid;
+    if (tid < GT) {
+      const int g = tile * GT + tid;
       const bool valid = g < mb;
       const size_t src = valid ? (size_t)idx[g] : 0;
 #pragma unroll
-      for (int k = 0; k < ACT; k++) sAct[k * TB + tid] = valid ? act[src * ACT + k] : 0.0f;
+      for (int k = 0; k < ACT; k++) sAct[k * GT + tid] = valid ? act[src * ACT + k] : 0.0f;
       sOld[tid] = valid ? logp_old[src] : 0.0f;
       sAdv[tid] = valid ? adv[src] : 0.0f;
       sRet[tid] = valid ? ret[src] : 0.0f;
@@ -433,18 +498,28 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
     for (int t = 0; t < 2; t++) {  // unrolled: the accumulators of both towers stay in registers
       const TowerS& W = T[t];
       const int nout = t == 0 ? ACT : 1;
-      tower_forward(W, X, H1, H1T, H2, H2T, o);
-      if (t == 0) head_forward<ACT>(W, H2, out, scratch);
-      else head_forward<1>(W, H2, out, scratch);
+      {
+        float acc[2][4];
+        zero_acc(acc);
+        gemm_mma<K1, 2, LD, LDG>(W.W1t, X, oA, acc);
+        store_tanh_g(acc, W.b1, oA, H1, H1T);
+        __syncthreads();
+        zero_acc(acc);
+        gemm_mma<HID, 2, LD, LDG>(W.W2t, H1, oA, acc);
+        store_tanh_g(acc, W.b2, oA, H2, nullptr);
+        __syncthreads();
+      }
+      if (t == 0) head_forward_g<ACT>(W, H2, out, scratch);
+      else head_forward_g<1>(W, H2, out, scratch);
       // ---- loss and its gradient with respect to the head outputs (one thread per sample)
-      if (tid < TB) {
+      if (tid < GT) {
         const float valid = sValid[tid];
         if (t == 0) {
           float lp = 0.0f, d[ACT], isig2[ACT];
 #pragma unroll
           for (int k = 0; k < ACT; k++) {
             isig2[k] = expf(-2.0f * ls[k]);
-            d[k] = sAct[k * TB + tid] - out[k * TB + tid];
+            d[k] = sAct[k * GT + tid] - out[k * GT + tid];
             lp += -0.5f * d[k] * d[k] * isig2[k] - ls[k] - LOG_SQRT_2PI;
           }
           const float lr = lp - sOld[tid], ratio = expf(lr);
@@ -461,7 +536,7 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
 #pragma unroll
           for (int k = 0; k < ACT; k++) {
             const float dm = dlp * d[k] * isig2[k];
-            dOut[k * TB + tid] = dm;
+            dOut[k * GT + tid] = dm;
             gOut[k] += dm;  // d b3
             gLs[k] += dlp * (d[k] * d[k] * isig2[k] - 1.0f) - ent_coef * inv_mb * valid;
           }
@@ -475,70 +550,71 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
         }
       }
       __syncthreads();
-      // ---- back through the head and the second tanh: dZ2 = (W3^T dOut) * (1 - H2^2), written over H2 and to dZ2T
+      // ---- back through the head and the second tanh: dZ2 = (W3^T dOut) * (1 - H2^2) -> the H1 buffer ([feature][sample],
+      //      h1 itself lives on in H1T) and dZ2T; H2 stays intact for the dW3 sums below
       {
         float w3[2][ACT];
 #pragma unroll
         for (int i = 0; i < 2; i++)
 #pragma unroll
-          for (int q = 0; q < ACT; q++) w3[i][q] = q < nout ? W.W3[q * HID + o.row(i)] : 0.0f;
+          for (int q = 0; q < ACT; q++) w3[i][q] = q < nout ? W.W3[q * HID + oA.row(i)] : 0.0f;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int c = o.col(j, 0);
+        for (int j = 0; j < 2; j++) {
+          const int c = oA.col(j, 0);
           float d[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
 #pragma unroll
           for (int q = 0; q < ACT; q++) {
             if (q >= nout) break;
-            const float2 g2 = *reinterpret_cast<const float2*>(dOut + q * TB + c);
+            const float2 g2 = *reinterpret_cast<const float2*>(dOut + q * GT + c);
 #pragma unroll
             for (int i = 0; i < 2; i++) { d[i][0] = fmaf(w3[i][q], g2.x, d[i][0]); d[i][1] = fmaf(w3[i][q], g2.y, d[i][1]); }
           }
 #pragma unroll
           for (int i = 0; i < 2; i++) {
-            const int r = o.row(i);
-            float2 h = *reinterpret_cast<const float2*>(H2 + r * LD + c);  // each element is owned by exactly one thread
+            const int r = oA.row(i);
+            float2 h = *reinterpret_cast<const float2*>(H2 + r * LDG + c);
             h.x = d[i][0] * (1.0f - h.x * h.x); h.y = d[i][1] * (1.0f - h.y * h.y);
-            *reinterpret_cast<float2*>(H2 + r * LD + c) = h;
+            *reinterpret_cast<float2*>(H1 + r * LDG + c) = h;
             dZ2T[c * LD + r] = h.x; dZ2T[(c + 1) * LD + r] = h.y;
           }
         }
       }
       __syncthreads();
-      // ---- dZ1 = (W2^T dZ2) * (1 - H1^2) -> dZ1T only (nothing propagates to the observations)
+      // ---- dZ1 = (W2^T dZ2) * (1 - h1^2) -> dZ1T only (nothing propagates to the observations); W2^T read from W2t row-major
       {
-        float acc[4][4];
+        float acc[2][4];
         zero_acc(acc);
-        gemm_mma<HID, 4, LD, LD>(W.W2n, H2, o, acc);
+        gemm_mma_rowA<HID, 2, LD, LDG>(W.W2t, H1, oA, acc);
 #pragma unroll
         for (int i = 0; i < 2; i++) {
-          const int r = o.row(i);
+          const int r = oA.row(i);
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int c = o.col(j, 0);
-            const float2 h = *reinterpret_cast<const float2*>(H1 + r * LD + c);
-            dZ1T[c * LD + r] = acc[j][2 * i] * (1.0f - h.x * h.x);
-            dZ1T[(c + 1) * LD + r] = acc[j][2 * i + 1] * (1.0f - h.y * h.y);
+          for (int j = 0; j < 2; j++) {
+            const int c = oA.col(j, 0);
+            const float h0 = H1T[c * LD + r], h1 = H1T[(c + 1) * LD + r];
+            dZ1T[c * LD + r] = acc[j][2 * i] * (1.0f - h0 * h0);
+            dZ1T[(c + 1) * LD + r] = acc[j][2 * i + 1] * (1.0f - h1 * h1);
           }
         }
       }
       __syncthreads();
       // ---- weight gradients (inner dimension = the tile's samples), accumulated in the persistent MMA fragments
-      gemm_mma<TB, 4, LD, LD>(dZ2T, H1T, o, gW2[t]);   // dW2[out][in] += dZ2[out][s] H1[in][s]
-      gemm_mma<TB, 1, LD, LDXT>(dZ1T, XT, o1, gW1[t]);   // dW1[out][in] += dZ1[out][s] X[in][s]
-      // dW3[o][k = fk] and the hidden biases: partial sums over this thread's 16 samples, NOUT + 2 independent chains
+      gemm_mma<GT, 4, LD, LD>(dZ2T, H1T, oW, gW2[t]);          // dW2[out][in] += dZ2[out][s] h1[in][s]
+      gemm_mma_rowA<GT, 1, LDG, LD>(X, dZ1T, o1, gW1[t]);      // dW1^T[in][out] += X[in][s] dZ1[out][s]
+      // dW3[o][k = fk] and the hidden biases: partial sums over this thread's 8 samples
 #pragma unroll
-      for (int s0 = 16 * sg; s0 < 16 * sg + 16; s0 += 4) {
-        float h[4];
+      for (int s0 = 8 * sg; s0 < 8 * sg + 8; s0 += 4) {
+        const float4 h4 = *reinterpret_cast<const float4*>(H2 + fk * LDG + s0);
+        const float h[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          h[i] = H2T[(s0 + i) * LD + fk];
           gb2p[t] += dZ2T[(s0 + i) * LD + fk];
           gb1p[t] += dZ1T[(s0 + i) * LD + fk];
         }
 #pragma unroll
         for (int q = 0; q < ACT; q++) {
           if (q >= nout) break;
-          const float4 g4 = *reinterpret_cast<const float4*>(dOut + q * TB + s0);  // warp broadcast
+          const float4 g4 = *reinterpret_cast<const float4*>(dOut + q * GT + s0);  // warp broadcast
           float& acc = gW3p[t == 0 ? q : ACT];
           acc = fmaf(g4.x, h[0], acc); acc = fmaf(g4.y, h[1], acc); acc = fmaf(g4.z, h[2], acc); acc = fmaf(g4.w, h[3], acc);
         }
@@ -556,13 +632,13 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
 #pragma unroll
       for (int e = 0; e < 2; e++) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) G[L.W2[t] + o.row(i) * HID + o.col(j, e)] = gW2[t][j][2 * i + e];
-        if (o1.col(0, e) < od) G[L.W1[t] + o1.row(i) * od + o1.col(0, e)] = gW1[t][0][2 * i + e];
+        for (int j = 0; j < 4; j++) G[L.W2[t] + oW.row(i) * HID + oW.col(j, e)] = gW2[t][j][2 * i + e];
+        if (o1.row(i) < od) G[L.W1[t] + o1.col(0, e) * od + o1.row(i)] = gW1[t][0][2 * i + e];  // fragment holds dW1^T[in][out]
       }
     }
   }
   __syncthreads();
-  float* scr = H1;  // the activation buffers are free now: combine the four sample groups / the 64 sample slots
+  float* scr = H1T;  // H1T, dZ2T, dZ1T are contiguous and free now: combine the four sample groups / the 32 sample slots
 #pragma unroll
   for (int o = 0; o < ACT + 1; o++) scr[(sg * 8 + o) * HID + fk] = gW3p[o];
 #pragma unroll
@@ -580,15 +656,15 @@ __global__ void __launch_bounds__(NT, 1) grad_kernel(Layout L, const float* __re
     G[(which == 0 ? L.b2[0] : which == 1 ? L.b1[0] : which == 2 ? L.b2[1] : L.b1[1]) + fk] = v;
   }
   __syncthreads();
-  if (tid < TB) {
+  if (tid < GT) {
 #pragma unroll
-    for (int o = 0; o < ACT; o++) { scr[o * TB + tid] = gOut[o]; scr[(ACT + o) * TB + tid] = gLs[o]; }
-    scr[12 * TB + tid] = gOut[ACT]; scr[13 * TB + tid] = sPg; scr[14 * TB + tid] = sV; scr[15 * TB + tid] = sKl;
+    for (int o = 0; o < ACT; o++) { scr[o * GT + tid] = gOut[o]; scr[(ACT + o) * GT + tid] = gLs[o]; }
+    scr[12 * GT + tid] = gOut[ACT]; scr[13 * GT + tid] = sPg; scr[14 * GT + tid] = sV; scr[15 * GT + tid] = sKl;
   }
   __syncthreads();
   if (tid < 16) {
     float v = 0.0f;
-    for (int k = 0; k < TB; k++) v += scr[tid * TB + k];
+    for (int k = 0; k < GT; k++) v += scr[tid * GT + k];
     const int dst = tid < ACT ? L.b3[0] + tid : tid < 2 * ACT ? L.log_std + tid - ACT : tid == 12 ? L.b3[1] : L.total + tid - 13;
     G[dst] = v;
   }
@@ -703,8 +779,8 @@ int so100_ppo_grad(int obs_dim, const float* params, const float* obs, const flo
   int dev = 0, sms = 0;
   CU(cudaGetDevice(&dev));
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int ntiles = (mb + ppo::TB - 1) / ppo::TB;
-  int grid = ntiles < sms ? ntiles : sms;  // persistent: one CTA per SM
+  const int ntiles = (mb + ppo::GT - 1) / ppo::GT;
+  int grid = ntiles < 2 * sms ? ntiles : 2 * sms;  // persistent: two CTAs per SM
   if (grid > SO100_PPO_MAX_CTAS) grid = SO100_PPO_MAX_CTAS;
   cudaStream_t st = (cudaStream_t)stream;
   // fp64 partials behind the gradient partials; (total + 4) * MAX_CTAS floats is a multiple of 8 bytes
