@@ -473,26 +473,49 @@ __global__ void __launch_bounds__(NT, 2) grad_kernel(Layout L, const float* __re
 #pragma unroll
   for (int o = 0; o < ACT; o++) gLs[o] = 0.0f;
 
+  // ---- software-pipelined gather: the rows of tile i+1 are fetched (through indices loaded one tile earlier) while tile i
+  //      is computed, so the idx -> obs dependent global loads never sit on the critical path
   const int ntiles = (mb + GT - 1) / GT;
+  const int gs = tid >> 4, gf = tid & 15;      // this thread stages feature gf of samples gs and gs + 16
+  int nidx[2] = {-1, -1}, nsi = -1;            // sample indices of the NEXT tile (-1 = past the end)
+  float px[2] = {0.0f, 0.0f}, pa[ACT] = {0, 0, 0, 0, 0, 0}, pold = 0.0f, padv = 0.0f, pret = 0.0f, pvalid = 0.0f;
+  auto load_indices = [&](int tile) {
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int g = tile * GT + gs + 16 * j;
+      nidx[j] = (tile < ntiles && g < mb) ? (int)idx[g] : -1;
+    }
+    const int g = tile * GT + tid;
+    nsi = (tid < GT && tile < ntiles && g < mb) ? (int)idx[g] : -1;
+  };
+  auto load_values = [&]() {
+#pragma unroll
+    for (int j = 0; j < 2; j++) px[j] = (nidx[j] >= 0 && gf < od) ? obs[(size_t)nidx[j] * od + gf] : 0.0f;
+    if (tid < GT) {
+      const bool valid = nsi >= 0;
+      const size_t src = valid ? (size_t)nsi : 0;
+#pragma unroll
+      for (int k = 0; k < ACT; k++) pa[k] = valid ? act[src * ACT + k] : 0.0f;
+      pold = valid ? logp_old[src] : 0.0f;
+      padv = valid ? adv[src] : 0.0f;
+      pret = valid ? ret[src] : 0.0f;
+      pvalid = valid ? 1.0f : 0.0f;
+    }
+  };
+  load_indices(blockIdx.x);
+  load_values();
+  load_indices(blockIdx.x + gridDim.x);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     __syncthreads();  // the previous tile's buffers are free (also orders the weight loads before first use)
-    for (int e = tid; e < GT * K1; e += NT) {
-      const int s = e / K1, f = e % K1, g = tile * GT + s;
-      float v = 0.0f;
-      if (g < mb && f < od) v = obs[(size_t)idx[g] * od + f];
-      X[f * LDG + s] = v;
-    }
-    if (tid < GT) {
-      const int g = tile * GT + tid;
-      const bool valid = g < mb;
-      const size_t src = valid ? (size_t)idx[g] : 0;
 #pragma unroll
-      for (int k = 0; k < ACT; k++) sAct[k * GT + tid] = valid ? act[src * ACT + k] : 0.0f;
-      sOld[tid] = valid ? logp_old[src] : 0.0f;
-      sAdv[tid] = valid ? adv[src] : 0.0f;
-      sRet[tid] = valid ? ret[src] : 0.0f;
-      sValid[tid] = valid ? 1.0f : 0.0f;
+    for (int j = 0; j < 2; j++) X[gf * LDG + gs + 16 * j] = px[j];
+    if (tid < GT) {
+#pragma unroll
+      for (int k = 0; k < ACT; k++) sAct[k * GT + tid] = pa[k];
+      sOld[tid] = pold; sAdv[tid] = padv; sRet[tid] = pret; sValid[tid] = pvalid;
     }
+    load_values();                                 // rows of the next tile (indices arrived during the previous tile)
+    load_indices(tile + 2 * (int)gridDim.x);       // indices of the tile after that
     __syncthreads();
 #pragma unroll
     for (int t = 0; t < 2; t++) {  // unrolled: the accumulators of both towers stay in registers
