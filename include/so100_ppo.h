@@ -11,6 +11,7 @@
  *   so100_ppo_post_step  <- OnPolicyAlgorithm.collect_rollouts bookkeeping: TimeLimit bootstrap
  *                           reward += gamma * V(terminal_observation), done flags, Monitor statistics
  *   so100_ppo_gae        <- RolloutBuffer.compute_returns_and_advantage
+ *   so100_ppo_permutation <- RolloutBuffer.get: the per-epoch shuffle of the sample indices
  *   so100_ppo_grad       <- PPO.train: policy.evaluate_actions + losses + loss.backward() for one minibatch
  *   so100_ppo_adam       <- clip_grad_norm_ + Adam.step
  *
@@ -61,6 +62,12 @@ int so100_ppo_post_step(int obs_dim, const float *params, int n, const float *re
 /* GAE(lambda) over [T][N] buffers; done[t] = the episode ended AT step t.  adv, ret: [T][N]. */
 int so100_ppo_gae(const float *rew, const float *val, const float *done, const float *last_val, int T, int N,
                   float gamma, float lam, float *adv, float *ret, void *stream);
+
+/*
+ * idx_out[0..n) = a keyed pseudo-random permutation of 0..n-1 (what np.random.permutation gives SB3's RolloutBuffer.get
+ * once per epoch): 6-round Feistel network with cycle walking, one launch, every index exactly once for any key.
+ */
+int so100_ppo_permutation(int n, uint64_t key, int64_t *idx_out, void *stream);
 
 /*
  * Gradient of  pg_loss + vf_coef * v_loss - ent_coef * entropy  over the minibatch idx[0..mb) of the flattened rollout

@@ -23,7 +23,7 @@ EXPORTS = [
     "so100_host_solver_constants",
     # include/so100_ppo.h
     "so100_ppo_param_count", "so100_ppo_workspace_floats", "so100_ppo_act", "so100_ppo_post_step", "so100_ppo_gae",
-    "so100_ppo_grad", "so100_ppo_adam",
+    "so100_ppo_grad", "so100_ppo_adam", "so100_ppo_permutation",
 ]
 
 
@@ -84,6 +84,7 @@ def lib() -> ctypes.CDLL:
     L.so100_ppo_post_step.argtypes = [ci, vp, ci, vp, vp, vp, vp, vp, vp, cf, vp, vp, vp, vp]
     L.so100_ppo_gae.argtypes = [vp, vp, vp, vp, ci, ci, cf, cf, vp, vp, vp]
     L.so100_ppo_grad.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, ci, cf, cf, cf, ci, vp, vp, vp, vp]
+    L.so100_ppo_permutation.argtypes = [ci, u64, vp, vp]
     L.so100_ppo_adam.argtypes = [ci, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, vp]
     for name in EXPORTS:
         if name not in ("so100_last_error", "so100_destroy"):

@@ -322,6 +322,36 @@ __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rew,
   }
 }
 
+// ------------------------------------------------------------------------------------------------ minibatch sampling
+// A keyed pseudo-random PERMUTATION of [0, n) computed element-wise (SB3 draws np.random.permutation per epoch): a
+// 6-round balanced Feistel network on 2*ceil(bits/2) bits with cycle walking back into [0, n).  Every index appears
+// exactly once per epoch whatever the key; one launch instead of torch.randperm's key generation + radix sort.
+__device__ __forceinline__ unsigned feistel_round(unsigned x, unsigned k) {
+  x = (x ^ k) * 0x9E3779B1u;
+  x ^= x >> 15;
+  x *= 0x85EBCA77u;
+  x ^= x >> 13;
+  return x;
+}
+__global__ void __launch_bounds__(256) permutation_kernel(int n, int half_bits, unsigned k0, unsigned k1, int64_t* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned mask = (1u << half_bits) - 1u;
+  unsigned x = (unsigned)i;
+  do {  // cycle walking: the network permutes [0, 2^(2 half_bits)), which is < 4 n
+    unsigned l = x >> half_bits, r = x & mask;
+#pragma unroll
+    for (int rd = 0; rd < 6; rd++) {
+      const unsigned f = feistel_round(r, (rd & 1 ? k1 : k0) + 0x632BE5ABu * (unsigned)rd) & mask;
+      const unsigned nl = r;
+      r = l ^ f;
+      l = nl;
+    }
+    x = (l << half_bits) | r;
+  } while (x >= (unsigned)n);
+  out[i] = (int64_t)x;
+}
+
 // ------------------------------------------------------------------------------------------------ minibatch gradient
 // Per-CTA partial sums (fp64) of adv[idx] and its square over the minibatch; the gradient kernel combines the partials in
 // a fixed order (deterministic) into mean and 1 / (unbiased std + 1e-8).
@@ -787,6 +817,16 @@ int so100_ppo_gae(const float* rew, const float* val, const float* done, const f
                   float* adv, float* ret, void* stream) {
   if (!rew || !val || !done || !last_val || !adv || !ret || T <= 0 || N <= 0) return fail(SO100_ERR_ARG, "bad argument");
   ppo::gae_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rew, val, done, last_val, T, N, gamma, lam, adv, ret);
+  CU(cudaGetLastError());
+  return SO100_OK;
+}
+
+int so100_ppo_permutation(int n, uint64_t key, int64_t* idx_out, void* stream) {
+  if (n <= 0 || !idx_out) return fail(SO100_ERR_ARG, "bad argument");
+  int bits = 1;
+  while ((1ll << bits) < (long long)n) bits++;
+  const int half_bits = (bits + 1) / 2;
+  ppo::permutation_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, half_bits, (unsigned)(key & 0xFFFFFFFFull), (unsigned)(key >> 32), idx_out);
   CU(cudaGetLastError());
   return SO100_OK;
 }

@@ -371,6 +371,7 @@ class FusedPPO(_LearnLoop):
         self.act_clip, self.last_val = torch.zeros((n, env.act_dim), **f), torch.zeros(n, **f)
         self._acc = torch.zeros(4, device=self.device, dtype=torch.float64)
         self.env_offset, self.tick = int(env_offset), 0
+        self._perm, self._epoch = None, 0
         self.obs = env.reset()
         self.stats = PPOStats()
 
@@ -423,10 +424,14 @@ class FusedPPO(_LearnLoop):
         cfg = self.cfg
         total = adv.numel()
         mb = total // cfg.n_minibatches
+        if self._perm is None or self._perm.numel() != total:
+            self._perm = torch.empty(total, dtype=torch.int64, device=self.device)
         for _ in range(cfg.n_epochs):
-            perm = torch.randperm(total, device=self.device)
+            self._epoch += 1  # a fresh keyed permutation per epoch (SB3: np.random.permutation in RolloutBuffer.get)
+            key = (cfg.seed * 0x9E3779B97F4A7C15 + self._epoch * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+            self._check(self._L.so100_ppo_permutation(total, key, self._perm.data_ptr(), self._stream()))
             for k in range(cfg.n_minibatches):
-                self.minibatch_step(perm[k * mb:(k + 1) * mb], adv, ret)
+                self.minibatch_step(self._perm[k * mb:(k + 1) * mb], adv, ret)
         pg, vl, kl = self.loss.tolist()
         return {"pg_loss": pg, "v_loss": vl, "approx_kl": kl}
 

@@ -188,3 +188,20 @@ def test_fused_ppo_tracks_the_torch_learner_and_learns():
     assert last > first + 0.2, (first, last)
     assert all(math.isfinite(h["pg_loss"]) and math.isfinite(h["v_loss"]) for h in hist)
     env.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 1000, 4096, 65536 * 32 + 17])
+def test_permutation_is_a_bijection_and_depends_on_the_key(n):
+    L, check = _lib()
+    a, b = torch.zeros(n, dtype=torch.int64, device="cuda"), torch.zeros(n, dtype=torch.int64, device="cuda")
+    check(L.so100_ppo_permutation(n, 12345, a.data_ptr(), _st()))
+    check(L.so100_ppo_permutation(n, 12346, b.data_ptr(), _st()))
+    assert torch.equal(torch.sort(a).values, torch.arange(n, device="cuda"))
+    assert torch.equal(torch.sort(b).values, torch.arange(n, device="cuda"))
+    if n >= 1000:
+        assert (a != b).float().mean() > 0.99 and (a != torch.arange(n, device="cuda")).float().mean() > 0.99
+        # no structure a minibatch could inherit: neighbouring positions map far apart, halves are balanced
+        x = a.double()
+        tol = 4.0 / n ** 0.5 + 0.005  # 4 sigma of an ideal random permutation
+        assert abs(float(torch.corrcoef(torch.stack([x[:-1], x[1:]]))[0, 1])) < tol
+        assert abs(float((a[: n // 2] < n // 2).float().mean()) - 0.5) < tol
