@@ -72,3 +72,44 @@ def test_two_ranks_reproduce_the_single_process_run(tmp_path):
                        env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "SHARDING_OK" in r.stdout
+
+
+PPO_WORKER = r'''
+import os, sys
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["SO100_ROOT"]); sys.path.insert(0, os.path.join(os.environ["SO100_ROOT"], "tests"))
+from test_ppo import ToyEnv
+from so100_mujoco_rl_b200.ppo import PPO, PPOConfig, pack_params
+from so100_mujoco_rl_b200.sharding import dist_env
+rank, local, world = dist_env()
+dist.init_process_group("gloo", rank=rank, world_size=world)
+torch.set_num_threads(1)
+algo = PPO(ToyEnv(32, limit=8, seed=100 + rank), PPOConfig(n_steps=8, n_epochs=2, n_minibatches=2, seed=5, cuda_graph=False))
+p0 = pack_params(algo.policy).clone()
+g = [torch.zeros_like(p0) for _ in range(world)]
+dist.all_gather(g, p0)
+assert all(torch.equal(g[0], x) for x in g), "ranks must start from identical weights"
+algo.learn(total_samples=32 * 8 * world * 3, log_every=0, callback=lambda rec: None)
+p1 = pack_params(algo.policy)
+dist.all_gather(g, p1)
+assert all(torch.equal(g[0], x) for x in g), "data-parallel update must keep the replicas identical"
+assert not torch.equal(p0, p1)
+assert algo.stats.samples == 32 * 8 * world * 3          # samples are counted over all ranks
+if rank == 0:
+    print("PPO_DP_OK")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_data_parallel_ppo_keeps_replicas_identical(tmp_path):
+    """world_size 2 over gloo: different env shards per rank, one flat gradient all-reduce per minibatch -> the two
+    replicas stay bit-identical (the learner's only collective; the env step path has none)."""
+    script = tmp_path / "ppo_worker.py"
+    script.write_text(PPO_WORKER)
+    env = dict(os.environ, SO100_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "PPO_DP_OK" in r.stdout
