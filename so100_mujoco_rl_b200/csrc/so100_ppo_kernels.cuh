@@ -96,7 +96,8 @@ __device__ __forceinline__ Own own_64x64() {  // 8 warps: 4 along M x 2 along N,
 // 3xTF32 operand split.  The tensor core reads only the upper 19 bits of an fp32 operand (sign, exponent, 10 mantissa
 // bits), so "hi" is x itself as far as the MMA is concerned; lo = x - trunc19(x) is exact in fp32 (two instructions;
 // cvt.rna.tf32 is emulated with ~8 on this architecture) and is itself truncated by the hardware to 11 significant bits:
-// the neglected terms are O(2^-21) relative per product.
+// the neglected lo*lo term is at most 2^-20 relative per product (truncation keeps its sign, so it under-estimates |ab|
+// by up to ~1e-6; the gradient test bounds the total at 2e-5 of the largest entry).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = __float_as_uint(x);
   lo = __float_as_uint(x - __uint_as_float(hi & 0xFFFFE000u));
