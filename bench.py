@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--envs-per-gpu", type=int, default=65536)
     ap.add_argument("--cpu-envs", type=int, default=0, help="envs in the CPU sample (default: 256 per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--subproc-harness", type=float, default=0.0, help=argparse.SUPPRESS)  # internal: run the SubprocVecEnv-style CPU harness for this many seconds
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -107,6 +108,61 @@ def cpu_oracle_rate(task: int, n_envs: int, seconds: float, threads: int):
     return n_envs * k / dt, k, dt
 
 
+def _subproc_worker(conn, task: int, seed: int):
+    """One env per process, stepped on request (SB3 SubprocVecEnv's worker loop)."""
+    import numpy as np
+    from oracle import pyoracle
+    from oracle.pyoracle import Oracle
+    from so100_mujoco_rl_b200.model import load_model
+    from so100_mujoco_rl_b200.tasks import make_task_cfg
+    pyoracle.use_native_build()
+    o = Oracle(load_model().to_ctypes(), make_task_cfg(task, 1, seed=seed, env_offset=seed))
+    conn.send(o.reset())
+    while True:
+        a = conn.recv()
+        if a is None:
+            break
+        obs, rew, term, trunc, *_ = o.step(np.asarray(a, dtype=np.float32).reshape(1, 6))
+        conn.send((obs, float(rew[0]), bool(term[0] or trunc[0])))
+
+
+def subproc_harness(task: int, seconds: float) -> dict:
+    """The reference's CPU architecture at scale: one process per host core, one env each, an action pipe down and an
+    (obs, reward, done) pipe up every step (Stable-Baselines3 SubprocVecEnv), oracle physics in the workers."""
+    import multiprocessing as mp
+    import numpy as np
+    ctx = mp.get_context("fork")
+    n = os.cpu_count() or 1
+    pipes, procs = [], []
+    for i in range(n):
+        a, b = ctx.Pipe()
+        pr = ctx.Process(target=_subproc_worker, args=(b, task, i), daemon=True)
+        pr.start()
+        pipes.append(a); procs.append(pr)
+    for c in pipes:
+        c.recv()
+    rng = np.random.default_rng(0)
+    acts = rng.uniform(-1, 1, (64, n, 6)).astype(np.float32)
+    for k in range(20):  # warm-up
+        for i, c in enumerate(pipes):
+            c.send(acts[k % 64, i])
+        for c in pipes:
+            c.recv()
+    t0, k = time.perf_counter(), 0
+    while time.perf_counter() - t0 < seconds:
+        for i, c in enumerate(pipes):
+            c.send(acts[k % 64, i])
+        for c in pipes:
+            c.recv()
+        k += 1
+    dt = time.perf_counter() - t0
+    for c in pipes:
+        c.send(None)
+    for pr in procs:
+        pr.join(timeout=5)
+    return {"value": n * k / dt, "unit": "env-steps/s", "processes": n, "seconds": dt}
+
+
 def run_reference(args, rank: int):
     """Reference arm: the CPU path on the host's cores (oracle port; see module docstring)."""
     if rank != 0:
@@ -156,6 +212,10 @@ os.dup2(2, 1)
 
 def main():
     args = parse()
+    if args.subproc_harness > 0:  # child invocation: no torch / CUDA in this process, workers are forked
+        from so100_mujoco_rl_b200.tasks import task_id
+        emit(subproc_harness(task_id(args.task), args.subproc_harness))
+        return
     rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
     if args.impl == "reference":
         run_reference(args, rank)
@@ -287,6 +347,12 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
                                     "sample": f"{ncpu} envs x {k} steps ({dt:.1f} s) of the same workload on the fp64 C oracle",
                                     "per_core": rate / threads, "single_env_single_core": one}
+            try:  # the reference's own architecture at scale (north star): SubprocVecEnv over the host's cores, fresh process
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--subproc-harness", "3", "--task", args.task],
+                                   capture_output=True, text=True, timeout=120)
+                line["cpu_baseline"]["subproc_vec_env"] = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as e:  # noqa: BLE001 - a reported extra, never fatal
+                line["cpu_baseline"]["subproc_vec_env"] = {"error": f"{type(e).__name__}: {e}"[:200]}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
