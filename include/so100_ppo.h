@@ -34,7 +34,7 @@ extern "C" {
 
 #define SO100_PPO_HIDDEN 64
 #define SO100_PPO_ACT 6
-#define SO100_PPO_TILE 64       /* samples per CTA tile */
+#define SO100_PPO_TILE 64       /* envs per CTA tile of the inference kernel (the gradient kernel uses 32-sample tiles) */
 #define SO100_PPO_MAX_CTAS 1024 /* upper bound of the gradient kernel's grid (workspace sizing) */
 
 int so100_ppo_param_count(int obs_dim); /* 10829 for obs_dim 15, 9933 for obs_dim 8; <0 if unsupported (obs_dim must be 1..16) */
