@@ -38,16 +38,20 @@ def main():
         rng = np.random.default_rng(5)
         dq_all, dv_all, dr_all, dobs_cols = [], [], [], []
         flag_mismatch = 0
+        alive = np.ones(n, dtype=bool)   # False once an env's done flags differed: from then on the two runs are in different episodes
         for t in range(args.steps):
             a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
             r = env.step(torch.from_numpy(a).cuda())
             oo, ro, to, co, *_ = o.step(a, nthreads=0)
             st = env.get_state()
-            dq_all.append(np.abs(st["qpos"].cpu().numpy().T - o.gather("qpos")).max(axis=1))
-            dv_all.append(np.abs(st["qvel"].cpu().numpy().T - o.gather("qvel")).max(axis=1))
-            dr_all.append(np.abs(r.reward.cpu().numpy() - ro))
-            dobs_cols.append(np.abs(r.obs.cpu().numpy() - oo).max(axis=0))
-            flag_mismatch += int((r.terminated.cpu().numpy() != to).sum() + (r.truncated.cpu().numpy() != co).sum())
+            mism = (r.terminated.cpu().numpy() != to) | (r.truncated.cpu().numpy() != co)
+            flag_mismatch += int((mism & alive).sum())
+            alive &= ~mism
+            w = np.where(alive, 1.0, 0.0)   # statistics over the envs still in the same episode in both runs
+            dq_all.append(np.abs(st["qpos"].cpu().numpy().T - o.gather("qpos")).max(axis=1) * w)
+            dv_all.append(np.abs(st["qvel"].cpu().numpy().T - o.gather("qvel")).max(axis=1) * w)
+            dr_all.append(np.abs(r.reward.cpu().numpy() - ro) * w)
+            dobs_cols.append((np.abs(r.obs.cpu().numpy() - oo) * w[:, None]).max(axis=0))
         dq, dv, dr = np.array(dq_all), np.array(dv_all), np.array(dr_all)
         q = lambda x, p: float(np.quantile(x, p))  # noqa: E731
         report[f"Env0{task}"] = {
@@ -57,7 +61,9 @@ def main():
             "dreward": {"max": float(dr.max()), "p999": q(dr, .999), "p99": q(dr, .99), "median": q(dr, .5)},
             "dobs_col_max": [float(x) for x in np.array(dobs_cols).max(axis=0)],
             "worst_step_dq": int(dq.max(axis=1).argmax()), "worst_env_dq": int(dq.max(axis=0).argmax()),
-            "done_flag_mismatches": flag_mismatch,
+            "done_flag_mismatches": flag_mismatch, "envs_bifurcated": int((~alive).sum()),
+            "samples_dq_over_2e-5": int((dq > 2e-5).sum()), "envs_ever_dq_over_2e-5": int((dq > 2e-5).any(axis=0).sum()),
+            "samples": int(dq.size),
             "stats": env.stats(),
         }
         print(task, json.dumps(report[f"Env0{task}"]), flush=True)
