@@ -324,9 +324,9 @@ def main():
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s",
                          "frac": ach_tf / tf.value if tf.value else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel launch at 65 536 envs from the
-                         # ncu --set full capture profiles/r1_v8_ncu_raw.csv (11.60 MB read, 1.8 KB written: the state is
+                         # ncu --set full capture profiles/r1_v11_ncu_raw.csv (11.60 MB read, 0 written: the state is
                          # written back from the 126 MB L2 later, under the flush memset); algorithmic 22.2 MB
-                         "traffic": 11603968 if (n == 65536 and task == 1) else None,
+                         "traffic": 11601920 if (n == 65536 and task == 1) else None,
                          "peak_source": "FFMA probe measured in this run (so100_bench_fp32_peak); nominal 74.5",
                          "flop_per_env_step": FLOP_PER_ENV_STEP[task]},
             "roofline_hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
