@@ -202,6 +202,9 @@ int so100_step_host(so100_ctx *ctx, const float *actions_host, float *obs_host, 
 int so100_get_state(so100_ctx *ctx, const so100_state_view *view, void *stream);
 int so100_set_state(so100_ctx *ctx, const so100_state_view *view, void *stream);
 
+/* Re-key the counter-based RNG (gymnasium `reset(seed=...)` / SB3 `VecEnv.seed`): takes effect from the next reset / step. */
+int so100_set_seed(so100_ctx *ctx, uint64_t seed);
+
 /* global step counter t (number of so100_step calls so far); part of the RNG key. */
 int so100_get_tick(so100_ctx *ctx, int64_t *tick);
 int so100_set_tick(so100_ctx *ctx, int64_t tick);

@@ -20,7 +20,7 @@ EXPORTS = [
     "so100_reset", "so100_step", "so100_reset_host", "so100_step_host", "so100_get_state", "so100_set_state",
     "so100_get_tick", "so100_set_tick", "so100_forward_dynamics", "so100_host_forward", "so100_get_derived",
     "so100_get_stats", "so100_bench_fp32_peak", "so100_host_constants", "so100_kernel_variant",
-    "so100_host_solver_constants",
+    "so100_host_solver_constants", "so100_set_seed",
     # include/so100_ppo.h
     "so100_ppo_param_count", "so100_ppo_workspace_floats", "so100_ppo_act", "so100_ppo_post_step", "so100_ppo_gae",
     "so100_ppo_grad", "so100_ppo_adam", "so100_ppo_permutation",
@@ -69,6 +69,7 @@ def lib() -> ctypes.CDLL:
     L.so100_set_state.argtypes = [vp, ctypes.POINTER(StateView), vp]
     L.so100_get_tick.argtypes = [vp, i64p]
     L.so100_set_tick.argtypes = [vp, ctypes.c_int64]
+    L.so100_set_seed.argtypes = [vp, ctypes.c_uint64]
     L.so100_forward_dynamics.argtypes = [vp, ci] + [vp] * 7 + [vp]
     L.so100_host_forward.argtypes = [ctypes.POINTER(So100Model), ci, dp, dp, dp, dp, dp, dp, dp, ci, ci]
     L.so100_host_constants.argtypes = [ctypes.POINTER(So100Model), dp]

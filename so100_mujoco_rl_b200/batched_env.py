@@ -172,6 +172,11 @@ class BatchedSo100Env:
     def tick(self, v: int):
         _native.check(self._L.so100_set_tick(self._h, int(v)))
 
+    def seed(self, seed: int) -> None:
+        """Re-key the device RNG (reset draws, Env02 relocations, Env05 targets and noise); the tick restarts at 0."""
+        _native.check(self._L.so100_set_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF))
+        self.tick = 0
+
     def derived(self):
         a, b, c = np.zeros(NJ), np.zeros(NJ), np.zeros(NJ)
         dp = lambda x: x.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # noqa: E731

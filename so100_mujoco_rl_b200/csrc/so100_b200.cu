@@ -1118,6 +1118,13 @@ int so100_set_tick(so100_ctx* c, int64_t tick) {
   return SO100_OK;
 }
 
+int so100_set_seed(so100_ctx* c, uint64_t seed) {
+  if (!c) return fail(SO100_ERR_ARG, "null argument");
+  c->C.t.seed_lo = (unsigned)(seed & 0xFFFFFFFFull);  // the constants travel by value with every launch
+  c->C.t.seed_hi = (unsigned)(seed >> 32);
+  return SO100_OK;
+}
+
 int so100_forward_dynamics(so100_ctx* c, int n, const float* qpos_dev, const float* qvel_dev, const float* ctrl_dev,
                            float* M_dev, float* bias_dev, float* qacc_dev, float* kin_dev, void* stream) {
   if (!c || n <= 0 || !qpos_dev || !qvel_dev || !ctrl_dev) return fail(SO100_ERR_ARG, "bad argument");

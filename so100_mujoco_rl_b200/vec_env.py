@@ -50,6 +50,9 @@ class TorchBackend:
         h = self.np
         return (h["obs"], h["reward"], h["terminated"], h["truncated"], h["terminal_obs"], h["ep_return"], h["ep_len"])
 
+    def seed(self, seed: int):
+        self.env.seed(seed)
+
     def close(self):
         self.env.close()
 
@@ -144,8 +147,11 @@ class So100VecEnv(_VecEnvBase):
         return [False for _ in self._indices(indices)]
 
     def seed(self, seed: int | None = None):
-        # the device RNG is counter-based and keyed at construction; SB3 only records these
+        """SB3 semantics: env i gets seed + i at its next reset.  Here the device RNG is counter-based and keyed by
+        (seed, global env id, tick), so one re-keying serves every env with its own stream."""
         self._seeds = [None if seed is None else seed + i for i in range(self.num_envs)]
+        if seed is not None and hasattr(self._backend, "seed"):
+            self._backend.seed(int(seed))
         return list(self._seeds)
 
     def set_options(self, options=None) -> None:

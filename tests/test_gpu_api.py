@@ -163,3 +163,23 @@ def test_static_block_flag_and_block_contact_state():
     assert (np.abs(bm[2] - 0.009892) < 2e-6).all() and (np.abs(bm[3]) < 1e-5).all()   # resting 0.108 mm inside the plane
     assert torch.equal(om[:, :6], oh[:, :6])                              # the arm does not feel the block
     assert (np.abs((om - oh).cpu().numpy()[:, [8, 11]] - bm[2][:, None]) < 1e-6).all()  # obs z columns carry the lift
+
+
+def test_reseeding_rekeys_the_device_rng():
+    """gymnasium reset(seed=...) / SB3 VecEnv.seed: the same seed reproduces the same episode starts, another one does not."""
+    a, b = _env(1, 256, seed=1), _env(1, 256, seed=2)
+    oa, ob = a.reset().clone(), b.reset().clone()
+    assert not torch.equal(oa, ob)
+    b.seed(1)
+    assert torch.equal(b.reset(), oa)
+    act = torch.zeros((256, 6), device="cuda")
+    for _ in range(3):
+        ra, rb = a.step(act), b.step(act)
+    assert torch.equal(ra.obs, rb.obs)
+    from so100_mujoco_rl_b200 import So100VecEnv
+    v = So100VecEnv("Env01", 64, device=0, seed=5)
+    first = v.reset().copy()
+    v.seed(9); second = v.reset().copy()
+    v.seed(5); third = v.reset().copy()
+    assert not np.array_equal(first, second) and np.array_equal(first, third)
+    v.close()
