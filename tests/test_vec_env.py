@@ -117,3 +117,28 @@ def test_sb3_can_drive_it_if_installed():
     env = make(1, 4, 50)
     model = sb3.PPO("MlpPolicy", env, n_steps=16, batch_size=32, device="cpu")
     model.learn(total_timesteps=128)
+
+
+def test_single_env_gymnasium_face_over_the_batched_backend():
+    """So100Env: reset -> (obs, info); step -> 5-tuple; the step that ends an episode returns its LAST observation and
+    the next reset() hands out the already-produced first observation of the next episode (gymnasium semantics)."""
+    from oracle_backend import OracleBackend
+    from so100_mujoco_rl_b200.gym_env import So100Env
+    env = So100Env("Env01", backend=OracleBackend(1, 1, seed=4, max_episode_steps=3), max_episode_steps=3)
+    with pytest.raises(RuntimeError):
+        env.step(np.zeros(6, dtype=np.float32))
+    obs, info = env.reset()
+    assert obs.shape == (15,) and obs.dtype == np.float32 and info == {}
+    assert env.observation_space.shape == (15,) and env.action_space.shape == (6,)
+    seen = []
+    for t in range(3):
+        o, r, term, trunc, info = env.step(np.zeros(6, dtype=np.float32))
+        seen.append(o)
+        assert isinstance(r, float) and term is False
+    assert trunc is True and "episode" in info and info["episode"]["l"] == 3
+    assert np.any(seen[-1][6:] != 0)                      # last observation of the finished episode: real kinematics
+    with pytest.raises(RuntimeError):
+        env.step(np.zeros(6, dtype=np.float32))
+    nxt, _ = env.reset()
+    assert np.all(nxt[6:] == 0)                           # first observation of the next episode: zero kinematics (Q2)
+    env.close()
