@@ -34,7 +34,8 @@ class So100Env:
             self._pending = None
         obs = self._pending if self._pending is not None else self._vec.reset()[0]
         self._pending, self._needs_reset = None, False
-        return np.array(obs, dtype=np.float32), {}
+        self._last = np.array(obs, dtype=np.float32)
+        return self._last.copy(), {}
 
     def step(self, action):
         if self._needs_reset:
@@ -48,7 +49,29 @@ class So100Env:
             terminated = not truncated
             self._pending, self._needs_reset = obs[0].copy(), True
             out = info.pop("terminal_observation")
-        return np.array(out, dtype=np.float32), float(rew[0]), terminated, truncated, info
+        self._last = np.array(out, dtype=np.float32)
+        return self._last.copy(), float(rew[0]), terminated, truncated, info
+
+    # ---- the reference's getters (envs/env_base_01.py:107-142, env_base_02.py:85-86), served from the last observation:
+    #      they read the same mjData fields the observation is assembled from
+    def get_joint_angles(self) -> np.ndarray:
+        return self._last[:6].copy()  # Env05: the COMMANDED angles, as env_base_02.py:85-86 returns
+
+    def _need15(self):
+        if self._last.shape[0] != 15:
+            raise AttributeError("Env05 observes the projected cube centre, not Cartesian positions (env05_v1.py:32-75)")
+
+    def get_block_pos(self) -> np.ndarray:
+        self._need15()
+        return self._last[9:12].copy()
+
+    def get_end_effector_pos(self) -> np.ndarray:
+        self._need15()
+        return self._last[12:15].copy()
+
+    def get_block_to_end_distance(self) -> float:
+        self._need15()
+        return float(np.linalg.norm(self._last[6:9]))
 
     def render(self):
         return None  # rendering is outside the hot path

@@ -136,6 +136,8 @@ def test_single_env_gymnasium_face_over_the_batched_backend():
         seen.append(o)
         assert isinstance(r, float) and term is False
     assert trunc is True and "episode" in info and info["episode"]["l"] == 3
+    assert np.allclose(env.get_block_pos() - env.get_end_effector_pos(), seen[-1][6:9], atol=1e-6)   # env_base_01.py:241-270
+    assert abs(env.get_block_to_end_distance() - np.linalg.norm(seen[-1][6:9])) < 1e-7 and env.get_joint_angles().shape == (6,)
     assert np.any(seen[-1][6:] != 0)                      # last observation of the finished episode: real kinematics
     with pytest.raises(RuntimeError):
         env.step(np.zeros(6, dtype=np.float32))
