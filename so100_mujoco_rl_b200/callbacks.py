@@ -84,7 +84,10 @@ class TrainCallbacks:
     def save(self, name: str) -> str:
         pol = self.learner.policy
         base = os.path.join(self.folder, name)
-        torch.save({"policy": pol.state_dict(), "samples": self.learner.stats.samples}, base + ".pt")
+        ckpt = {"policy": pol.state_dict(), "samples": self.learner.stats.samples}
+        if hasattr(self.learner, "state_dict"):  # optimizer moments and counters: `-m <file>.pt` resumes exactly
+            ckpt["learner"] = self.learner.state_dict()
+        torch.save(ckpt, base + ".pt")
         export_sb3_zip(base + ".zip", pol.state_dict_sb3(), {"num_timesteps": self.learner.stats.samples})
         return base
 

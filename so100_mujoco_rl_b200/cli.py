@@ -67,8 +67,13 @@ def train(ctx, environment, num_envs, device, trainer, total_timesteps, n_steps,
     env = BatchedSo100Env(environment, num_envs, device=device, seed=seed)
     cfg = PPOConfig(n_steps=n_steps, seed=seed)
     learner = FusedPPO(env, cfg) if learner_kind == "fused" else PPO(env, cfg)
-    if ctx.obj["MODEL_PATH"]:
-        learner.load_policy(_load_policy(ctx.obj["MODEL_PATH"], env.obs_dim, env.device))
+    if ctx.obj["MODEL_PATH"]:  # main.py:201-207: continue from a saved model (weights; a .pt also restores Adam and the counters)
+        path = ctx.obj["MODEL_PATH"]
+        full = torch.load(path, map_location="cpu").get("learner") if path.endswith(".pt") else None
+        if full is not None:
+            learner.load_state_dict(full)
+        else:
+            learner.load_policy(_load_policy(path, env.obs_dim, env.device))
     # main.py:211-232: EvalCallback(eval_freq=20000) + reward threshold 6000 + no-improvement stop, CheckpointCallback(40000)
     eval_env = BatchedSo100Env(environment, eval_envs, device=device, seed=seed + 1) if eval_envs > 0 else None
     cb = TrainCallbacks(learner, folder, f"{environment}_{algo}", eval_env=eval_env, eval_freq=eval_freq, eval_steps=eval_steps,

@@ -335,6 +335,16 @@ class PPO(_LearnLoop):
     def load_policy(self, policy: MlpPolicy) -> None:
         self.policy.load_state_dict(policy.state_dict())
 
+    def state_dict(self) -> dict:
+        """Everything a resumed run needs: weights, Adam moments and step, sample counter."""
+        return {"kind": "torch", "policy": self.policy.state_dict(), "optimizer": self.opt.state_dict(), "samples": self.stats.samples}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.policy.load_state_dict(sd["policy"])
+        if sd.get("kind") == "torch" and "optimizer" in sd:
+            self.opt.load_state_dict(sd["optimizer"])
+        self.stats.samples = int(sd.get("samples", 0))
+
 
 class FusedPPO(_LearnLoop):
     """PPO on the hand-written kernels of include/so100_ppo.h; same interface and hyper-parameters as `PPO`.
@@ -442,6 +452,21 @@ class FusedPPO(_LearnLoop):
         """Continue from the weights of a torch MlpPolicy (Adam moments restart)."""
         self.params.copy_(pack_params(policy).to(self.device))
         self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.step_count.zero_()
+
+    def state_dict(self) -> dict:
+        """Everything a resumed run needs: weights (as an MlpPolicy state dict), Adam moments and step, counters."""
+        return {"kind": "fused", "policy": self.policy.state_dict(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "step_count": int(self.step_count.item()), "tick": self.tick, "epoch": self._epoch, "samples": self.stats.samples}
+
+    def load_state_dict(self, sd: dict) -> None:
+        pol = MlpPolicy(self.od, 6)
+        pol.load_state_dict(sd["policy"])
+        self.load_policy(pol)
+        if sd.get("kind") == "fused":
+            self.exp_avg.copy_(sd["exp_avg"].to(self.device)); self.exp_avg_sq.copy_(sd["exp_avg_sq"].to(self.device))
+            self.step_count.fill_(int(sd["step_count"]))
+            self.tick, self._epoch = int(sd.get("tick", 0)), int(sd.get("epoch", 0))
+        self.stats.samples = int(sd.get("samples", 0))
 
     @property
     def policy(self) -> MlpPolicy:

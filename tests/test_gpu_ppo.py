@@ -205,3 +205,22 @@ def test_permutation_is_a_bijection_and_depends_on_the_key(n):
         tol = 4.0 / n ** 0.5 + 0.005  # 4 sigma of an ideal random permutation
         assert abs(float(torch.corrcoef(torch.stack([x[:-1], x[1:]]))[0, 1])) < tol
         assert abs(float((a[: n // 2] < n // 2).float().mean()) - 0.5) < tol
+
+
+def test_fused_learner_state_roundtrip_resumes_bit_exactly():
+    from so100_mujoco_rl_b200.batched_env import BatchedSo100Env
+    from so100_mujoco_rl_b200.ppo import FusedPPO, PPOConfig
+    cfg = PPOConfig(n_steps=8, n_minibatches=2, n_epochs=2, seed=3)
+    a = FusedPPO(BatchedSo100Env(5, 512, device=0, seed=2), cfg)
+    a.learn(total_samples=512 * 8 * 3, log_every=0, callback=lambda r: None)
+    sd = a.state_dict()
+    b = FusedPPO(BatchedSo100Env(5, 512, device=0, seed=2), cfg)
+    b.load_state_dict({k: (v.cpu() if torch.is_tensor(v) else v) for k, v in sd.items()})   # as read back from a .pt file
+    assert torch.equal(a.params, b.params) and torch.equal(a.exp_avg, b.exp_avg) and int(b.step_count) == int(a.step_count)
+    assert b.stats.samples == a.stats.samples and b.tick == a.tick
+    # the same minibatch on the same rollout data moves both learners identically
+    for k in a.buf:
+        b.buf[k].copy_(a.buf[k])
+    idx = torch.randperm(a.adv.numel(), device="cuda")[:1024]
+    a.minibatch_step(idx, a.adv, a.ret); b.minibatch_step(idx, a.adv, a.ret)
+    assert torch.equal(a.params, b.params)

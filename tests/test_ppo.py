@@ -142,3 +142,19 @@ def test_callbacks_checkpoint_eval_and_sb3_zip(tmp_path):
     assert not cb2.stop and len(cb2.checkpoints) == 4 and len(cb2.evals) == 4
     assert (tmp_path / "b" / "Toy_PPO_cp__1024_steps.zip").exists()
     assert any((tmp_path / "logs" / "Toy_PPO").iterdir())                                  # TensorBoard event file
+
+
+def test_checkpoint_resume_restores_optimizer_and_counters(tmp_path):
+    from so100_mujoco_rl_b200.callbacks import TrainCallbacks
+    from so100_mujoco_rl_b200.ppo import pack_params
+    cfg = PPOConfig(n_steps=8, n_epochs=1, n_minibatches=1, seed=4, cuda_graph=False)
+    a = PPO(ToyEnv(32, limit=8, seed=1), cfg)
+    a.learn(total_samples=32 * 8 * 2, log_every=0, callback=lambda r: None)
+    cb = TrainCallbacks(a, str(tmp_path), "Toy", eval_env=None, save_freq=0, tensorboard_dir=None, verbose=False)
+    cb.save("ckpt")
+    sd = torch.load(tmp_path / "ckpt.pt")["learner"]
+    b = PPO(ToyEnv(32, limit=8, seed=1), cfg)
+    b.load_state_dict(sd)
+    assert torch.equal(pack_params(a.policy), pack_params(b.policy)) and b.stats.samples == a.stats.samples
+    sa, sb = a.opt.state_dict()["state"], b.opt.state_dict()["state"]
+    assert all(torch.equal(sa[k]["exp_avg"], sb[k]["exp_avg"]) and torch.equal(sa[k]["step"], sb[k]["step"]) for k in sa)
