@@ -25,8 +25,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# Algorithmic work per env step (DESIGN.md "Roofline arithmetic"; tools/count_flops.cpp for the FLOPs)
-FLOP_PER_ENV_STEP = {1: 60400.0, 2: 60400.0, 5: 60700.0, 6: 60400.0}
+# Algorithmic work per env step (DESIGN.md "Roofline arithmetic"; tools/count_flops.cpp counts the generic recursion with
+# the shipped sweep schedule: 5 Gauss-Seidel sweeps on the first substep of an env step, 3 on the other 15)
+FLOP_PER_ENV_STEP = {1: 56900.0, 2: 56900.0, 5: 57200.0, 6: 56900.0}
 BYTES_PER_ENV_STEP = {1: 338.0, 2: 362.0, 5: 420.0, 6: 362.0}
 
 
@@ -42,7 +43,16 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--subproc-harness", type=float, default=0.0, help=argparse.SUPPRESS)  # internal: run the SubprocVecEnv-style CPU harness for this many seconds
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-groups", type=int, default=4, help="env groups of the pipelined host path (so100_step_host_async)")
+    ap.add_argument("--no-tasks", action="store_true", help="skip the Env02 / Env05 records (BASELINE configs 3, 4)")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the Env05 PPO record (BASELINE config 5)")
+    ap.add_argument("--flags", type=int, default=0, help="SO100_FLAG_* bits for the env (e.g. 16 = no arm-floor contact)")
     return ap.parse_args()
+
+
+def workload(args) -> str:
+    return (f"{args.task}, {args.envs_per_gpu} envs/GPU, U(-1,1) random actions, 16 substeps/step, in-kernel auto-reset, "
+            "episode clocks staggered over the TimeLimit (decorrelated start)")
 
 
 class ClockSampler:
@@ -171,16 +181,21 @@ def run_reference(args, rank: int):
     from oracle import pyoracle
     from oracle.pyoracle import Oracle, lib
     from so100_mujoco_rl_b200.model import load_model
-    from so100_mujoco_rl_b200.tasks import make_task_cfg, task_id
+    from so100_mujoco_rl_b200.tasks import MAX_EPISODE_STEPS, make_task_cfg, task_id
     native = pyoracle.use_native_build()  # -O3 -march=native for the timed CPU leg
     task = task_id(args.task)
     threads = lib().orc_hw_threads()
     n = args.cpu_envs or 256 * threads
-    o = Oracle(load_model().to_ctypes(), make_task_cfg(task, n, seed=0))
+    o = Oracle(load_model().to_ctypes(), make_task_cfg(task, n, seed=0, flags=args.flags))
     o.reset(nthreads=threads)
+    for i in range(n):  # the same decorrelated start as the GPU arm: episode clocks staggered over the TimeLimit
+        st = o.state(i)
+        st.elapsed_steps = (i * 2654435761) % MAX_EPISODE_STEPS[task]
+        st.time = st.elapsed_steps * 0.032
+        st.target_time = st.time
     rng = np.random.default_rng(0)
     acts = [rng.uniform(-1, 1, (n, 6)).astype(np.float32) for _ in range(8)]
-    for w in range(args.warmup):
+    for w in range(max(args.warmup, 3)):
         o.step(acts[w % 8], nthreads=threads)
     t0 = time.perf_counter()
     for k in range(args.steps):
@@ -190,9 +205,9 @@ def run_reference(args, rank: int):
     sample = f"{n} envs x {args.steps} steps of the {args.envs_per_gpu}-env workload, fp64 C oracle{' -O3 -march=native' if native else ''} (MuJoCo not installable here), {threads} threads"
     line = {
         "impl": "reference", "metric": "so100 env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.task} reach, {args.envs_per_gpu} envs/GPU, U(-1,1) random actions (CPU sample: {n} envs)"},
+        "config": {"workload": workload(args), "envs_per_gpu": args.envs_per_gpu, "task": args.task, "env_flags": args.flags},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -210,6 +225,59 @@ _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
 
 
+def profile_lookup(task: int, n: int, build_id: str):
+    """ncu-derived figures of one step_kernel launch (profiles/step_kernel_profile.json, written by
+    tools/ncu_to_profile.py from an `ncu --set full` capture), valid only for the sources they were measured on."""
+    try:
+        entries = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_profile.json")))["entries"]
+    except Exception:  # noqa: BLE001
+        return None, True
+    same = [e for e in entries if e.get("task") == task and e.get("envs") == n]
+    for e in same:
+        if e.get("csrc_hash") == build_id:
+            return e, False
+    return (same[-1] if same else None), True
+
+
+def pin_to_gpu_numa_node(local_rank: int):
+    """Run this rank's host threads (and hence its first-touch pinned allocations) on the NUMA node of its GPU."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return {"numa_node": node, "pinned": False}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "pinned": bool(allowed), "cpus": len(allowed)}
+    except Exception as e:  # noqa: BLE001 - a hint, never fatal
+        return {"numa_node": None, "pinned": False, "why": f"{type(e).__name__}"[:60]}
+
+
+def timed_steps(env, ring, steps, flush, torch, before=None):
+    """`steps` env.step launches, each bracketed by CUDA events on the launch stream, L2 flushed in between."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    out = []
+    for k in range(steps):
+        a = ring[k % len(ring)]
+        if before is not None:
+            a = before(k, a)
+        flush.zero_()  # evict the env state from L2 between timed iterations
+        ev[k][0].record()
+        r = env.step(a)
+        ev[k][1].record()
+        out.append(r)
+    return ev, out
+
+
 def main():
     args = parse()
     if args.subproc_harness > 0:  # child invocation: no torch / CUDA in this process, workers are forked
@@ -225,7 +293,8 @@ def main():
     import torch.distributed as dist
     from so100_mujoco_rl_b200 import _native
     from so100_mujoco_rl_b200.batched_env import BatchedSo100Env
-    from so100_mujoco_rl_b200.tasks import OBS_DIM, task_id
+    from so100_mujoco_rl_b200.sharding import max_over_ranks
+    from so100_mujoco_rl_b200.tasks import MAX_EPISODE_STEPS, OBS_DIM, task_id
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
@@ -235,74 +304,164 @@ def main():
         raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = pin_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
     task = task_id(args.task)
     n = args.envs_per_gpu
-    env = BatchedSo100Env(task, n, device=local_rank, seed=0, env_offset=rank * n)  # env-sharded, no collective on the step path
-    env.reset()
+    steps, warmup = args.steps, max(args.warmup, 3)
+    build_id = _native.lib().so100_build_id().decode()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # > 126 MB L2
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     ring = [torch.rand((n, 6), device=dev, generator=g) * 2 - 1 for _ in range(64)]  # U(-1,1) actions, resident in HBM
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # > 126 MB L2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for w in range(max(args.warmup, 3)):
+    def fresh_env(t, seed=0):
+        """Env-sharded (no collective on the step path), started from a DECORRELATED state: episode clocks staggered over
+        the whole TimeLimit, then 64 untimed steps, so truncations + in-kernel resets run inside the timed region at
+        their steady rate and no env is in its post-reset transient."""
+        e = BatchedSo100Env(t, n, device=local_rank, seed=seed, env_offset=rank * n, flags=args.flags)
+        e.reset()
+        e.stagger_episodes()
+        for w in range(64):
+            e.step(ring[w % 64])
+        return e
+
+    env = fresh_env(task)
+    for w in range(warmup):
         env.step(ring[w % 64])
     launches0 = env.stats()["launches"]
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()  # evict the env state from L2 between timed iterations
-        ev[k][0].record()
-        env.step(ring[k % 64])
-        ev[k][1].record()
+    ev, res = timed_steps(env, ring, steps, flush, torch)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = sum(step_ms)
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = env.stats()["launches"] - launches0
     stats = env.stats()
 
-    # end to end through the host-buffer C-ABI call (what the VecEnv adapter uses)
+    # ---- end to end through the host-buffer C ABI (host actions in, host obs / reward / flags out, every step)
     e2e = None
     if not args.no_e2e:
+        od = OBS_DIM[task]
         host = env.alloc_host()
         host_ring = [r.cpu().pin_memory() for r in ring[:8]]
-        for w in range(max(args.warmup, 16)):  # also records the library's CUDA graph of each pinned action buffer
+        # (a) the synchronous call (what the SB3 VecEnv adapter makes): one launch, phases in series
+        for w in range(max(warmup, 8)):
             env.step_host(host, actions=host_ring[w % 8])
         barrier()
         t0 = time.perf_counter()
-        for k in range(args.steps):
-            env.step_host(host, actions=host_ring[k % 8])  # pinned actions in, host obs/reward/done out, synchronous
+        for k in range(steps):
+            env.step_host(host, actions=host_ring[k % 8])
         barrier()
-        e2e_s = time.perf_counter() - t0
-        od = OBS_DIM[task]
-        # obs + reward + terminated + truncated + the 4-byte any-done flag; terminal_obs / ep_return / ep_len (another
-        # n*(od*4+8) bytes) cross only on steps where some episode ended (none inside this window: 4000-step episodes)
-        e2e = {"seconds": e2e_s, "h2d": n * 6 * 4, "d2h": n * (od * 4 + 4 + 1 + 1) + 4}
+        sync_s = time.perf_counter() - t0
+        # (b) the pipelined call: G env groups in rotation, each step of a group = its action rows in from pinned host
+        # memory, its obs / reward / flag rows back into pinned host memory; the host waits for a group's rows before it
+        # issues that group's next step (the policy's data dependency), while the other groups keep the GPU and both
+        # directions of the link busy
+        G = max(1, min(args.e2e_groups, 16))
+        env.host_groups(G)
+        for g_ in range(G):
+            env.step_host_async(host, g_, actions=host_ring[0])
+        for w in range(1, max(warmup, 8)):
+            for g_ in range(G):
+                env.step_host_wait(g_)
+                env.step_host_async(host, g_, actions=host_ring[w % 8])
+        for g_ in range(G):
+            env.step_host_wait(g_)
+        barrier()
+        t0 = time.perf_counter()
+        for g_ in range(G):
+            env.step_host_async(host, g_, actions=host_ring[0])
+        for k in range(1, steps):
+            a = host_ring[k % 8]
+            for g_ in range(G):
+                env.step_host_wait(g_)
+                env.step_host_async(host, g_, actions=a)
+        for g_ in range(G):
+            env.step_host_wait(g_)
+        barrier()
+        pipe_s = time.perf_counter() - t0
+        done_rows = float((host["terminated"] | host["truncated"]).sum())
+        env.host_groups(1)
+        # bytes per step: actions in; obs + reward + terminated + truncated out, plus the terminal rows
+        # (terminal_obs + ep_return + ep_len) of the ~n/max_steps envs whose episode ended in that step
+        per_done = od * 4 + 8
+        e2e = {"pipe_s": max_over_ranks(pipe_s, dev), "sync_s": max_over_ranks(sync_s, dev), "groups": G, "h2d": n * 6 * 4,
+               "d2h": n * (od * 4 + 4 + 1 + 1) + int(round(n / MAX_EPISODE_STEPS[task])) * per_done, "done_rows_last_step": done_rows}
 
-    # max over ranks
-    if world > 1:
-        t = torch.tensor([total_ms, e2e["seconds"] if e2e else 0.0], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_max = float(t[0]), float(t[1])
-    else:
-        e2e_max = e2e["seconds"] if e2e else 0.0
+    total_ms = max_over_ranks(total_ms, dev)
+
+    # ---- BASELINE configs 3 and 4: Env02 with a scripted-reach subset (relocations/s), Env05 (lost-cube resets/s)
+    tasks_rec = None
+    if not args.no_tasks:
+        from so100_mujoco_rl_b200.scripted import reach_actions
+        tasks_rec = {}
+        for name, t in (("Env02", 2), ("Env05", 5)):
+            e = fresh_env(t, seed=3)
+            ksteps, kscr = max(20, min(steps, 50)), (min(2048, n) if t == 2 else 0)
+            obs = e.obs.clone()
+            aux_prev = e.get_state()["aux"][:3].clone() if t == 2 else None
+            ms = reloc = dones = 0
+            for k in range(ksteps + 5):
+                a = ring[(k + 7) % 64].clone()
+                if kscr:  # the scripted envs servo onto their block; the controller is host-side tooling, outside the timing
+                    a[:kscr] = reach_actions(e, obs, kscr)
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); r = e.step(a); e1.record()
+                obs = r.obs.clone()
+                e1.synchronize()
+                if k >= 5:
+                    ms += e0.elapsed_time(e1)
+                    dones += int((r.terminated | r.truncated).sum())
+                if t == 2:
+                    aux = e.get_state()["aux"][:3]
+                    if k >= 5:
+                        reloc += int(((aux - aux_prev).abs().sum(0) > 0).sum()) - int((r.terminated | r.truncated).sum())
+                    aux_prev = aux.clone()
+            ms = max_over_ranks(ms, dev)
+            rec = {"envs_per_gpu": n, "steps": ksteps, "ms_per_step": ms / ksteps, "env_steps_per_s": n * world * ksteps / (ms * 1e-3),
+                   "episode_resets_per_s_rank0": dones / (ms * 1e-3)}
+            if t == 2:
+                rec.update({"scripted_envs": kscr, "relocations_rank0": reloc, "relocations_per_s_rank0": reloc / (ms * 1e-3)})
+            tasks_rec[name] = rec
+            e.close()
+
+    # ---- BASELINE config 5: Env05 PPO rollout + update (fused learner), env-sharded, one flat all-reduce per minibatch
+    ppo_rec = None
+    if not args.no_ppo:
+        from so100_mujoco_rl_b200.ppo import FusedPPO, PPOConfig
+        e = BatchedSo100Env(5, n, device=local_rank, seed=0, env_offset=rank * n, flags=args.flags)
+        cfg = PPOConfig(n_steps=32, n_minibatches=8, n_epochs=10, seed=0)
+        algo = FusedPPO(e, cfg, env_offset=rank * n)
+        algo.learn(total_samples=n * world * cfg.n_steps, log_every=0, callback=lambda r_: None)   # warm-up iteration
+        s0, r0, u0 = algo.stats.samples, algo.stats.rollout_s, algo.stats.update_s
+        iters = 2
+        barrier()
+        t0 = time.perf_counter()
+        algo.learn(total_samples=s0 + iters * n * world * cfg.n_steps, log_every=0, callback=lambda r_: None)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0, dev)
+        ppo_rec = {"task": "Env05", "envs_per_gpu": n, "n_steps": cfg.n_steps, "n_minibatches": cfg.n_minibatches, "n_epochs": cfg.n_epochs,
+                   "iterations": iters, "samples_per_s": (algo.stats.samples - s0) / dt, "rollout_s_per_iter": (algo.stats.rollout_s - r0) / iters,
+                   "update_s_per_iter": (algo.stats.update_s - u0) / iters,
+                   "mean_step_reward": algo.stats.history[-1]["mean_step_reward"]}
+        e.close()
 
     if rank == 0:
         import ctypes
         total_envs = n * world
-        value = total_envs * args.steps / (total_ms * 1e-3)
+        value = total_envs * steps / (total_ms * 1e-3)
         per_gpu = value / world
         tf = ctypes.c_double(0.0)
         _native.check(_native.lib().so100_bench_fp32_peak(local_rank, 4096, ctypes.byref(tf)))
@@ -314,31 +473,49 @@ def main():
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "of measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "of fallback")
         ach_tf = per_gpu * FLOP_PER_ENV_STEP[task] / 1e12
         ach_gb = per_gpu * BYTES_PER_ENV_STEP[task] / 1e9
+        prof, stale = profile_lookup(task, n, build_id)
+        dones_in_region = int(sum(int((r.terminated | r.truncated).sum()) for r in res[-1:]))
         line = {
-            "metric": "so100 env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": "so100 env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.task}, {n} envs/GPU, U(-1,1) random actions, 16 substeps/step, in-kernel auto-reset",
-                       "envs_per_gpu": n, "task": args.task, "l2": "flushed between timed steps (256 MiB memset)",
-                       "parallelism": f"env-sharded x{world}, no collective on the step path"},
+            "config": {"workload": workload(args), "envs_per_gpu": n, "task": args.task, "l2": "flushed between timed steps (256 MiB memset)",
+                       "parallelism": f"env-sharded x{world}, no collective on the step path",
+                       "env_flags": args.flags, "episodes_ended_in_last_timed_step_rank0": dones_in_region},
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": tf.value, "unit": "TFLOP/s",
                          "frac": ach_tf / tf.value if tf.value else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel launch at 65 536 envs from the
-                         # ncu --set full capture profiles/r1_v11_ncu_raw.csv (11.60 MB read, 0 written: the state is
-                         # written back from the 126 MB L2 later, under the flush memset); algorithmic 22.2 MB
-                         "traffic": 11601920 if (n == 65536 and task == 1) else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE step_kernel launch from an `ncu --set full` capture of
+                         # this library build (profiles/step_kernel_profile.json); null + stale when the sources have changed since
+                         "traffic": (prof or {}).get("traffic_bytes") if not stale else None,
                          "peak_source": "FFMA probe measured in this run (so100_bench_fp32_peak); nominal 74.5",
-                         "flop_per_env_step": FLOP_PER_ENV_STEP[task]},
+                         "flop_per_env_step": FLOP_PER_ENV_STEP[task],
+                         "frac_is": "useful algorithmic FLOP of the generic recursion per second / FFMA peak (not pipe utilisation)",
+                         "executed_flop_per_env_step": (prof or {}).get("executed_flop_per_env_step"),
+                         "executed_frac": (per_gpu * prof["executed_flop_per_env_step"] / 1e12 / tf.value
+                                           if prof and prof.get("executed_flop_per_env_step") and tf.value else None),
+                         "pipe_fma_pct": (prof or {}).get("pipe_fma_pct"), "issue_active_pct": (prof or {}).get("issue_active_pct"),
+                         "profile": {"file": "profiles/step_kernel_profile.json", "csrc_hash": (prof or {}).get("csrc_hash"),
+                                     "build_id": build_id, "stale": stale}},
             "roofline_hbm": {"bound": "hbm", "achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
                              "peak_source": hbm_src, "bytes_per_env_step": BYTES_PER_ENV_STEP[task]},
             "gpu_launches": launches,
             "clocks": clocks,
             "wall_s_timed_region": t_wall,
             "solver_unconverged": stats["solver_unconverged"], "nan_resets": stats["nan_resets"],
+            "host": numa,
         }
         if e2e:
-            line["e2e"] = {"value": total_envs * args.steps / e2e_max, "unit": "env-steps/s",
-                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
+            line["e2e"] = {"value": total_envs * steps / e2e["pipe_s"], "unit": "env-steps/s",
+                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                           "how": f"so100_step_host_async / _wait over {e2e['groups']} env groups in rotation (pinned host buffers in place "
+                                  "over the host link; every group's rows are on the host before its next step is issued)",
+                           "groups": e2e["groups"]}
+            line["e2e_sync"] = {"value": total_envs * steps / e2e["sync_s"], "unit": "env-steps/s",
+                                "how": "so100_step_host: one synchronous call per step for the whole batch (the SB3 VecEnv adapter's call)"}
+        if tasks_rec:
+            line["tasks"] = tasks_rec
+        if ppo_rec:
+            line["ppo"] = ppo_rec
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             ncpu = args.cpu_envs or 256 * threads

@@ -41,6 +41,7 @@ extern "C" {
 #define SO100_ABI_VERSION 2
 #define SO100_NJ 6            /* arm hinges incl. the jaw */
 #define SO100_MAX_START 64    /* rows available for Env01 start poses (reference: 36) */
+#define SO100_MAX_GROUPS 16   /* env groups of the asynchronous host path */
 
 /* error codes */
 #define SO100_OK 0
@@ -162,6 +163,8 @@ typedef struct so100_ctx so100_ctx;
 
 int so100_abi_version(void);
 const char *so100_last_error(void);
+/* Hash of the env-step kernel's sources this library was built from (keys the ncu figures in profiles/). */
+const char *so100_build_id(void);
 
 int so100_obs_dim(int task);   /* 15 for Env01/Env02/Env06, 8 for Env05; <0 on unknown task */
 int so100_act_dim(int task);   /* 6 */
@@ -188,16 +191,50 @@ int so100_step(so100_ctx *ctx, const float *actions_dev, float *obs_dev, float *
                float *ep_return_dev, int32_t *ep_len_dev, void *stream);
 
 /*
+ * Debug / parity triage (SURVEY.md §8 b): advance the PHYSICS of every env by n_substeps x mj_step under
+ * ctrl_dev[N, 6] (absolute position-servo targets, i.e. mjData.ctrl), with no task logic around it: no reward,
+ * observation, episode counters, auto-reset or RNG tick.  Read the per-substep state back with so100_get_state
+ * (qpos, qvel, qacc_warm, block; `snap` holds the kinematics of the last substep's start state, as after a full step).
+ * The reference-side equivalent is `mujoco.mj_step(model, data, nstep=n)` at env01_v1.py:26.
+ */
+int so100_step_substeps(so100_ctx *ctx, const float *ctrl_dev, int n_substeps, void *stream);
+
+/*
  * Host-buffer variants (the reference-facing call), synchronised on return.  Page-locked (pinned / registered) host
- * buffers are read and written by the kernel directly over the host link (one launch per step, each CTA's transfers
- * overlapping the others' arithmetic); pageable buffers go through chunked H2D copy -> kernel -> D2H copy on helper
- * streams.  terminal_obs / ep_return / ep_len rows cross only on steps in which some episode ended.
- * Environment knobs (experiments): SO100_HOST_ZEROCOPY=0 forces the copy pipeline, SO100_HOST_CHUNKS=1..16 its chunk count.
+ * buffers are read and written by the kernel directly over the host link: ONE launch per step, every CTA pulling its
+ * action rows when it starts and posting its obs / reward / flag rows - and the terminal rows of envs whose episode
+ * ended - when it ends.  At 65 536 envs all CTAs are resident at once, so the three phases (actions in, arithmetic,
+ * results out) run in series; so100_step_host_async below overlaps them across env groups.  Pageable buffers go through
+ * chunked H2D copy -> kernel -> D2H copy on helper streams (terminal rows are then copied only on steps in which some
+ * episode ended).
+ * Environment knobs (experiments): SO100_HOST_ZEROCOPY=0 forces the copy pipeline, SO100_HOST_CHUNKS=1..16 its chunk
+ * count, SO100_HOST_CTAS_PER_SM=1 launches the zero-copy kernel one CTA per SM (two waves at 65 536 envs).
  */
 int so100_reset_host(so100_ctx *ctx, float *obs_host, void *stream);
 int so100_step_host(so100_ctx *ctx, const float *actions_host, float *obs_host, float *reward_host,
                     uint8_t *terminated_host, uint8_t *truncated_host, float *terminal_obs_host,
                     float *ep_return_host, int32_t *ep_len_host, void *stream);
+
+/*
+ * Pipelined host path (the caller of the reference, main.py:56-64, is host-side code: a policy that maps a batch of
+ * observations to a batch of actions).  The envs of a ctx are split into n_groups contiguous ranges
+ * (so100_host_group_range); so100_step_host_async enqueues ONE group's step on that group's own stream and returns at
+ * once, so100_step_host_wait blocks until that group's rows are in the host buffers.  With >= 2 groups in rotation
+ *     async(g0) async(g1) ... | wait(g0) [policy on g0's rows] async(g0) | wait(g1) [policy on g1's rows] async(g1) | ...
+ * one group's results cross the host link while another group's arithmetic runs, and the link is used in both
+ * directions at once; the floor is max(kernel, D2H) instead of their sum.
+ * All pointers are the FULL [num_envs, dim] host arrays of so100_step_host (page-locked: required here); a group reads
+ * and writes only its own rows.  `stream` is the caller's stream: the group's work is ordered after what it holds.
+ * Every group counts its own steps; the RNG tick of a group's k-th step is k, so stepping all groups once equals one
+ * so100_step_host / so100_step call bit for bit.  Full-batch calls (so100_step, so100_step_host) return
+ * SO100_ERR_STATE while groups are at different step counts or have a step in flight.
+ */
+int so100_host_groups(so100_ctx *ctx, int n_groups);   /* 1..SO100_MAX_GROUPS; default 1 = the whole batch */
+int so100_host_group_range(so100_ctx *ctx, int group, int *env_lo, int *env_hi);
+int so100_step_host_async(so100_ctx *ctx, int group, const float *actions_host, float *obs_host, float *reward_host,
+                          uint8_t *terminated_host, uint8_t *truncated_host, float *terminal_obs_host,
+                          float *ep_return_host, int32_t *ep_len_host, void *stream);
+int so100_step_host_wait(so100_ctx *ctx, int group);
 
 int so100_get_state(so100_ctx *ctx, const so100_state_view *view, void *stream);
 int so100_set_state(so100_ctx *ctx, const so100_state_view *view, void *stream);

@@ -108,6 +108,8 @@ def lib():
         L.orc_block_substeps.argtypes = [ctypes.c_void_p, dp, dp, ctypes.c_double, ctypes.c_int]
         L.orc_reset.argtypes = [ctypes.c_void_p, u8p, fp, ctypes.c_int]
         L.orc_step.argtypes = [ctypes.c_void_p, fp, fp, dp, u8p, u8p, fp, dp, i32p, ctypes.c_int]
+        L.orc_set_state_soa.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 9
+        L.orc_get_state_soa.argtypes = [ctypes.c_void_p, dp, dp, dp]
         L.orc_philox.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                  ctypes.POINTER(ctypes.c_uint32)]
         L.orc_hw_threads.restype = ctypes.c_int
@@ -249,6 +251,30 @@ class Oracle:
                          trunc.ctypes.data_as(u8p), term_obs.ctypes.data_as(fp), _d(ep_ret),
                          ep_len.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), nthreads)
         return obs, rew, term, trunc, term_obs, ep_ret, ep_len
+
+    def set_state_soa(self, state: dict) -> None:
+        """Adopt a state of the CUDA path: `state` maps so100_state_view field names to [k, N] float32 / int32 arrays
+        (what `BatchedSo100Env.get_state()` returns, moved to the host)."""
+        keep, ptr = [], {}
+        for name, dt in (("qpos", np.float32), ("qvel", np.float32), ("qacc_warm", np.float32), ("qpos_comp", np.float32),
+                         ("block", np.float32), ("snap", np.float32), ("aux", np.float32), ("counters", np.int32),
+                         ("ep_return", np.float32)):
+            a = state.get(name)
+            if a is None:
+                ptr[name] = None
+                continue
+            a = np.ascontiguousarray(a, dtype=dt)
+            assert a.shape[-1] == self.num_envs, name
+            keep.append(a)
+            ptr[name] = a.ctypes.data
+        self._L.orc_set_state_soa(self._h, ptr["qpos"], ptr["qvel"], ptr["qacc_warm"], ptr["qpos_comp"], ptr["block"], ptr["snap"],
+                                  ptr["aux"], ptr["counters"], ptr["ep_return"])
+
+    def get_state_soa(self):
+        """(qpos [6, N], qvel [6, N], block [4, N]) as float64."""
+        q, v, b = np.zeros((NJ, self.num_envs)), np.zeros((NJ, self.num_envs)), np.zeros((4, self.num_envs))
+        self._L.orc_get_state_soa(self._h, _d(q), _d(v), _d(b))
+        return q, v, b
 
     def gather(self, field: str) -> np.ndarray:
         """Stack one orc_env_state field over all envs -> [N, ...]."""

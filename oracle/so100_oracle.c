@@ -538,6 +538,55 @@ orc_env_state *orc_state(orc_sim *s, int env) { return (env >= 0 && env < s->n) 
 int64_t orc_get_tick(const orc_sim *s) { return s->tick; }
 void orc_set_tick(orc_sim *s, int64_t tick) { s->tick = tick; }
 
+/* ------------------------------------------------------------------ bulk state exchange (layout of so100_state_view) */
+void orc_set_state_soa(orc_sim *s, const float *qpos, const float *qvel, const float *warm, const float *qcomp, const float *block,
+                       const float *snap, const float *aux, const int32_t *cnt, const float *ep_return) {
+  const int n = s->n, task = s->cfg.task;
+  const double dt = s->m.nsubstep * s->m.timestep;
+  for (int i = 0; i < n; i++) {
+    orc_env_state *e = &s->env[i];
+    for (int j = 0; j < NJ; j++) {
+      if (qpos) e->qpos[j] = (double)qpos[j * n + i] - (qcomp ? (double)qcomp[j * n + i] : 0.0);
+      if (qvel) e->qvel[j] = qvel[j * n + i];
+      if (warm) e->qacc_warm[j] = warm[j * n + i];
+    }
+    if (block) { for (int k = 0; k < 3; k++) e->block[k] = block[k * n + i]; e->block_vz = task == 5 ? 0.0 : block[3 * n + i]; }
+    if (snap) {
+      if (task == 5) {
+        for (int k = 0; k < 3; k++) e->cam_xpos[k] = snap[k * n + i];
+        for (int k = 0; k < 9; k++) e->cam_xmat[k] = snap[(3 + k) * n + i];
+      } else {
+        for (int k = 0; k < 3; k++) { e->end_pos[k] = snap[k * n + i]; e->block_xpos[k] = snap[(4 + k) * n + i]; }
+        e->wrist_pos[0] = e->wrist_pos[1] = 0.0; e->wrist_pos[2] = snap[3 * n + i]; /* only z is ever read (env_base_01.py:213) */
+      }
+    }
+    if (aux) {
+      if (task == 2 || task == 6)
+        for (int k = 0; k < 3; k++) { e->task_block_pos[k] = aux[k * n + i]; e->last_block_pos[k] = aux[(3 + k) * n + i]; }
+      if (task == 5) {
+        for (int j = 0; j < NJ; j++) { e->cmd[j] = aux[j * n + i]; e->last_angvel[j] = aux[(6 + j) * n + i]; }
+        for (int k = 0; k < 3; k++) e->target[k] = aux[(12 + k) * n + i];
+        e->target_dt = aux[15 * n + i]; e->last_centre[0] = aux[16 * n + i]; e->last_centre[1] = aux[17 * n + i];
+      }
+    }
+    if (cnt) {
+      int fl = cnt[n + i];
+      e->elapsed_steps = cnt[i]; e->time = e->elapsed_steps * dt;
+      e->ever_stepped = fl & 1; e->has_last_block = (fl >> 1) & 1; e->angvel_valid = (fl >> 2) & 1; e->centre_valid = (fl >> 3) & 1;
+      if (task == 5) { e->miss_count = cnt[2 * n + i]; e->target_time = cnt[3 * n + i] * dt; }
+    }
+    if (ep_return) e->ep_return = ep_return[i];
+  }
+}
+void orc_get_state_soa(const orc_sim *s, double *qpos, double *qvel, double *block) {
+  const int n = s->n;
+  for (int i = 0; i < n; i++) {
+    const orc_env_state *e = &s->env[i];
+    for (int j = 0; j < NJ; j++) { if (qpos) qpos[j * n + i] = e->qpos[j]; if (qvel) qvel[j * n + i] = e->qvel[j]; }
+    if (block) { for (int k = 0; k < 3; k++) block[k * n + i] = e->block[k]; block[3 * n + i] = e->block_vz; }
+  }
+}
+
 /* ------------------------------------------------------------------ task logic */
 static void draw(const orc_sim *s, int env, int stream, double u[4], uint32_t raw[4]) {
   uint32_t r[4];

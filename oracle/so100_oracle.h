@@ -114,6 +114,16 @@ void orc_reset(orc_sim *s, const uint8_t *mask, float *obs, int nthreads);
 void orc_step(orc_sim *s, const float *actions, float *obs, double *reward, uint8_t *terminated,
               uint8_t *truncated, float *terminal_obs, double *ep_return, int32_t *ep_len, int nthreads);
 
+/* Bulk state exchange with the product's structure-of-arrays layout (include/so100_b200.h so100_state_view:
+   field[k][env] at ptr[k * N + env], float32 / int32), so that a parity test can start the oracle from a state the
+   CUDA path has reached (65 536 envs, decorrelated) and compare after K more steps.  qpos is qpos - qpos_comp (the
+   kernel's compensated sum).  NULL = skip. */
+void orc_set_state_soa(orc_sim *s, const float *qpos, const float *qvel, const float *qacc_warm, const float *qpos_comp,
+                       const float *block /*[4][N]*/, const float *snap /*[12][N]*/, const float *aux /*[24][N]*/,
+                       const int32_t *counters /*[4][N]*/, const float *ep_return);
+/* qpos, qvel [6][N], block [4][N] (x y z vz) as doubles */
+void orc_get_state_soa(const orc_sim *s, double *qpos, double *qvel, double *block);
+
 /* RNG exposed for tests: Philox4x32-10, key=(seed lo, seed hi), counter=(global env id, tick, stream, 0).
    streams: 0 auto-reset draws, 1 task draws (Env02 relocate / Env05 retarget), 2 Env05 obs noise,
    3 draws of an explicit orc_reset call, 4 Env05 reset-obs noise (only with FRESH_FK_ON_RESET) */

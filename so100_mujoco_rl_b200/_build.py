@@ -30,10 +30,23 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+STEP_KERNEL_SOURCES = ["so100_b200.cu", "so100_dyn.cuh", "so100_dyn_gen.cuh"]
+
+
+def csrc_hash() -> str:
+    """Identity of the env-step kernel's sources (compiled into the library as so100_build_id(); ncu-derived figures in
+    profiles/step_kernel_profile.json are keyed by it so that bench.py can tell when they are stale)."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in STEP_KERNEL_SOURCES:
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    return h.hexdigest()[:12]
+
+
 def build_native(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc(), *NVCC_FLAGS, f'-DSO100_CSRC_HASH="{csrc_hash()}"', "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -16,11 +16,12 @@ LIB_PATH = os.environ.get("SO100_B200_LIB") or os.path.join(PKG_DIR, "libso100_b
 
 # every symbol include/so100_b200.h declares (tests/test_abi.py checks the two lists against each other)
 EXPORTS = [
-    "so100_abi_version", "so100_last_error", "so100_obs_dim", "so100_act_dim", "so100_create", "so100_destroy",
+    "so100_abi_version", "so100_last_error", "so100_build_id", "so100_obs_dim", "so100_act_dim", "so100_create", "so100_destroy",
     "so100_reset", "so100_step", "so100_reset_host", "so100_step_host", "so100_get_state", "so100_set_state",
     "so100_get_tick", "so100_set_tick", "so100_forward_dynamics", "so100_host_forward", "so100_get_derived",
     "so100_get_stats", "so100_bench_fp32_peak", "so100_host_constants", "so100_kernel_variant",
-    "so100_host_solver_constants", "so100_set_seed",
+    "so100_host_solver_constants", "so100_set_seed", "so100_step_substeps",
+    "so100_host_groups", "so100_host_group_range", "so100_step_host_async", "so100_step_host_wait",
     # include/so100_ppo.h
     "so100_ppo_param_count", "so100_ppo_workspace_floats", "so100_ppo_act", "so100_ppo_post_step", "so100_ppo_gae",
     "so100_ppo_grad", "so100_ppo_adam", "so100_ppo_permutation",
@@ -56,6 +57,7 @@ def lib() -> ctypes.CDLL:
     i64p = ctypes.POINTER(ctypes.c_int64)
     L.so100_abi_version.restype = ci
     L.so100_last_error.restype = ctypes.c_char_p
+    L.so100_build_id.restype = ctypes.c_char_p
     L.so100_obs_dim.argtypes = [ci]
     L.so100_act_dim.argtypes = [ci]
     L.so100_create.argtypes = [ctypes.POINTER(So100Model), ctypes.POINTER(So100TaskCfg), ci, ctypes.POINTER(vp)]
@@ -63,8 +65,13 @@ def lib() -> ctypes.CDLL:
     L.so100_destroy.restype = None
     L.so100_reset.argtypes = [vp, vp, vp, vp]
     L.so100_step.argtypes = [vp] + [vp] * 8 + [vp]
+    L.so100_step_substeps.argtypes = [vp, vp, ci, vp]
     L.so100_reset_host.argtypes = [vp, vp, vp]
     L.so100_step_host.argtypes = [vp] + [vp] * 8 + [vp]
+    L.so100_host_groups.argtypes = [vp, ci]
+    L.so100_host_group_range.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    L.so100_step_host_async.argtypes = [vp, ci] + [vp] * 8 + [vp]
+    L.so100_step_host_wait.argtypes = [vp, ci]
     L.so100_get_state.argtypes = [vp, ctypes.POINTER(StateView), vp]
     L.so100_set_state.argtypes = [vp, ctypes.POINTER(StateView), vp]
     L.so100_get_tick.argtypes = [vp, i64p]
@@ -88,7 +95,7 @@ def lib() -> ctypes.CDLL:
     L.so100_ppo_permutation.argtypes = [ci, u64, vp, vp]
     L.so100_ppo_adam.argtypes = [ci, vp, vp, vp, vp, vp, cf, cf, cf, cf, cf, cf, vp]
     for name in EXPORTS:
-        if name not in ("so100_last_error", "so100_destroy"):
+        if name not in ("so100_last_error", "so100_destroy", "so100_build_id"):
             getattr(L, name).restype = ci
     L.so100_ppo_workspace_floats.restype = i64
     if L.so100_abi_version() != 2:

@@ -33,6 +33,26 @@ class StepResult:
     ep_len: torch.Tensor        # [N] i32, valid where done
 
 
+class HostBuffers(dict):
+    """Page-locked host arrays of one env batch (`BatchedSo100Env.alloc_host`).  Their addresses are cached: the ctypes
+    call is on the per-step path of the host-side caller."""
+    _ORDER = ("actions", "obs", "reward", "terminated", "truncated", "terminal_obs", "ep_return", "ep_len")
+
+    def ptrs(self, with_terminal: bool = True) -> tuple:
+        key = "_p1" if with_terminal else "_p0"
+        p = self.__dict__.get(key)
+        if p is None:
+            p = tuple(self[k].data_ptr() if (with_terminal or i < 5) else None for i, k in enumerate(self._ORDER))
+            self.__dict__[key] = p
+        return p
+
+
+def _host_ptrs(host: dict, with_terminal: bool) -> tuple:
+    if isinstance(host, HostBuffers):
+        return host.ptrs(with_terminal)
+    return tuple(host[k].data_ptr() if (with_terminal or i < 5) else None for i, k in enumerate(HostBuffers._ORDER))
+
+
 class BatchedSo100Env:
     def __init__(self, env: str | int, num_envs: int, device: int | str | torch.device = 0, seed: int = 0,
                  env_offset: int = 0, flags: int = 0, model: ModelSpec | None = None,
@@ -106,11 +126,18 @@ class BatchedSo100Env:
         return StepResult(self.obs, self.reward, self.terminated, self.truncated, self.terminal_obs, self.ep_return,
                           self.ep_len)
 
+    def step_substeps(self, ctrl: torch.Tensor, n_substeps: int = 1) -> None:
+        """Debug / parity triage: n x mj_step under absolute servo targets ctrl [N, 6]; no task logic (see the header)."""
+        ctrl = ctrl.to(device=self.device, dtype=torch.float32).contiguous()
+        if ctrl.shape != (self.num_envs, NJ):
+            raise ValueError(f"ctrl must have shape ({self.num_envs}, {NJ})")
+        _native.check(self._L.so100_step_substeps(self._h, ctrl.data_ptr(), int(n_substeps), self._stream()))
+
     # ---- host-buffer path (the reference-facing call: numpy in / numpy out, copies inside the library)
-    def alloc_host(self) -> dict:
+    def alloc_host(self) -> "HostBuffers":
         n, od = self.num_envs, self.obs_dim
         pin = dict(pin_memory=True)
-        return {
+        return HostBuffers({
             "actions": torch.zeros((n, NJ), dtype=torch.float32, **pin),
             "obs": torch.zeros((n, od), dtype=torch.float32, **pin),
             "reward": torch.zeros(n, dtype=torch.float32, **pin),
@@ -119,7 +146,7 @@ class BatchedSo100Env:
             "terminal_obs": torch.zeros((n, od), dtype=torch.float32, **pin),
             "ep_return": torch.zeros(n, dtype=torch.float32, **pin),
             "ep_len": torch.zeros(n, dtype=torch.int32, **pin),
-        }
+        })
 
     def reset_host(self, host: dict) -> torch.Tensor:
         _native.check(self._L.so100_reset_host(self._h, host["obs"].data_ptr(), self._stream()))
@@ -127,16 +154,46 @@ class BatchedSo100Env:
 
     def step_host(self, host: dict, with_terminal: bool = True, actions: torch.Tensor | None = None) -> dict:
         """actions are read from host['actions'] (or from `actions`, a host float32 [N, 6] tensor); results land in the
-        other host buffers (synchronous).  With pinned buffers the library replays a cached CUDA graph per buffer set."""
-        opt = (lambda k: host[k].data_ptr()) if with_terminal else (lambda k: None)
+        other host buffers (synchronous).  With pinned buffers the kernel reads / writes them in place over the host link."""
         act = host["actions"] if actions is None else actions
         if act.device.type != "cpu" or act.dtype != torch.float32 or not act.is_contiguous() or act.shape != (self.num_envs, NJ):
             raise ValueError(f"host actions must be a contiguous CPU float32 tensor of shape ({self.num_envs}, {NJ})")
-        _native.check(self._L.so100_step_host(
-            self._h, act.data_ptr(), host["obs"].data_ptr(), host["reward"].data_ptr(),
-            host["terminated"].data_ptr(), host["truncated"].data_ptr(), opt("terminal_obs"), opt("ep_return"),
-            opt("ep_len"), self._stream()))
+        p = _host_ptrs(host, with_terminal)
+        _native.check(self._L.so100_step_host(self._h, act.data_ptr(), p[1], p[2], p[3], p[4], p[5], p[6], p[7], self._stream()))
         return host
+
+    def stagger_episodes(self, seed: int = 0) -> None:
+        """Spread the envs' episode clocks uniformly over [0, max_episode_steps) (a scrambled assignment, so every CTA of
+        envs sees the same mix): TimeLimit truncations and the in-kernel resets then arrive at a steady rate of
+        num_envs / max_episode_steps per step instead of all at once.  Env05's retarget clock is kept consistent."""
+        st = self.get_state()
+        i = torch.arange(self.num_envs, device=self.device, dtype=torch.int64)
+        el = ((i * 2654435761 + seed * 40503) % self.max_episode_steps).to(torch.int32)
+        st["counters"][0] = el
+        st["counters"][3] = el
+        self.set_state({"counters": st["counters"]})
+
+    # ---- pipelined host path: env groups stepped asynchronously (include/so100_b200.h, so100_step_host_async)
+    def host_groups(self, n_groups: int) -> list[tuple[int, int]]:
+        """Split the envs into n_groups contiguous ranges; returns their (lo, hi) env indices."""
+        _native.check(self._L.so100_host_groups(self._h, int(n_groups)))
+        out = []
+        for g in range(int(n_groups)):
+            lo, hi = ctypes.c_int(0), ctypes.c_int(0)
+            _native.check(self._L.so100_host_group_range(self._h, g, ctypes.byref(lo), ctypes.byref(hi)))
+            out.append((int(lo.value), int(hi.value)))
+        return out
+
+    def step_host_async(self, host: dict, group: int, with_terminal: bool = True, actions: torch.Tensor | None = None) -> None:
+        """Enqueue one step of env group `group`: its rows of host['actions'] (or of `actions`, a pinned [N, 6] float32
+        tensor) in, its rows of the other (pinned) host buffers out; returns immediately.  `step_host_wait(group)` blocks
+        until those rows have landed."""
+        p = _host_ptrs(host, with_terminal)
+        a = p[0] if actions is None else actions.data_ptr()
+        _native.check(self._L.so100_step_host_async(self._h, int(group), a, p[1], p[2], p[3], p[4], p[5], p[6], p[7], self._stream()))
+
+    def step_host_wait(self, group: int) -> None:
+        _native.check(self._L.so100_step_host_wait(self._h, int(group)))
 
     # ---- state access (parity tests, checkpoints)
     _STATE_FIELDS = {"qpos": (6, torch.float32), "qvel": (6, torch.float32), "qacc_warm": (6, torch.float32), "qpos_comp": (6, torch.float32),

@@ -289,7 +289,7 @@ __device__ __forceinline__ float reward_reach(const TaskC& t, EnvRegs& e, bool i
 // ctrl is carried as an unevaluated sum ctrl_hi + ctrl_lo so that Env01/02's closed loop ctrl = qpos + a*0.075 does not
 // round the 0.075-rad increment to the ulp of a 3-rad angle (that rounding random-walks qpos in a neutrally stable loop).
 template <int TASK, bool SPEC>
-__device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs& e, const float* ctrl_hi, const float* ctrl_lo, bool live) {
+__device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs& e, const float* ctrl_hi, const float* ctrl_lo, bool live, int nsub) {
   const TaskC& t = C.t;
   // SPEC: the solver / servo constants of the so100 MJCF are literals (immediates after unrolling), not constant-bank loads
   ConC<float> Kg;
@@ -310,14 +310,14 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
   }
   bool unconverged = false;
 #pragma unroll 1
-  for (int sub = 0; sub < t.nsub; sub++) {
+  for (int sub = 0; sub < nsub; sub++) {
 #if SO100_SYNC
     __syncthreads();
 #endif
     float s[SO_NJ], c[SO_NJ], bias[SO_NJ], M[21], b[SO_NJ];
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) so_sincos(e.q[j], &s[j], &c[j]);
-    if (sub == t.nsub - 1) take_snapshot<TASK>(C, s, c, e);  // kinematics of the LAST substep's start state (Q3)
+    if (sub == nsub - 1) take_snapshot<TASK>(C, s, c, e);  // kinematics of the LAST substep's start state (Q3)
     if (SPEC) dyn_bias_mass_so100<float>(s, c, e.v, bias, M);  // constants folded at build time (so100 MJCF)
     else dyn_bias_mass<float>(C.dyn, s, c, e.v, bias, M);       // any other model: constants from the ctx
 #pragma unroll
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
           for (int k = 0; k < 3; k++) e.aux[k] = e.blk[k];
         }
       }
-      physics<TASK, SPEC>(C, B, e, ctrl, ctrl_lo, live);
+      physics<TASK, SPEC>(C, B, e, ctrl, ctrl_lo, live, t.nsub);
       write_obs<TASK>(t, e, i, tick, STREAM_NOISE, obs);
     } else {  // env03_v1.py:124-201
       float time = (float)e.elapsed * t.dt_env;
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
       float newcmd[SO_NJ];
 #pragma unroll
       for (int j = 0; j < SO_NJ; j++) { newcmd[j] = e.aux[j] + a[j] * t.step_scale; ctrl[j] = newcmd[j]; ctrl_lo[j] = 0.0f; }  // open loop (Q6)
-      physics<TASK, SPEC>(C, B, e, ctrl, ctrl_lo, live);
+      physics<TASK, SPEC>(C, B, e, ctrl, ctrl_lo, live, t.nsub);
       write_obs<TASK>(t, e, i, tick, STREAM_NOISE, obs);
       if (obs[6] == -1.0f && obs[7] == -1.0f) {  // :152-164
         if (e.miss > t.lost_limit) term = true;
@@ -464,6 +464,9 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
     for (int j = 0; j < SO_NJ; j++) chk += e.q[j] + e.v[j];
     bool bad = !isfinite(chk);
     if (bad && live) atomicAdd(&B.stats[1], 1ULL);
+    // A blown-up env ends its episode as TERMINATED (never truncated: a learner bootstraps truncations with
+    // V(terminal_obs)), with a finite reward and, below, a finite terminal observation (the reset one).
+    if (bad) { term = true; if (!isfinite(rew)) rew = 0.0f; }
     e.elapsed += 1;
     e.ep_ret += rew;
     bool trunc = e.elapsed >= t.max_steps;  // gymnasium TimeLimit
@@ -472,16 +475,19 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
       io.terminated[i] = term ? 1 : 0;
       io.truncated[i] = (trunc && !term) ? 1 : 0;
     }
-    if (term || trunc || bad) {
-      if (live && io.terminal_obs) {
+    if (term || trunc) {
+      if (live && io.terminal_obs && !bad) {
 #pragma unroll
         for (int k = 0; k < OD; k++) io.terminal_obs[(size_t)i * OD + k] = obs[k];
       }
       if (live && io.ep_return_out) io.ep_return_out[i] = e.ep_ret;
       if (live && io.ep_len_out) io.ep_len_out[i] = e.elapsed;
-      if (live && bad) io.truncated[i] = term ? 0 : 1;
       if (live && io.any_done) *io.any_done = 1;
       reset_env<TASK>(C, B, e, i, tick, STREAM_RESET, obs);
+      if (live && io.terminal_obs && bad) {
+#pragma unroll
+        for (int k = 0; k < OD; k++) io.terminal_obs[(size_t)i * OD + k] = obs[k];
+      }
     }
     if (live) store_env<TASK>(B, n, i, e);
 #pragma unroll
@@ -506,6 +512,22 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ C
   store_env<TASK>(B, n, i, e);
 #pragma unroll
   for (int k = 0; k < OD; k++) obs_out[(size_t)i * OD + k] = obs[k];
+}
+
+// debug / parity triage: n x mj_step under a given ctrl, no task logic (no reward / obs / counters / reset); the snapshot
+// is refreshed with the kinematics of the last substep's start state, as in a full env step
+template <int TASK, bool SPEC>
+__global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) substeps_kernel(const __grid_constant__ Consts C, const Bufs B, const float* ctrl, int nsub) {
+  const int n = C.t.n, base = blockIdx.x * kBlock;
+  const bool live = base + (int)threadIdx.x < n;
+  const int i = live ? base + (int)threadIdx.x : n - 1;  // tail threads shadow the last env (physics has CTA barriers)
+  EnvRegs e;
+  load_env<TASK>(B, n, i, e);
+  float ch[SO_NJ], cl[SO_NJ];
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) { ch[j] = ctrl[(size_t)i * SO_NJ + j]; cl[j] = 0.0f; }
+  physics<TASK, SPEC>(C, B, e, ch, cl, live, nsub);
+  if (live) store_env<TASK>(B, n, i, e);
 }
 
 // debug / parity: one cold-start forward-dynamics evaluation per sample
@@ -802,15 +824,24 @@ struct so100_ctx {
   float *h_act = nullptr, *h_obs = nullptr, *h_rew = nullptr, *h_tobs = nullptr, *h_epr = nullptr;
   uint8_t *h_term = nullptr, *h_trunc = nullptr;
   int* h_epl = nullptr;
-  // host path.  Pinned host buffers: the kernel reads the actions and writes obs / reward / flags straight through
-  // the host link (zero-copy), one launch per step.  Pageable buffers: chunks of envs on helper streams so that H2D,
-  // kernel and D2H overlap.
+  // host path.  Pinned host buffers: the kernel reads the actions and writes obs / reward / flags / terminal rows
+  // straight through the host link (zero-copy), one launch per call.  Pageable buffers: chunks of envs on helper
+  // streams so that H2D, kernel and D2H overlap.
   static constexpr int kMaxChunks = 16;
   int n_chunks = 2;
   bool zero_copy = true;
+  int host_min_ctas = 0;  // experiment knob SO100_HOST_CTAS_PER_SM=1: one CTA per SM (two waves at 65 536 envs)
   cudaStream_t hs[kMaxChunks] = {};
   cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {};
   int *d_any_done = nullptr, *p_any_done = nullptr;  // device flag + pinned host copy (the zero-copy path writes the latter)
+  // env groups of the asynchronous host path (so100_host_groups / so100_step_host_async / so100_step_host_wait):
+  // contiguous CTA-aligned env ranges, each with its own stream, completion event and step counter
+  static constexpr int kMaxGroups = SO100_MAX_GROUPS;
+  int n_groups = 1, g_lo[kMaxGroups] = {}, g_hi[kMaxGroups] = {};
+  int64_t g_tick[kMaxGroups] = {};
+  bool g_pending[kMaxGroups] = {};
+  cudaStream_t gs[kMaxGroups] = {};
+  cudaEvent_t g_done[kMaxGroups] = {}, g_fork = nullptr;
 };
 
 static void free_ctx(so100_ctx* c) {
@@ -826,12 +857,21 @@ static void free_ctx(so100_ctx* c) {
     if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
   }
   if (c->ev_start) cudaEventDestroy(c->ev_start);
+  for (int k = 0; k < so100_ctx::kMaxGroups; k++) {
+    if (c->gs[k]) cudaStreamDestroy(c->gs[k]);
+    if (c->g_done[k]) cudaEventDestroy(c->g_done[k]);
+  }
+  if (c->g_fork) cudaEventDestroy(c->g_fork);
   delete c;
 }
 
 extern "C" {
 
+#ifndef SO100_CSRC_HASH
+#define SO100_CSRC_HASH "unknown"
+#endif
 int so100_abi_version(void) { return SO100_ABI_VERSION; }
+const char* so100_build_id(void) { return SO100_CSRC_HASH; }
 const char* so100_last_error(void) { return g_err.c_str(); }
 int so100_obs_dim(int task) {
   if (task == SO100_TASK_ENV01 || task == SO100_TASK_ENV02 || task == SO100_TASK_ENV06) return 15;
@@ -919,6 +959,7 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
   for (int i = 0; i < kMaxStart; i++) for (int j = 0; j < SO_NJ; j++) tab[i * SO_NJ + j] = (float)cfg->start_positions[i][j];
   if (cudaMemcpy(c->start_tab, tab, sizeof tab, cudaMemcpyHostToDevice) != cudaSuccess) { free_ctx(c); return fail(SO100_ERR_CUDA, "cudaMemcpy(start table)"); }
   c->B.start_tab = c->start_tab;
+  c->n_groups = 1; c->g_lo[0] = 0; c->g_hi[0] = c->n;
   *out = c;
   return SO100_OK;
 }
@@ -943,26 +984,45 @@ int so100_reset(so100_ctx* c, const uint8_t* mask_dev, float* obs_dev, void* str
   return SO100_OK;
 }
 
-static int launch_step(so100_ctx* c, const StepIO& io, cudaStream_t st) {
+static int launch_step(so100_ctx* c, const StepIO& io, cudaStream_t st, size_t dyn_smem = 0) {
   const int g = grid_for(io.env_hi - io.env_lo);
+#define SO100_LAUNCH(T, S)                                                                                          \
+  do {                                                                                                              \
+    if (dyn_smem) cudaFuncSetAttribute(step_kernel<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem); \
+    step_kernel<T, S><<<g, kBlock, dyn_smem, st>>>(c->C, c->B, io);                                                  \
+  } while (0)
   if (c->specialised) {
     switch (c->task) {
-      case 1: step_kernel<1, true><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
-      case 2: step_kernel<2, true><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
-      case 6: step_kernel<6, true><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
-      default: step_kernel<5, true><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
+      case 1: SO100_LAUNCH(1, true); break;
+      case 2: SO100_LAUNCH(2, true); break;
+      case 6: SO100_LAUNCH(6, true); break;
+      default: SO100_LAUNCH(5, true); break;
     }
   } else {
     switch (c->task) {
-      case 1: step_kernel<1, false><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
-      case 2: step_kernel<2, false><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
-      case 6: step_kernel<6, false><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
-      default: step_kernel<5, false><<<g, kBlock, 0, st>>>(c->C, c->B, io); break;
+      case 1: SO100_LAUNCH(1, false); break;
+      case 2: SO100_LAUNCH(2, false); break;
+      case 6: SO100_LAUNCH(6, false); break;
+      default: SO100_LAUNCH(5, false); break;
     }
   }
+#undef SO100_LAUNCH
   c->launches++;
   CU(cudaGetLastError());
   return SO100_OK;
+}
+
+// a full step needs every env group at the same step count (they share the RNG tick)
+static int groups_in_step(so100_ctx* c) {
+  for (int g = 0; g < c->n_groups; g++) {
+    if (c->g_pending[g]) return fail(SO100_ERR_STATE, "an asynchronous group step is in flight: call so100_step_host_wait first");
+    if (c->g_tick[g] != c->tick) return fail(SO100_ERR_STATE, "env groups are at different step counts: advance the lagging groups first");
+  }
+  return SO100_OK;
+}
+static void set_all_ticks(so100_ctx* c, int64_t tick) {
+  c->tick = tick;
+  for (int g = 0; g < so100_ctx::kMaxGroups; g++) c->g_tick[g] = tick;
 }
 
 int so100_step(so100_ctx* c, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* terminated_dev,
@@ -970,9 +1030,37 @@ int so100_step(so100_ctx* c, const float* actions_dev, float* obs_dev, float* re
   if (!c || !actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail(SO100_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
-  c->tick += 1;
+  if (int rc = groups_in_step(c)) return rc;
+  set_all_ticks(c, c->tick + 1);
   StepIO io{actions_dev, obs_dev, reward_dev, terminal_obs_dev, ep_return_dev, terminated_dev, truncated_dev, ep_len_dev, (unsigned)c->tick, 0, c->n, nullptr};
   return launch_step(c, io, st);
+}
+
+int so100_step_substeps(so100_ctx* c, const float* ctrl_dev, int n_substeps, void* stream) {
+  if (!c || !ctrl_dev || n_substeps <= 0) return fail(SO100_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = grid_for(c->n);
+#define SO100_SUBSTEPS(T, S) substeps_kernel<T, S><<<g, kBlock, 0, st>>>(c->C, c->B, ctrl_dev, n_substeps)
+  if (c->specialised) {
+    switch (c->task) {
+      case 1: SO100_SUBSTEPS(1, true); break;
+      case 2: SO100_SUBSTEPS(2, true); break;
+      case 6: SO100_SUBSTEPS(6, true); break;
+      default: SO100_SUBSTEPS(5, true); break;
+    }
+  } else {
+    switch (c->task) {
+      case 1: SO100_SUBSTEPS(1, false); break;
+      case 2: SO100_SUBSTEPS(2, false); break;
+      case 6: SO100_SUBSTEPS(6, false); break;
+      default: SO100_SUBSTEPS(5, false); break;
+    }
+  }
+#undef SO100_SUBSTEPS
+  c->launches++;
+  CU(cudaGetLastError());
+  return SO100_OK;
 }
 
 static int ensure_staging(so100_ctx* c) {
@@ -998,6 +1086,12 @@ static int ensure_staging(so100_ctx* c) {
     CU(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
   }
   CU(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+  if (const char* e = getenv("SO100_HOST_CTAS_PER_SM")) c->host_min_ctas = atoi(e);  // experiment: 1 = two waves at 65 536 envs
+  for (int k = 0; k < so100_ctx::kMaxGroups; k++) {
+    CU(cudaStreamCreateWithFlags(&c->gs[k], cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->g_done[k], cudaEventDisableTiming));
+  }
+  CU(cudaEventCreateWithFlags(&c->g_fork, cudaEventDisableTiming));
   return SO100_OK;
 }
 
@@ -1053,29 +1147,53 @@ static void* mapped_alias(const void* host) {
   return a.devicePointer;
 }
 
+// Device-visible aliases of one set of host buffers; ok = every mandatory buffer (and every optional one that was
+// given) is page-locked and mapped, so one launch can read / write them in place.
+struct HostAlias {
+  const float* act; float *obs, *rew, *tobs, *epr; uint8_t *term, *trunc; int* epl; bool ok;
+};
+static HostAlias alias_host(const float* actions_host, float* obs_host, float* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
+                            float* terminal_obs_host, float* ep_return_host, int32_t* ep_len_host) {
+  HostAlias a{};
+  a.act = (const float*)mapped_alias(actions_host);
+  a.obs = a.act ? (float*)mapped_alias(obs_host) : nullptr;
+  a.rew = a.obs ? (float*)mapped_alias(reward_host) : nullptr;
+  a.term = a.rew ? (uint8_t*)mapped_alias(terminated_host) : nullptr;
+  a.trunc = a.term ? (uint8_t*)mapped_alias(truncated_host) : nullptr;
+  a.ok = a.trunc != nullptr;
+  if (a.ok && terminal_obs_host) a.ok = (a.tobs = (float*)mapped_alias(terminal_obs_host)) != nullptr;
+  if (a.ok && ep_return_host) a.ok = (a.epr = (float*)mapped_alias(ep_return_host)) != nullptr;
+  if (a.ok && ep_len_host) a.ok = (a.epl = (int*)mapped_alias(ep_len_host)) != nullptr;
+  return a;
+}
+// one CTA per SM for the host path's launch (experiment): a CTA's static shared memory + this much fills an SM
+static size_t host_dyn_smem(const so100_ctx* c) { return c->host_min_ctas == 1 ? 120 * 1024 : 0; }
+
 int so100_step_host(so100_ctx* c, const float* actions_host, float* obs_host, float* reward_host, uint8_t* terminated_host,
                     uint8_t* truncated_host, float* terminal_obs_host, float* ep_return_host, int32_t* ep_len_host, void* stream) {
   if (!c || !actions_host || !obs_host || !reward_host || !terminated_host || !truncated_host) return fail(SO100_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
   int rc = ensure_staging(c);
   if (rc) return rc;
+  if ((rc = groups_in_step(c))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t od = (size_t)c->obs_dim;
   const bool want_term = terminal_obs_host || ep_return_host || ep_len_host;
-  c->tick += 1;
-  const float* za = c->zero_copy ? (const float*)mapped_alias(actions_host) : nullptr;
-  float *zo = za ? (float*)mapped_alias(obs_host) : nullptr, *zr = zo ? (float*)mapped_alias(reward_host) : nullptr;
-  uint8_t *zt = zr ? (uint8_t*)mapped_alias(terminated_host) : nullptr, *zc = zt ? (uint8_t*)mapped_alias(truncated_host) : nullptr;
-  if (zc) {
-    // zero-copy: ONE launch; each CTA pulls its action rows over the host link and posts its obs / reward / flag
-    // rows back as coalesced stores, so the transfers of one CTA overlap the arithmetic of the others
-    *c->p_any_done = 0;
-    StepIO io{za, zo, zr, want_term ? c->h_tobs : nullptr, want_term ? c->h_epr : nullptr, zt, zc,
-              want_term ? c->h_epl : nullptr, (unsigned)c->tick, 0, c->n, (int*)mapped_alias(c->p_any_done)};
-    rc = launch_step(c, io, st);
-  } else {
-    rc = enqueue_host_pipeline(c, st, actions_host, obs_host, reward_host, terminated_host, truncated_host, want_term);
+  set_all_ticks(c, c->tick + 1);
+  HostAlias z{};
+  if (c->zero_copy) z = alias_host(actions_host, obs_host, reward_host, terminated_host, truncated_host, terminal_obs_host, ep_return_host, ep_len_host);
+  if (z.ok) {
+    // zero-copy: ONE launch.  Each CTA pulls its action rows over the host link when it starts and posts its obs /
+    // reward / flag rows (and, for envs whose episode ended, the terminal rows) when it ends.  65 536 envs are a single
+    // wave of CTAs, so the three phases are in series: actions in, ~85 us of arithmetic, results out; the pipelined
+    // alternative is so100_step_host_async over env groups.
+    StepIO io{z.act, z.obs, z.rew, z.tobs, z.epr, z.term, z.trunc, z.epl, (unsigned)c->tick, 0, c->n, nullptr};
+    rc = launch_step(c, io, st, host_dyn_smem(c));
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(st));
+    return SO100_OK;
   }
+  rc = enqueue_host_pipeline(c, st, actions_host, obs_host, reward_host, terminated_host, truncated_host, want_term);
   if (rc) return rc;
   CU(cudaStreamSynchronize(st));
   if (want_term && *c->p_any_done) {  // the terminal rows are only meaningful for envs that finished: copy them only then
@@ -1085,6 +1203,60 @@ int so100_step_host(so100_ctx* c, const float* actions_host, float* obs_host, fl
     if (ep_len_host) CU(cudaMemcpyAsync(ep_len_host, c->h_epl, n * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
   }
+  return SO100_OK;
+}
+
+// ---- asynchronous host path over env groups
+int so100_host_groups(so100_ctx* c, int n_groups) {
+  if (!c || n_groups < 1 || n_groups > so100_ctx::kMaxGroups) return fail(SO100_ERR_ARG, "n_groups out of range");
+  if (int rc = groups_in_step(c)) return rc;
+  const int ctas = grid_for(c->n);
+  if (n_groups > ctas) return fail(SO100_ERR_ARG, "more groups than CTAs of envs");
+  for (int g = 0; g < n_groups; g++) {  // balanced, CTA-aligned, contiguous
+    c->g_lo[g] = (int)((int64_t)ctas * g / n_groups) * kBlock;
+    int hi = (int)((int64_t)ctas * (g + 1) / n_groups) * kBlock;
+    c->g_hi[g] = hi < c->n ? hi : c->n;
+  }
+  c->n_groups = n_groups;
+  return SO100_OK;
+}
+int so100_host_group_range(so100_ctx* c, int group, int* env_lo, int* env_hi) {
+  if (!c || group < 0 || group >= c->n_groups) return fail(SO100_ERR_ARG, "no such env group");
+  if (env_lo) *env_lo = c->g_lo[group];
+  if (env_hi) *env_hi = c->g_hi[group];
+  return SO100_OK;
+}
+
+int so100_step_host_async(so100_ctx* c, int group, const float* actions_host, float* obs_host, float* reward_host, uint8_t* terminated_host,
+                          uint8_t* truncated_host, float* terminal_obs_host, float* ep_return_host, int32_t* ep_len_host, void* stream) {
+  if (!c || !actions_host || !obs_host || !reward_host || !terminated_host || !truncated_host) return fail(SO100_ERR_ARG, "null argument");
+  if (group < 0 || group >= c->n_groups) return fail(SO100_ERR_ARG, "no such env group");
+  if (c->g_pending[group]) return fail(SO100_ERR_STATE, "this group already has a step in flight: call so100_step_host_wait first");
+  CU(cudaSetDevice(c->device));
+  int rc = ensure_staging(c);
+  if (rc) return rc;
+  HostAlias z = alias_host(actions_host, obs_host, reward_host, terminated_host, truncated_host, terminal_obs_host, ep_return_host, ep_len_host);
+  if (!z.ok) return fail(SO100_ERR_ARG, "so100_step_host_async needs page-locked (pinned / registered) host buffers");
+  cudaStream_t gs = c->gs[group];
+  if (stream != (void*)gs) {  // order after whatever the caller has enqueued on its own stream (a reset, a set_state)
+    CU(cudaEventRecord(c->g_fork, (cudaStream_t)stream));
+    CU(cudaStreamWaitEvent(gs, c->g_fork, 0));
+  }
+  c->g_tick[group] += 1;
+  if (c->g_tick[group] > c->tick) c->tick = c->g_tick[group];
+  StepIO io{z.act, z.obs, z.rew, z.tobs, z.epr, z.term, z.trunc, z.epl, (unsigned)c->g_tick[group], c->g_lo[group], c->g_hi[group], nullptr};
+  rc = launch_step(c, io, gs);
+  if (rc) return rc;
+  CU(cudaEventRecord(c->g_done[group], gs));
+  c->g_pending[group] = true;
+  return SO100_OK;
+}
+
+int so100_step_host_wait(so100_ctx* c, int group) {
+  if (!c || group < 0 || group >= c->n_groups) return fail(SO100_ERR_ARG, "no such env group");
+  if (!c->g_pending[group]) return SO100_OK;
+  CU(cudaEventSynchronize(c->g_done[group]));
+  c->g_pending[group] = false;
   return SO100_OK;
 }
 
@@ -1114,7 +1286,7 @@ int so100_get_tick(so100_ctx* c, int64_t* tick) {
 }
 int so100_set_tick(so100_ctx* c, int64_t tick) {
   if (!c || tick < 0) return fail(SO100_ERR_ARG, "bad argument");
-  c->tick = tick;
+  set_all_ticks(c, tick);
   return SO100_OK;
 }
 

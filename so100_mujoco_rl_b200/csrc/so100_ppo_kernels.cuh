@@ -286,7 +286,10 @@ __global__ void __launch_bounds__(256) post_step_kernel(Layout L, const float* _
     r = reward[i];
     const bool tr = trunc[i] != 0, done = tr || term[i] != 0;
     float ro = r;
-    if (tr) ro += gamma * value_one(L, P, tobs + (size_t)i * L.od);  // TimeLimit bootstrap (SB3 on_policy_algorithm.collect_rollouts)
+    if (tr) {  // TimeLimit bootstrap (SB3 on_policy_algorithm.collect_rollouts); a non-finite value never enters the returns
+      const float boot = gamma * value_one(L, P, tobs + (size_t)i * L.od);
+      if (isfinite(boot)) ro += boot;
+    }
     reward_out[i] = ro;
     done_out[i] = done ? 1.0f : 0.0f;
     if (done) { er = ep_return[i]; el = (float)ep_len[i]; dn = 1.0f; }

@@ -237,7 +237,7 @@ class PPO(_LearnLoop):
             # TimeLimit: bootstrap with the value of the terminal observation (SB3 on_policy_algorithm); rows of envs
             # that did not finish hold stale (finite) data and are masked out
             boot = cfg.gamma * self.policy.value(r.terminal_obs)
-            rew = torch.where(trunc, rew + boot, rew)
+            rew = torch.where(trunc & torch.isfinite(boot), rew + boot, rew)
             b["rew"][t], b["done"][t] = rew, done.float()
             df = done.float()
             self._acc[1] += (r.ep_return * df).sum(); self._acc[2] += (r.ep_len.float() * df).sum(); self._acc[3] += df.sum()
@@ -276,29 +276,38 @@ class PPO(_LearnLoop):
         self.opt.step()
         self._last_info.copy_(torch.stack([pg.detach(), vl.detach(), ((ratio - 1) - lr).mean().detach()]))
 
+    def _restore_optimizer(self, saved: dict) -> None:
+        """Write a saved `opt.state_dict()` back IN PLACE (a captured graph holds the addresses of the live state
+        tensors); entries the snapshot lacks (fresh optimiser) restart from zero."""
+        params = [p for g in self.opt.param_groups for p in g["params"]]
+        for i, p in enumerate(params):
+            old = saved["state"].get(i, {})
+            for k, v in self.opt.state.get(p, {}).items():
+                if torch.is_tensor(v):
+                    if k in old:
+                        v.copy_(torch.as_tensor(old[k]).to(device=v.device, dtype=v.dtype))
+                    else:
+                        v.zero_()
+
     def _build_graph(self, flat, mb):
-        """Capture one minibatch step on static tensors; replayed n_epochs * n_minibatches times per iteration."""
+        """Capture one minibatch step on static tensors; replayed n_epochs * n_minibatches times per iteration.
+        Weights AND optimiser state (Adam moments, step: possibly restored from a checkpoint before the first update)
+        are snapshotted before the warm-up steps and written back after capture."""
+        import copy
         self._idx = torch.zeros(mb, dtype=torch.long, device=self.device)
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
-        saved = ({k: v.clone() for k, v in self.policy.state_dict().items()}, None)
+        saved = {k: v.clone() for k, v in self.policy.state_dict().items()}
+        saved_opt = copy.deepcopy(self.opt.state_dict())
         with torch.cuda.stream(side):  # warm-up outside capture (allocations, optimizer state)
             for _ in range(3):
                 self._minibatch_step(self._idx, flat, self._adv, self._ret)
         torch.cuda.current_stream(self.device).wait_stream(side)
-        self.policy.load_state_dict(saved[0])  # undo the warm-up updates (Adam moments restart from the warm-up; negligible)
-        for st in self.opt.state.values():
-            for k, v in st.items():
-                if torch.is_tensor(v):
-                    v.zero_()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._minibatch_step(self._idx, flat, self._adv, self._ret)
-        self.policy.load_state_dict(saved[0])
-        for st in self.opt.state.values():
-            for k, v in st.items():
-                if torch.is_tensor(v):
-                    v.zero_()
+        self.policy.load_state_dict(saved)  # undo the warm-up updates
+        self._restore_optimizer(saved_opt)
 
     def update(self, adv, ret):
         cfg, b = self.cfg, self.buf

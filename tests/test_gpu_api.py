@@ -60,8 +60,28 @@ def test_non_finite_state_is_reset_and_counted():
     r = env.step(torch.zeros((n, 6), device="cuda"))
     assert env.stats()["nan_resets"] == 2
     assert torch.isfinite(r.obs).all()
-    assert r.truncated[7] == 1 and r.truncated[9] == 1 and int(r.truncated.sum()) == 2
+    # a blown-up env is TERMINATED, never truncated (learners bootstrap truncations with V(terminal_obs)), and what it
+    # reports is finite: reward, terminal observation (the reset one), episode return
+    assert r.terminated[7] == 1 and r.terminated[9] == 1 and int(r.terminated.sum()) == 2 and int(r.truncated.sum()) == 0
+    assert torch.isfinite(r.terminal_obs[[7, 9]]).all() and torch.equal(r.terminal_obs[[7, 9]], r.obs[[7, 9]])
+    assert torch.isfinite(r.reward).all() and torch.isfinite(r.ep_return[[7, 9]]).all()
     assert (env.get_state()["counters"][0, [7, 9]] == 0).all()
+
+
+@pytest.mark.parametrize("task", [1, 5])
+def test_non_finite_env_does_not_poison_the_fused_learner(task):
+    from so100_mujoco_rl_b200.ppo import FusedPPO, PPOConfig
+    env = _env(task, 256, seed=4)
+    algo = FusedPPO(env, PPOConfig(n_steps=4, n_minibatches=2, n_epochs=1, seed=1))
+    algo.collect()
+    st = env.get_state()
+    st["qvel"][1, 3] = float("nan")
+    env.set_state(st)
+    adv, ret = algo.collect()
+    assert env.stats()["nan_resets"] >= 1
+    assert torch.isfinite(adv).all() and torch.isfinite(ret).all() and torch.isfinite(algo.buf["obs"]).all()
+    algo.update(adv, ret)
+    assert torch.isfinite(algo.params).all()
 
 
 def test_argument_errors_surface_as_exceptions():
@@ -183,3 +203,51 @@ def test_reseeding_rekeys_the_device_rng():
     v.seed(5); third = v.reset().copy()
     assert not np.array_equal(first, second) and np.array_equal(first, third)
     v.close()
+
+
+@pytest.mark.parametrize("task,n,groups", [(1, 1000, 3), (5, 4096, 4), (2, 300, 2)])
+def test_async_env_groups_equal_the_full_batch_step(task, n, groups):
+    """so100_step_host_async over every group once == one so100_step_host call, bit for bit (each group counts its own
+    steps; the RNG tick of a group's k-th step is k), also with short episodes so that auto-reset and the terminal rows
+    are exercised, and with the groups finishing in a different order than they were issued."""
+    from so100_mujoco_rl_b200 import _native
+    e1, e2 = _env(task, n, seed=6, max_episode_steps=7), _env(task, n, seed=6, max_episode_steps=7)
+    h1, h2 = e1.alloc_host(), e2.alloc_host()
+    assert torch.equal(e1.reset_host(h1), e2.reset_host(h2))
+    ranges = e2.host_groups(groups)
+    assert ranges[0][0] == 0 and ranges[-1][1] == n and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    rng = np.random.default_rng(0)
+    for t in range(20):
+        a = torch.from_numpy(rng.uniform(-1, 1, (n, 6)).astype(np.float32))
+        h1["actions"].copy_(a); h2["actions"].copy_(a)
+        e1.step_host(h1)
+        order = list(range(groups)) if t % 2 == 0 else list(reversed(range(groups)))
+        for g in order:
+            e2.step_host_async(h2, g)
+        for g in range(groups):
+            e2.step_host_wait(g)
+        for k in ("obs", "reward", "terminated", "truncated"):
+            assert torch.equal(h1[k], h2[k]), (k, t)
+        done = (h1["terminated"] | h1["truncated"]).bool()
+        if done.any():
+            for k in ("terminal_obs", "ep_return", "ep_len"):
+                assert torch.equal(h1[k][done], h2[k][done]), (k, t)
+    assert e1.tick == e2.tick == 20
+    # groups out of step: the full-batch calls refuse until the lagging groups have caught up
+    e2.step_host_async(h2, 0)
+    with pytest.raises(_native.So100Error, match="in flight"):
+        e2.step_host(h2)
+    e2.step_host_wait(0)
+    with pytest.raises(_native.So100Error, match="different step counts"):
+        e2.step(torch.zeros((n, 6), device="cuda"))
+    with pytest.raises(_native.So100Error, match="already has a step in flight"):
+        e2.step_host_async(h2, 1); e2.step_host_async(h2, 1)
+    for g in range(1, groups):
+        e2.step_host_wait(g)
+        if g > 1:
+            e2.step_host_async(h2, g); e2.step_host_wait(g)
+    e2.step_host(h2)   # all groups at 21 now
+    assert e2.tick == 22
+    with pytest.raises(_native.So100Error, match="page-locked"):
+        pageable = {k: torch.zeros_like(v) for k, v in h2.items()}
+        e2.step_host_async(pageable, 0)

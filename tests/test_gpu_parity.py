@@ -1,10 +1,17 @@
 """GPU parity: the CUDA path (through the C ABI) against the fp64 oracle on the same seeds and actions.
 
-Tolerances (fp32 kernel vs fp64 oracle, BASELINE.md §4 / SURVEY D4): over `steps` env steps of U(-1,1) actions
-max |dqpos| <= 2e-5 rad, max |dqvel| <= 1e-3 rad/s, max |dobs| <= 2e-5 (Env05 centre: one raster pixel where the
-int() truncation flips), max |dreward| <= 1e-4 (Env05: 2e-3, one pixel).  Measured on B200 (profiles/r1_*_parity.json):
-max |dqpos| 5e-7 (Env01/02) / 4e-6 (Env05) over 256 envs x 600 steps; the slack covers the rare joint-limit
-activation that lands within one fp32 ulp of a substep boundary.
+The oracle is the repo's fp64 RESTATEMENT of MuJoCo's mj_step for this model (oracle/so100_oracle.c); it has never been
+compared with MuJoCo itself (not installable here), so "parity" below means fp32 kernel vs that restatement.
+
+Stated tolerance, in the form a discontinuous model admits - bulk quantiles plus an event rate:
+  * bulk:    p99.9 of |dqpos| over all (env, step) samples < 5e-6 rad, median < 1e-6 rad;
+  * events:  the fraction of samples with |dqpos| > 2e-5 rad is < 1e-5 (Env01/02/06) - a joint-limit row or a contact
+             corner that engages one substep apart in fp32 and fp64; they decay within a few steps;
+  * splits:  an env whose done flags differ from the oracle's (Env05: a projected cube on the other side of a raster
+             edge moves a lost-cube termination by a step) is counted as bifurcated and dropped from then on; the
+             count is bounded; for every other env the flags are identical at every step.
+The small fixed-seed runs below (256 envs x 300 steps) additionally assert max-norms (TOL_*): no event falls into them.
+`test_parity_at_baseline_size` asserts the quantile form at the BASELINE size, 65 536 envs, from a decorrelated state.
 """
 import numpy as np
 import pytest
@@ -325,3 +332,50 @@ def test_large_sample_parity_statistics(task):
     assert np.quantile(dq, 0.999) < 5e-6 and np.median(dq) < 1e-6
     assert (dq > TOL_Q).mean() < 1e-4                # tolerance exceedances are isolated events
     env.close()
+
+
+@pytest.mark.parametrize("task", [1, 2, 5])
+def test_parity_at_baseline_size(task):
+    """BASELINE.json configs 2-4 at their size: 65 536 envs.  The CUDA path is advanced to a decorrelated state
+    (episode clocks staggered over the TimeLimit + 100 steps of random actions), the fp64 oracle adopts that state
+    (so100_get_state -> orc_set_state_soa), and both replay the same 16 steps (1.05e6 (env, step) samples) on all host
+    threads.  Asserted: the stated tolerance in its quantile + event-rate form, and identical done flags for every env
+    that has not bifurcated."""
+    n, K, seed = 65536, 16, 0
+    env = _gpu_env(task, n, seed=seed)
+    env.reset()
+    env.stagger_episodes()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for _ in range(100):
+        env.step(torch.rand((n, 6), device="cuda", generator=g) * 2 - 1)
+    o = make_oracle(task, n, seed=seed)
+    o.set_state_soa({k: v.cpu().numpy() for k, v in env.get_state().items()})
+    o.tick = env.tick
+    alive = np.ones(n, dtype=bool)
+    dq, dv, drew, ndone = [], [], [], 0
+    for t in range(K):
+        a = torch.rand((n, 6), device="cuda", generator=g) * 2 - 1
+        r = env.step(a)
+        oo, ro, to, co, *_ = o.step(a.cpu().numpy(), nthreads=0)
+        tg, cg = r.terminated.cpu().numpy(), r.truncated.cpu().numpy()
+        alive &= ~((tg != to) | (cg != co))
+        ndone += int(((to | co) != 0).sum())
+        st = env.get_state()
+        qo, vo, _ = o.get_state_soa()
+        qg = st["qpos"].cpu().numpy().astype(np.float64) - st["qpos_comp"].cpu().numpy()
+        dq.append(np.where(alive, np.abs(qg - qo).max(axis=0), 0.0))
+        dv.append(np.where(alive, np.abs(st["qvel"].cpu().numpy() - vo).max(axis=0), 0.0))
+        drew.append(np.where(alive, np.abs(r.reward.cpu().numpy() - ro), 0.0))
+    dq, dv, drew = np.array(dq), np.array(dv), np.array(drew)
+    split = int((~alive).sum())
+    rate = float((dq > TOL_Q).mean())
+    print(f"task {task} @ {n} envs x {K} steps: |dq| median {np.median(dq):.2e} p99.9 {np.quantile(dq, 0.999):.2e} max {dq.max():.2e}; "
+          f"rate(|dq| > {TOL_Q:g}) {rate:.2e}; |dv| p99.9 {np.quantile(dv, 0.999):.2e}; |drew| p99.9 {np.quantile(drew, 0.999):.2e}; "
+          f"bifurcated {split}; episodes ended {ndone}")
+    assert ndone > 0                                   # auto-reset ran inside the compared window
+    assert np.median(dq) < 1e-6 and np.quantile(dq, 0.999) < 5e-6
+    assert rate < (1e-5 if task != 5 else 5e-5)
+    assert np.quantile(drew, 0.999) < (1e-4 if task != 5 else 2e-3)
+    assert split <= (0 if task != 5 else 10)           # Env01/02 never terminate: their flags can only be TimeLimit's
+    env.close()
+

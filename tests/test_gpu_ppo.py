@@ -224,3 +224,26 @@ def test_fused_learner_state_roundtrip_resumes_bit_exactly():
     idx = torch.randperm(a.adv.numel(), device="cuda")[:1024]
     a.minibatch_step(idx, a.adv, a.ret); b.minibatch_step(idx, a.adv, a.ret)
     assert torch.equal(a.params, b.params)
+
+
+def test_torch_learner_resume_keeps_adam_state_under_cuda_graph():
+    """with cuda_graph=True the graph is built lazily on the first update(), AFTER load_state_dict; the
+    warm-up steps of the capture must not wipe the restored Adam moments / step.  The resumed learner's next update
+    has to equal the uninterrupted learner's."""
+    from so100_mujoco_rl_b200.batched_env import BatchedSo100Env
+    from so100_mujoco_rl_b200.ppo import PPO, PPOConfig, pack_params
+    cfg = PPOConfig(n_steps=4, n_minibatches=2, n_epochs=1, seed=5, cuda_graph=True)
+    a = PPO(BatchedSo100Env(1, 256, device=0, seed=9), cfg)
+    a.learn(total_samples=256 * 4 * 2, log_every=0, callback=lambda r: None)
+    sd = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in a.state_dict().items()}
+    b = PPO(BatchedSo100Env(1, 256, device=0, seed=9), cfg)
+    b.load_state_dict(sd)
+    for k in a.buf:
+        b.buf[k].copy_(a.buf[k])
+    adv, ret = torch.randn_like(a.buf["rew"]), torch.randn_like(a.buf["rew"])
+    torch.manual_seed(123); a.update(adv, ret)
+    torch.manual_seed(123); b.update(adv, ret)   # builds b's graph here, after the restore
+    sa, sb = a.opt.state_dict()["state"], b.opt.state_dict()["state"]
+    assert all(float(sa[k]["step"]) == float(sb[k]["step"]) for k in sa), "Adam step was reset by the graph capture"
+    assert all(torch.allclose(sa[k]["exp_avg"], sb[k]["exp_avg"], atol=1e-7) for k in sa)
+    assert torch.allclose(pack_params(a.policy), pack_params(b.policy), atol=1e-6)

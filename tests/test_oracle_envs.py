@@ -167,3 +167,40 @@ def test_env06_gripper_reward_and_no_relocation():
     assert np.allclose(r1, grip + pen, atol=1e-9)                       # very first step: guards closed, bonus 0
     _, r2, *_ = o.step(zeros(4))
     assert (r2 < 0).all()                                               # real kinematics now: not in reach any more
+
+
+@pytest.mark.parametrize("task", [1, 2, 5])
+def test_bulk_state_exchange_resumes_a_trajectory(task):
+    """orc_set_state_soa (the product's so100_state_view layout) carries everything a run needs: an oracle that adopts
+    another oracle's state (through float32, as it comes from the GPU) continues with the same flags and, to float32
+    rounding of the hand-over, the same observations and rewards."""
+    n = 24
+    a, b = make_oracle(task, n, seed=3, max_episode_steps=40), make_oracle(task, n, seed=3, max_episode_steps=40)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(1)
+    for _ in range(30):
+        a.step(rng.uniform(-1, 1, (n, 6)).astype(np.float32))
+    f32 = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float64).T, dtype=np.float32)  # noqa: E731  [N, k] -> [k, N]
+    snap, aux, cnt = np.zeros((12, n), np.float32), np.zeros((24, n), np.float32), np.zeros((4, n), np.int32)
+    if task == 5:
+        snap[:3], snap[3:12] = f32(a.gather("cam_xpos")), f32(a.gather("cam_xmat"))
+        aux[:6], aux[6:12], aux[12:15] = f32(a.gather("cmd")), f32(a.gather("last_angvel")), f32(a.gather("target"))
+        aux[15], aux[16:18] = a.gather("target_dt"), f32(a.gather("last_centre"))
+        cnt[2], cnt[3] = a.gather("miss_count"), np.round(a.gather("target_time") / 0.032)
+    else:
+        snap[:3], snap[3], snap[4:7] = f32(a.gather("end_pos")), a.gather("wrist_pos")[:, 2], f32(a.gather("block_xpos"))
+        aux[:3], aux[3:6] = f32(a.gather("task_block_pos")), f32(a.gather("last_block_pos"))
+    cnt[0] = a.gather("elapsed_steps")
+    cnt[1] = a.gather("ever_stepped") | (a.gather("has_last_block") << 1) | (a.gather("angvel_valid") << 2) | (a.gather("centre_valid") << 3)
+    block = np.concatenate([f32(a.gather("block")), a.gather("block_vz")[None].astype(np.float32)])
+    b.set_state_soa({"qpos": f32(a.gather("qpos")), "qvel": f32(a.gather("qvel")), "qacc_warm": f32(a.gather("qacc_warm")),
+                     "block": block, "snap": snap, "aux": aux, "counters": cnt, "ep_return": a.gather("ep_return").astype(np.float32)})
+    b.tick = a.tick
+    qa, va, ba = a.get_state_soa(); qb, vb, bb = b.get_state_soa()
+    assert np.abs(qa - qb).max() < 3e-7 and np.abs(va - vb).max() < 1e-5 and np.abs(ba - bb).max() < 1e-7
+    for _ in range(15):   # crosses the 40-step TimeLimit
+        act = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        oa, ra, ta, ca, *_ = a.step(act); ob, rb, tb, cb, *_ = b.step(act)
+        assert (ta == tb).all() and (ca == cb).all()
+        cols = slice(0, 6) if task == 5 else slice(None)
+        assert np.abs(oa[:, cols] - ob[:, cols]).max() < 2e-5 and np.abs(ra - rb).max() < 5e-3
