@@ -43,7 +43,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--subproc-harness", type=float, default=0.0, help=argparse.SUPPRESS)  # internal: run the SubprocVecEnv-style CPU harness for this many seconds
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-groups", type=int, default=4, help="env groups of the pipelined host path (so100_step_host_async)")
+    ap.add_argument("--e2e-device-buffers", default="", choices=["", "in", "out", "both"], help=argparse.SUPPRESS)  # experiment: the pipeline without the host link (needs SO100_HOST_ALLOW_DEVICE=1); not an e2e number
+    ap.add_argument("--e2e-groups", type=int, default=8, help="env groups of the pipelined host path (so100_step_host_async)")
     ap.add_argument("--no-tasks", action="store_true", help="skip the Env02 / Env05 records (BASELINE configs 3, 4)")
     ap.add_argument("--no-ppo", action="store_true", help="skip the Env05 PPO record (BASELINE config 5)")
     ap.add_argument("--flags", type=int, default=0, help="SO100_FLAG_* bits for the env (e.g. 16 = no arm-floor contact)")
@@ -355,40 +356,45 @@ def main():
         od = OBS_DIM[task]
         host = env.alloc_host()
         host_ring = [r.cpu().pin_memory() for r in ring[:8]]
+        if args.e2e_device_buffers in ("out", "both"):
+            host = {k: v.to(dev) for k, v in host.items()}
+        if args.e2e_device_buffers in ("in", "both"):
+            host_ring = ring[:8]
+        st_ptr = torch.cuda.current_stream(dev).cuda_stream
         # (a) the synchronous call (what the SB3 VecEnv adapter makes): one launch, phases in series
-        for w in range(max(warmup, 8)):
-            env.step_host(host, actions=host_ring[w % 8])
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(steps):
-            env.step_host(host, actions=host_ring[k % 8])
-        barrier()
-        sync_s = time.perf_counter() - t0
+        sync_s = float("nan")
+        if not args.e2e_device_buffers:
+            for w in range(max(warmup, 8)):
+                env.step_host(host, actions=host_ring[w % 8])
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(steps):
+                env.step_host(host, actions=host_ring[k % 8])
+            barrier()
+            sync_s = time.perf_counter() - t0
         # (b) the pipelined call: G env groups in rotation, each step of a group = its action rows in from pinned host
         # memory, its obs / reward / flag rows back into pinned host memory; the host waits for a group's rows before it
         # issues that group's next step (the policy's data dependency), while the other groups keep the GPU and both
-        # directions of the link busy
+        # directions of the link busy; groups are served in completion order (so100_step_host_wait_any)
         G = max(1, min(args.e2e_groups, 16))
         env.host_groups(G)
-        for g_ in range(G):
-            env.step_host_async(host, g_, actions=host_ring[0])
-        for w in range(1, max(warmup, 8)):
+        def rotate(nsteps):
+            """Every group takes `nsteps` steps; a group's next step is issued as soon as ITS previous rows are on the host."""
+            count = [1] * G
             for g_ in range(G):
-                env.step_host_wait(g_)
-                env.step_host_async(host, g_, actions=host_ring[w % 8])
-        for g_ in range(G):
-            env.step_host_wait(g_)
+                env.step_host_async(host, g_, actions=host_ring[0], stream=st_ptr)
+            left = G * nsteps
+            while left:
+                g_ = env.step_host_wait_any()
+                left -= 1
+                if count[g_] < nsteps:
+                    env.step_host_async(host, g_, actions=host_ring[count[g_] % 8], stream=st_ptr)
+                    count[g_] += 1
+
+        rotate(max(warmup, 8))
         barrier()
         t0 = time.perf_counter()
-        for g_ in range(G):
-            env.step_host_async(host, g_, actions=host_ring[0])
-        for k in range(1, steps):
-            a = host_ring[k % 8]
-            for g_ in range(G):
-                env.step_host_wait(g_)
-                env.step_host_async(host, g_, actions=a)
-        for g_ in range(G):
-            env.step_host_wait(g_)
+        rotate(steps)
         barrier()
         pipe_s = time.perf_counter() - t0
         done_rows = float((host["terminated"] | host["truncated"]).sum())

@@ -207,8 +207,7 @@ int so100_step_substeps(so100_ctx *ctx, const float *ctrl_dev, int n_substeps, v
  * results out) run in series; so100_step_host_async below overlaps them across env groups.  Pageable buffers go through
  * chunked H2D copy -> kernel -> D2H copy on helper streams (terminal rows are then copied only on steps in which some
  * episode ended).
- * Environment knobs (experiments): SO100_HOST_ZEROCOPY=0 forces the copy pipeline, SO100_HOST_CHUNKS=1..16 its chunk
- * count, SO100_HOST_CTAS_PER_SM=1 launches the zero-copy kernel one CTA per SM (two waves at 65 536 envs).
+ * Environment knobs (experiments): SO100_HOST_ZEROCOPY=0 forces the copy pipeline, SO100_HOST_CHUNKS=1..16 its chunk count.
  */
 int so100_reset_host(so100_ctx *ctx, float *obs_host, void *stream);
 int so100_step_host(so100_ctx *ctx, const float *actions_host, float *obs_host, float *reward_host,
@@ -224,7 +223,8 @@ int so100_step_host(so100_ctx *ctx, const float *actions_host, float *obs_host, 
  * one group's results cross the host link while another group's arithmetic runs, and the link is used in both
  * directions at once; the floor is max(kernel, D2H) instead of their sum.
  * All pointers are the FULL [num_envs, dim] host arrays of so100_step_host (page-locked: required here); a group reads
- * and writes only its own rows.  `stream` is the caller's stream: the group's work is ordered after what it holds.
+ * and writes only its own rows.  `stream` is the caller's stream: the group's step is ordered after the work this library
+ * has enqueued on it (so100_reset, so100_set_state, ...).
  * Every group counts its own steps; the RNG tick of a group's k-th step is k, so stepping all groups once equals one
  * so100_step_host / so100_step call bit for bit.  Full-batch calls (so100_step, so100_step_host) return
  * SO100_ERR_STATE while groups are at different step counts or have a step in flight.
@@ -235,6 +235,9 @@ int so100_step_host_async(so100_ctx *ctx, int group, const float *actions_host, 
                           uint8_t *terminated_host, uint8_t *truncated_host, float *terminal_obs_host,
                           float *ep_return_host, int32_t *ep_len_host, void *stream);
 int so100_step_host_wait(so100_ctx *ctx, int group);
+/* Blocks until ANY group with a step in flight has finished and returns its index in *group (-1: nothing in flight).
+   Serving groups in completion order keeps them from queueing up behind the slowest one. */
+int so100_step_host_wait_any(so100_ctx *ctx, int *group);
 
 int so100_get_state(so100_ctx *ctx, const so100_state_view *view, void *stream);
 int so100_set_state(so100_ctx *ctx, const so100_state_view *view, void *stream);

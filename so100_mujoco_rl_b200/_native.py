@@ -21,7 +21,7 @@ EXPORTS = [
     "so100_get_tick", "so100_set_tick", "so100_forward_dynamics", "so100_host_forward", "so100_get_derived",
     "so100_get_stats", "so100_bench_fp32_peak", "so100_host_constants", "so100_kernel_variant",
     "so100_host_solver_constants", "so100_set_seed", "so100_step_substeps",
-    "so100_host_groups", "so100_host_group_range", "so100_step_host_async", "so100_step_host_wait",
+    "so100_host_groups", "so100_host_group_range", "so100_step_host_async", "so100_step_host_wait", "so100_step_host_wait_any",
     # include/so100_ppo.h
     "so100_ppo_param_count", "so100_ppo_workspace_floats", "so100_ppo_act", "so100_ppo_post_step", "so100_ppo_gae",
     "so100_ppo_grad", "so100_ppo_adam", "so100_ppo_permutation",
@@ -72,6 +72,7 @@ def lib() -> ctypes.CDLL:
     L.so100_host_group_range.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
     L.so100_step_host_async.argtypes = [vp, ci] + [vp] * 8 + [vp]
     L.so100_step_host_wait.argtypes = [vp, ci]
+    L.so100_step_host_wait_any.argtypes = [vp, ctypes.POINTER(ci)]
     L.so100_get_state.argtypes = [vp, ctypes.POINTER(StateView), vp]
     L.so100_set_state.argtypes = [vp, ctypes.POINTER(StateView), vp]
     L.so100_get_tick.argtypes = [vp, i64p]

@@ -77,6 +77,7 @@ class BatchedSo100Env:
         _native.check(self._L.so100_create(ctypes.byref(self._model_ct), ctypes.byref(self._cfg_ct),
                                            self.device.index, ctypes.byref(h)))
         self._h = h
+        self._any_group = ctypes.c_int(-1)
         n, od = self.num_envs, self.obs_dim
         f32 = dict(dtype=torch.float32, device=self.device)
         self.obs = torch.zeros((n, od), **f32)
@@ -184,16 +185,29 @@ class BatchedSo100Env:
             out.append((int(lo.value), int(hi.value)))
         return out
 
-    def step_host_async(self, host: dict, group: int, with_terminal: bool = True, actions: torch.Tensor | None = None) -> None:
+    def step_host_async(self, host: dict, group: int, with_terminal: bool = True, actions: torch.Tensor | None = None,
+                        stream: int | None = None) -> None:
         """Enqueue one step of env group `group`: its rows of host['actions'] (or of `actions`, a pinned [N, 6] float32
         tensor) in, its rows of the other (pinned) host buffers out; returns immediately.  `step_host_wait(group)` blocks
-        until those rows have landed."""
+        until those rows have landed.  `stream` (a cudaStream_t as int) saves the lookup of torch's current stream."""
         p = _host_ptrs(host, with_terminal)
-        a = p[0] if actions is None else actions.data_ptr()
-        _native.check(self._L.so100_step_host_async(self._h, int(group), a, p[1], p[2], p[3], p[4], p[5], p[6], p[7], self._stream()))
+        rc = self._L.so100_step_host_async(self._h, group, p[0] if actions is None else actions.data_ptr(), p[1], p[2], p[3], p[4],
+                                           p[5], p[6], p[7], self._stream() if stream is None else stream)
+        if rc < 0:
+            _native.check(rc)
 
     def step_host_wait(self, group: int) -> None:
-        _native.check(self._L.so100_step_host_wait(self._h, int(group)))
+        rc = self._L.so100_step_host_wait(self._h, group)
+        if rc < 0:
+            _native.check(rc)
+
+    def step_host_wait_any(self) -> int:
+        """Block until any group with a step in flight has finished; returns its index (-1 if nothing is in flight)."""
+        g = self._any_group
+        rc = self._L.so100_step_host_wait_any(self._h, ctypes.byref(g))
+        if rc < 0:
+            _native.check(rc)
+        return g.value
 
     # ---- state access (parity tests, checkpoints)
     _STATE_FIELDS = {"qpos": (6, torch.float32), "qvel": (6, torch.float32), "qacc_warm": (6, torch.float32), "qpos_comp": (6, torch.float32),

@@ -351,7 +351,8 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
 template <int TASK, bool SPEC>
 __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __grid_constant__ Consts C, const Bufs B, const StepIO io) {
   constexpr int OD = TASK == 5 ? 8 : 15;
-  __shared__ float sh[kBlock * OD];
+  __shared__ __align__(16) float sh[kBlock * OD];
+  static_assert((kBlock * OD) % 4 == 0, "obs rows of a CTA must be a whole number of float4");
   const TaskC& t = C.t;
   const int n = t.n, base = io.env_lo + blockIdx.x * kBlock, hi = io.env_hi;
   const bool live = base + (int)threadIdx.x < hi;
@@ -494,9 +495,17 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
     for (int k = 0; k < OD; k++) sh[threadIdx.x * OD + k] = obs[k];
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < kBlock * OD; k += kBlock) {
-    size_t g = (size_t)base * OD + k;
-    if (g < (size_t)hi * OD) io.obs[g] = sh[k];
+  // the CTA's obs rows are one contiguous, 16-byte aligned span (kBlock * OD floats): 512 bytes per warp instruction
+  // (on the host path these stores cross the link; larger write bursts pack into fuller PCIe packets)
+  if (base + kBlock <= hi) {
+    float4* dst = reinterpret_cast<float4*>(io.obs + (size_t)base * OD);
+    const float4* src = reinterpret_cast<const float4*>(sh);
+    for (int k = threadIdx.x; k < kBlock * OD / 4; k += kBlock) dst[k] = src[k];
+  } else {
+    for (int k = threadIdx.x; k < kBlock * OD; k += kBlock) {
+      size_t g = (size_t)base * OD + k;
+      if (g < (size_t)hi * OD) io.obs[g] = sh[k];
+    }
   }
 }
 
@@ -830,7 +839,6 @@ struct so100_ctx {
   static constexpr int kMaxChunks = 16;
   int n_chunks = 2;
   bool zero_copy = true;
-  int host_min_ctas = 0;  // experiment knob SO100_HOST_CTAS_PER_SM=1: one CTA per SM (two waves at 65 536 envs)
   cudaStream_t hs[kMaxChunks] = {};
   cudaEvent_t ev_start = nullptr, ev_done[kMaxChunks] = {};
   int *d_any_done = nullptr, *p_any_done = nullptr;  // device flag + pinned host copy (the zero-copy path writes the latter)
@@ -840,6 +848,12 @@ struct so100_ctx {
   int n_groups = 1, g_lo[kMaxGroups] = {}, g_hi[kMaxGroups] = {};
   int64_t g_tick[kMaxGroups] = {};
   bool g_pending[kMaxGroups] = {};
+  int g_next = 0;  // where so100_step_host_wait_any resumes its scan
+  // async path: a group's action rows come in by copy engine (measured 5 % faster than loads over the link from the SMs, whose
+  // read requests queue behind the other groups' posted obs writes: profiles/r2_e2e_groups.txt); obs go out as stores from
+  // the kernel.  A/B knobs SO100_ASYNC_H2D_COPY / SO100_ASYNC_D2H_COPY.
+  bool async_h2d_copy = true, async_d2h_copy = false;
+  bool g_fork_needed[kMaxGroups] = {};  // work enqueued on a caller stream since this group's last async step (reset, set_state, ...)
   cudaStream_t gs[kMaxGroups] = {};
   cudaEvent_t g_done[kMaxGroups] = {}, g_fork = nullptr;
 };
@@ -863,6 +877,10 @@ static void free_ctx(so100_ctx* c) {
   }
   if (c->g_fork) cudaEventDestroy(c->g_fork);
   delete c;
+}
+
+static void mark_caller_stream_work(so100_ctx* c) {
+  for (int g = 0; g < so100_ctx::kMaxGroups; g++) c->g_fork_needed[g] = true;
 }
 
 extern "C" {
@@ -980,17 +998,14 @@ int so100_reset(so100_ctx* c, const uint8_t* mask_dev, float* obs_dev, void* str
     default: reset_kernel<5><<<grid_for(c->n), kBlock, 0, st>>>(c->C, c->B, mask_dev, obs_dev, tick); break;
   }
   c->launches++;
+  mark_caller_stream_work(c);
   CU(cudaGetLastError());
   return SO100_OK;
 }
 
-static int launch_step(so100_ctx* c, const StepIO& io, cudaStream_t st, size_t dyn_smem = 0) {
+static int launch_step(so100_ctx* c, const StepIO& io, cudaStream_t st) {
   const int g = grid_for(io.env_hi - io.env_lo);
-#define SO100_LAUNCH(T, S)                                                                                          \
-  do {                                                                                                              \
-    if (dyn_smem) cudaFuncSetAttribute(step_kernel<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem); \
-    step_kernel<T, S><<<g, kBlock, dyn_smem, st>>>(c->C, c->B, io);                                                  \
-  } while (0)
+#define SO100_LAUNCH(T, S) step_kernel<T, S><<<g, kBlock, 0, st>>>(c->C, c->B, io)
   if (c->specialised) {
     switch (c->task) {
       case 1: SO100_LAUNCH(1, true); break;
@@ -1033,6 +1048,7 @@ int so100_step(so100_ctx* c, const float* actions_dev, float* obs_dev, float* re
   if (int rc = groups_in_step(c)) return rc;
   set_all_ticks(c, c->tick + 1);
   StepIO io{actions_dev, obs_dev, reward_dev, terminal_obs_dev, ep_return_dev, terminated_dev, truncated_dev, ep_len_dev, (unsigned)c->tick, 0, c->n, nullptr};
+  mark_caller_stream_work(c);
   return launch_step(c, io, st);
 }
 
@@ -1058,6 +1074,7 @@ int so100_step_substeps(so100_ctx* c, const float* ctrl_dev, int n_substeps, voi
     }
   }
 #undef SO100_SUBSTEPS
+  mark_caller_stream_work(c);
   c->launches++;
   CU(cudaGetLastError());
   return SO100_OK;
@@ -1086,12 +1103,13 @@ static int ensure_staging(so100_ctx* c) {
     CU(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
   }
   CU(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
-  if (const char* e = getenv("SO100_HOST_CTAS_PER_SM")) c->host_min_ctas = atoi(e);  // experiment: 1 = two waves at 65 536 envs
   for (int k = 0; k < so100_ctx::kMaxGroups; k++) {
     CU(cudaStreamCreateWithFlags(&c->gs[k], cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&c->g_done[k], cudaEventDisableTiming));
   }
   CU(cudaEventCreateWithFlags(&c->g_fork, cudaEventDisableTiming));
+  if (const char* e = getenv("SO100_ASYNC_H2D_COPY")) c->async_h2d_copy = atoi(e) != 0;
+  if (const char* e = getenv("SO100_ASYNC_D2H_COPY")) c->async_d2h_copy = atoi(e) != 0;
   return SO100_OK;
 }
 
@@ -1143,6 +1161,7 @@ static int enqueue_host_pipeline(so100_ctx* c, cudaStream_t st, const float* act
 static void* mapped_alias(const void* host) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type == cudaMemoryTypeDevice && getenv("SO100_HOST_ALLOW_DEVICE")) return a.devicePointer;  // pipeline experiments without the link
   if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
   return a.devicePointer;
 }
@@ -1166,8 +1185,6 @@ static HostAlias alias_host(const float* actions_host, float* obs_host, float* r
   if (a.ok && ep_len_host) a.ok = (a.epl = (int*)mapped_alias(ep_len_host)) != nullptr;
   return a;
 }
-// one CTA per SM for the host path's launch (experiment): a CTA's static shared memory + this much fills an SM
-static size_t host_dyn_smem(const so100_ctx* c) { return c->host_min_ctas == 1 ? 120 * 1024 : 0; }
 
 int so100_step_host(so100_ctx* c, const float* actions_host, float* obs_host, float* reward_host, uint8_t* terminated_host,
                     uint8_t* truncated_host, float* terminal_obs_host, float* ep_return_host, int32_t* ep_len_host, void* stream) {
@@ -1188,7 +1205,7 @@ int so100_step_host(so100_ctx* c, const float* actions_host, float* obs_host, fl
     // wave of CTAs, so the three phases are in series: actions in, ~85 us of arithmetic, results out; the pipelined
     // alternative is so100_step_host_async over env groups.
     StepIO io{z.act, z.obs, z.rew, z.tobs, z.epr, z.term, z.trunc, z.epl, (unsigned)c->tick, 0, c->n, nullptr};
-    rc = launch_step(c, io, st, host_dyn_smem(c));
+    rc = launch_step(c, io, st);
     if (rc) return rc;
     CU(cudaStreamSynchronize(st));
     return SO100_OK;
@@ -1238,15 +1255,26 @@ int so100_step_host_async(so100_ctx* c, int group, const float* actions_host, fl
   HostAlias z = alias_host(actions_host, obs_host, reward_host, terminated_host, truncated_host, terminal_obs_host, ep_return_host, ep_len_host);
   if (!z.ok) return fail(SO100_ERR_ARG, "so100_step_host_async needs page-locked (pinned / registered) host buffers");
   cudaStream_t gs = c->gs[group];
-  if (stream != (void*)gs) {  // order after whatever the caller has enqueued on its own stream (a reset, a set_state)
+  if (c->g_fork_needed[group]) {  // order after what the library has enqueued on the caller's stream (a reset, a set_state)
     CU(cudaEventRecord(c->g_fork, (cudaStream_t)stream));
     CU(cudaStreamWaitEvent(gs, c->g_fork, 0));
+    c->g_fork_needed[group] = false;
   }
   c->g_tick[group] += 1;
   if (c->g_tick[group] > c->tick) c->tick = c->g_tick[group];
-  StepIO io{z.act, z.obs, z.rew, z.tobs, z.epr, z.term, z.trunc, z.epl, (unsigned)c->g_tick[group], c->g_lo[group], c->g_hi[group], nullptr};
+  const int lo = c->g_lo[group], hi = c->g_hi[group];
+  const size_t cnt = (size_t)(hi - lo), od = (size_t)c->obs_dim;
+  const float* act = z.act;
+  float* obs = z.obs;
+  if (c->async_h2d_copy) {  // the group's action rows by copy engine instead of loads over the link from the SMs
+    CU(cudaMemcpyAsync(c->h_act + (size_t)lo * SO_NJ, actions_host + (size_t)lo * SO_NJ, cnt * SO_NJ * 4, cudaMemcpyHostToDevice, gs));
+    act = c->h_act;
+  }
+  if (c->async_d2h_copy) obs = c->h_obs;
+  StepIO io{act, obs, z.rew, z.tobs, z.epr, z.term, z.trunc, z.epl, (unsigned)c->g_tick[group], lo, hi, nullptr};
   rc = launch_step(c, io, gs);
   if (rc) return rc;
+  if (c->async_d2h_copy) CU(cudaMemcpyAsync(obs_host + (size_t)lo * od, c->h_obs + (size_t)lo * od, cnt * od * 4, cudaMemcpyDeviceToHost, gs));
   CU(cudaEventRecord(c->g_done[group], gs));
   c->g_pending[group] = true;
   return SO100_OK;
@@ -1258,6 +1286,26 @@ int so100_step_host_wait(so100_ctx* c, int group) {
   CU(cudaEventSynchronize(c->g_done[group]));
   c->g_pending[group] = false;
   return SO100_OK;
+}
+
+int so100_step_host_wait_any(so100_ctx* c, int* group_out) {
+  if (!c || !group_out) return fail(SO100_ERR_ARG, "null argument");
+  int pending = 0;
+  for (int g = 0; g < c->n_groups; g++) pending += c->g_pending[g] ? 1 : 0;
+  *group_out = -1;
+  if (!pending) return SO100_OK;
+  CU(cudaSetDevice(c->device));
+  for (int g = c->g_next;; g = (g + 1) % c->n_groups) {  // round-robin from the group after the last one returned
+    if (!c->g_pending[g]) continue;
+    cudaError_t e = cudaEventQuery(c->g_done[g]);
+    if (e == cudaSuccess) {
+      c->g_pending[g] = false;
+      c->g_next = (g + 1) % c->n_groups;
+      *group_out = g;
+      return SO100_OK;
+    }
+    if (e != cudaErrorNotReady) return fail(SO100_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(e));
+  }
 }
 
 static int copy_state(so100_ctx* c, const so100_state_view* v, void* stream, bool get) {
@@ -1274,6 +1322,7 @@ static int copy_state(so100_ctx* c, const so100_state_view* v, void* stream, boo
     if (get) CU(cudaMemcpyAsync(x.ext, x.in, x.bytes, cudaMemcpyDeviceToDevice, st));
     else CU(cudaMemcpyAsync(x.in, x.ext, x.bytes, cudaMemcpyDeviceToDevice, st));
   }
+  mark_caller_stream_work(c);  // (a get must also be ordered before a later group step overwrites the state)
   return SO100_OK;
 }
 int so100_get_state(so100_ctx* c, const so100_state_view* v, void* stream) { return copy_state(c, v, stream, true); }

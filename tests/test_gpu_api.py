@@ -224,8 +224,12 @@ def test_async_env_groups_equal_the_full_batch_step(task, n, groups):
         order = list(range(groups)) if t % 2 == 0 else list(reversed(range(groups)))
         for g in order:
             e2.step_host_async(h2, g)
-        for g in range(groups):
-            e2.step_host_wait(g)
+        if t % 3 == 0:   # served in completion order
+            got = sorted(e2.step_host_wait_any() for _ in range(groups))
+            assert got == list(range(groups)) and e2.step_host_wait_any() == -1
+        else:
+            for g in range(groups):
+                e2.step_host_wait(g)
         for k in ("obs", "reward", "terminated", "truncated"):
             assert torch.equal(h1[k], h2[k]), (k, t)
         done = (h1["terminated"] | h1["truncated"]).bool()
