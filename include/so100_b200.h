@@ -38,10 +38,11 @@
 extern "C" {
 #endif
 
-#define SO100_ABI_VERSION 2
+#define SO100_ABI_VERSION 3
 #define SO100_NJ 6            /* arm hinges incl. the jaw */
 #define SO100_MAX_START 64    /* rows available for Env01 start poses (reference: 36) */
 #define SO100_MAX_GROUPS 16   /* env groups of the asynchronous host path */
+#define SO100_MAX_PAD 8       /* primitive box colliders on the arm (reference: 4 + 4 jaw pads) */
 
 /* error codes */
 #define SO100_OK 0
@@ -61,6 +62,7 @@ extern "C" {
 #define SO100_FLAG_CLIP_ACTIONS 2u      /* clip actions to [-1,1] on device (the reference env does not) */
 #define SO100_FLAG_GENERIC_KERNEL 4u    /* never use the model-specialised kernel (tests: generic vs specialised) */
 #define SO100_FLAG_STATIC_BLOCK 8u      /* hold the Env01/02/06 block at its spawn pose: no gravity, no floor contact (round-1 behaviour) */
+#define SO100_FLAG_NO_ARM_CONTACT 16u   /* no jaw-pad <-> floor contact: the arm passes through the floor (round-1 behaviour) */
 
 /*
  * Model constants as they stand in the MJCF (so_arm100_camera.xml + env01.xml), nothing derived.
@@ -111,6 +113,22 @@ typedef struct so100_model {
   double contact_solimp[5];  /* 0.9 0.95 0.001 0.5 2 */
   int32_t block_ncon;        /* contact points of MuJoCo's plane-box collider for a flat box: 4; 0 = the pair does not collide */
   int32_t _pad1;
+  /* arm <-> floor contact: the PRIMITIVE box colliders the reference MJCF puts on the jaws (so_arm100_camera.xml:60-61
+     class finger_collision; :108-111 fixed_jaw_pad_1..4; :120-123 moving_jaw_pad_1..4) against the floor plane
+     (env01.xml:39; env01.xml:42-49 excludes only block <-> arm pairs).  Boxes are axis-aligned in their body frame.
+     Geom parameters as they stand in the MJCF; the library mixes the pair like mj_contactParam (mean solref / solimp,
+     max friction) and clamps solimp like getsolparam.  The arm's mesh colliders are not available. */
+  int32_t n_pad;             /* 8; 0 = the arm has no primitive colliders */
+  int32_t _pad2;
+  int32_t pad_body[SO100_MAX_PAD];   /* 4 = Fixed_Jaw, 5 = Moving_Jaw */
+  double pad_pos[SO100_MAX_PAD][3];  /* box centre in the body frame */
+  double pad_size[SO100_MAX_PAD][3]; /* half sizes */
+  double pad_solref[2];      /* 0.01 1 */
+  double pad_solimp[5];      /* 2 1 0.01 0.5 2 (clamped to 0.9999 0.9999 ... at use) */
+  double pad_friction;       /* 1 */
+  double floor_solref[2];    /* 0.02 1 */
+  double floor_solimp[5];    /* 0.9 0.95 0.001 0.5 2 */
+  double floor_friction;     /* 1 */
 } so100_model;
 
 /* Task constants: the literals of envs/utils.py, env03_v1.py, env05_v1.py, env_base_02.py, __init__.py. */
@@ -264,7 +282,9 @@ int so100_forward_dynamics(so100_ctx *ctx, int n, const float *qpos_dev, const f
  * and is how so100_create derives dof_M0 / kv / invweight0.  Row-major host arrays: qpos/qvel/ctrl [n][6],
  * M [n][21] (packed lower triangle), bias [n][6], qacc [n][6] (cold start, `sweeps` Gauss-Seidel sweeps),
  * kin [n][18] (end_pos 3, wrist 3, cam_xpos 3, cam_xmat 9).  Outputs may be NULL.  variant 0 = generic recursion,
- * 1 = the generated model-specialised code (error if `model` is not the one it was generated from).
+ * 1 = the generated model-specialised code (error if `model` is not the one it was generated from), 2 = the generic
+ * recursion instantiated in fp32 (what the kernels compute, incl. the arm-floor contact solve; kin is not written).
+ * Samples whose jaw pads touch the floor are solved by the contact path (Newton), the others by `sweeps` Gauss-Seidel sweeps.
  */
 int so100_host_forward(const so100_model *model, int n, const double *qpos, const double *qvel, const double *ctrl,
                        double *M, double *bias, double *qacc, double *kin, int sweeps, int variant);

@@ -102,6 +102,8 @@ def lib():
         L.orc_fk.argtypes = [ctypes.c_void_p, dp, ctypes.POINTER(OrcKin)]
         L.orc_mass_matrix.argtypes = [ctypes.c_void_p, dp, dp]
         L.orc_bias.argtypes = [ctypes.c_void_p, dp, dp, dp]
+        L.orc_contacts.argtypes = [ctypes.c_void_p, dp, dp, dp, i32p]
+        L.orc_body_invweight0.argtypes = [ctypes.c_void_p, dp]
         L.orc_forward.argtypes = [ctypes.c_void_p, dp, dp, dp, dp, dp, dp, dp, i32p]
         L.orc_substeps.argtypes = [ctypes.c_void_p, dp, dp, dp, dp, ctypes.c_int]
         L.orc_energy.argtypes = [ctypes.c_void_p, dp, dp, dp, dp]
@@ -192,6 +194,18 @@ class Oracle:
         self._L.orc_forward(self._h, _d(q), _d(v), _d(c), None if w is None else _d(w), _d(qacc), _d(qs), _d(qc),
                             ctypes.byref(it))
         return qacc, qs, qc, int(it.value)
+
+    def contacts(self, qpos):
+        """Pad <-> floor contacts of one configuration: (pos [n, 3], dist [n], body [n])."""
+        q = np.ascontiguousarray(qpos, dtype=np.float64)
+        pos, dist, body = np.zeros((32, 3)), np.zeros(32), np.zeros(32, dtype=np.int32)
+        n = self._L.orc_contacts(self._h, _d(q), _d(pos), _d(dist), body.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+        return pos[:n], dist[:n], body[:n]
+
+    def body_invweight0(self) -> np.ndarray:
+        t = np.zeros(NJ)
+        self._L.orc_body_invweight0(self._h, _d(t))
+        return t
 
     def substeps(self, qpos, qvel, warm, ctrl, n):
         q = np.array(qpos, dtype=np.float64)

@@ -40,6 +40,8 @@ struct orc_sim {
   double body_I[NJ][9]; /* inertia about COM, body frame */
   double dof_M0[NJ], kv[NJ], invw[NJ];
   double fy;            /* focal length in pixels, env_base_02.py:100 */
+  /* pad <-> floor contact pair: mixed geom parameters (mj_contactParam) and body_invweight0 (translational) */
+  double pc_solref[2], pc_solimp[5], pc_mu, body_tran[NJ];
 };
 
 /* ------------------------------------------------------------------ small math */
@@ -264,7 +266,10 @@ void orc_energy(const orc_sim *s, const double *qpos, const double *qvel, double
 }
 
 /* ------------------------------------------------------------------ constraints + solver */
-typedef struct { int dof; double sign, aref, D, R, floss; int friction; } crow;
+#define MAX_CON (4 * ORC_MAX_PAD)
+#define MAX_ROWS (3 * NJ + 4 * MAX_CON)
+typedef struct { double J[NJ]; double aref, D, R, floss; int friction; } crow;
+typedef struct { double pos[3], dist; int body; } ccontact;
 
 static double impedance(const double *solimp, double pos) { /* MuJoCo getimpedance, margin 0 */
   if (solimp[0] == solimp[1] || solimp[2] <= MJMINVAL) return 0.5 * (solimp[0] + solimp[1]);
@@ -285,7 +290,52 @@ static void kb_from_solref(const double *solref, const double *solimp, double h,
     *B = 2.0 / fmax(MJMINVAL, dmax * tc);
   } else { *K = -solref[0] / (dmax * dmax); *B = -solref[1] / dmax; }
 }
-static int make_rows(const orc_sim *s, const double *qpos, const double *qvel, crow *rows) {
+
+/* Arm <-> floor contacts.  The reference MJCF gives the jaws eight PRIMITIVE box colliders
+ * (so_arm100_camera.xml:60-61 class finger_collision, :108-111 fixed-jaw pads, :120-123 moving-jaw pads); the floor is
+ * the plane geom of env01.xml:39, and only block <-> arm pairs are excluded (env01.xml:42-49), so pad <-> floor is live.
+ * MuJoCo 3.3.1 semantics restated [3P, from knowledge of mjc_PlaneBox / mj_collideGeoms; no source in the container]:
+ * for each of the box's 8 corners (bit 0/1/2 of the index = +x/+y/+z half-size) with ldist = n . (R corner) <= 0 and
+ * dist = n . (centre - plane) + ldist <= margin (= 0), at most 4 per box in index order, a contact with that dist,
+ * frame normal = plane normal and pos = corner - n dist / 2; it enters the constraints iff dist < margin - gap (= 0).
+ * (The arm's MESH colliders are not in the checkout: DESIGN.md D2.) */
+static int collide_pads(const orc_sim *s, const orc_kin *k, ccontact *con) {
+  const orc_model *m = &s->m;
+  int n = 0;
+  if (s->cfg.flags & 16u) return 0; /* SO100_FLAG_NO_ARM_CONTACT */
+  for (int p = 0; p < m->n_pad && p < ORC_MAX_PAD; p++) {
+    int b = m->pad_body[p], cnt = 0;
+    double c[3], t[3];
+    mv(k->xmat[b], m->pad_pos[p], t);
+    for (int a = 0; a < 3; a++) c[a] = k->xpos[b][a] + t[a];
+    double dist = c[2]; /* plane z = 0, normal +z */
+    for (int i = 0; i < 8 && cnt < 4; i++) {
+      double vec[3] = {(i & 1) ? m->pad_size[p][0] : -m->pad_size[p][0], (i & 2) ? m->pad_size[p][1] : -m->pad_size[p][1],
+                       (i & 4) ? m->pad_size[p][2] : -m->pad_size[p][2]}, corner[3];
+      mv(k->xmat[b], vec, corner);
+      double ldist = corner[2];
+      if (dist + ldist > 0 || ldist > 0) continue;
+      cnt++;
+      if (!(dist + ldist < 0)) continue; /* in the gap: detected, not instantiated */
+      ccontact *q = &con[n++];
+      q->dist = dist + ldist; q->body = b;
+      for (int a = 0; a < 3; a++) q->pos[a] = c[a] + corner[a];
+      q->pos[2] -= q->dist / 2;
+    }
+  }
+  return n;
+}
+int orc_contacts(const orc_sim *s, const double *qpos, double *pos, double *dist, int *body) {
+  orc_kin k;
+  ccontact con[MAX_CON];
+  orc_fk(s, qpos, &k);
+  int n = collide_pads(s, &k, con);
+  for (int i = 0; i < n; i++) { memcpy(pos + 3 * i, con[i].pos, sizeof con[i].pos); dist[i] = con[i].dist; body[i] = con[i].body; }
+  return n;
+}
+void orc_body_invweight0(const orc_sim *s, double *tran) { memcpy(tran, s->body_tran, sizeof s->body_tran); }
+
+static int make_rows(const orc_sim *s, const orc_kin *k, const double *qpos, const double *qvel, crow *rows) {
   const orc_model *m = &s->m;
   int n = 0;
   for (int j = 0; j < NJ; j++) { /* friction-loss rows first (MuJoCo order: equality, friction, limit, contact) */
@@ -293,7 +343,8 @@ static int make_rows(const orc_sim *s, const double *qpos, const double *qvel, c
     double K, B, imp = impedance(m->dof_solimp_friction[j], 0.0);
     kb_from_solref(m->dof_solref_friction[j], m->dof_solimp_friction[j], m->timestep, &K, &B);
     crow *r = &rows[n++];
-    r->dof = j; r->sign = 1; r->friction = 1; r->floss = m->jnt_frictionloss[j];
+    memset(r->J, 0, sizeof r->J);
+    r->J[j] = 1; r->friction = 1; r->floss = m->jnt_frictionloss[j];
     r->R = fmax(MJMINVAL, (1 - imp) / imp * s->invw[j]); r->D = 1 / r->R;
     r->aref = -B * qvel[j]; /* K = 0 for friction rows */
   }
@@ -304,10 +355,43 @@ static int make_rows(const orc_sim *s, const double *qpos, const double *qvel, c
       double K, B, imp = impedance(m->jnt_solimp_limit[j], dist);
       kb_from_solref(m->jnt_solref_limit[j], m->jnt_solimp_limit[j], m->timestep, &K, &B);
       crow *r = &rows[n++];
-      r->dof = j; r->sign = side == 0 ? 1 : -1; r->friction = 0; r->floss = 0;
+      memset(r->J, 0, sizeof r->J);
+      r->J[j] = side == 0 ? 1 : -1; r->friction = 0; r->floss = 0;
       r->R = fmax(MJMINVAL, (1 - imp) / imp * s->invw[j]); r->D = 1 / r->R;
-      r->aref = -B * (r->sign * qvel[j]) - K * imp * dist;
+      r->aref = -B * (r->J[j] * qvel[j]) - K * imp * dist;
     }
+  }
+  /* contact rows: condim 3, pyramidal cone (the scene's <option>; the attached model's elliptic setting does not
+   * survive <attach>): J = J_n +- mu J_t1, J_n +- mu J_t2; every row pos = dist, aref = -B (J qvel) - K imp dist;
+   * diagApprox = (1 + mu^2) body_invweight0_trans(body), R = 2 mu_reg^2 max(MINVAL, (1-imp)/imp diagApprox),
+   * mu_reg = mu / sqrt(impratio) = mu [3P: mj_instantiateContact, mj_diagApprox, mj_makeImpedance]. */
+  ccontact con[MAX_CON];
+  int nc = collide_pads(s, k, con);
+  for (int c = 0; c < nc; c++) {
+    double J3[3][NJ] = {{0}};
+    for (int j = 0; j <= con[c].body; j++) {
+      double r[3], col[3];
+      for (int a = 0; a < 3; a++) r[a] = con[c].pos[a] - k->xpos[j][a];
+      cross(k->xaxis[j], r, col);
+      for (int a = 0; a < 3; a++) J3[a][j] = col[a];
+    }
+    double K, B, mu = s->pc_mu, imp = impedance(s->pc_solimp, con[c].dist);
+    kb_from_solref(s->pc_solref, s->pc_solimp, m->timestep, &K, &B);
+    double R0 = fmax(MJMINVAL, (1 - imp) / imp * (1 + mu * mu) * s->body_tran[con[c].body]);
+    double R = fmax(MJMINVAL, 2 * mu * mu * R0);
+    /* tangent frame of mju_makeFrame for normal (0,0,1): t1 = +y, t2 = -x */
+    for (int t = 0; t < 2; t++)
+      for (int sg = 0; sg < 2; sg++) {
+        crow *r = &rows[n++];
+        double vel = 0;
+        for (int j = 0; j < NJ; j++) {
+          double jt = t == 0 ? J3[1][j] : -J3[0][j];
+          r->J[j] = J3[2][j] + (sg == 0 ? mu : -mu) * jt;
+          vel += r->J[j] * qvel[j];
+        }
+        r->friction = 0; r->floss = 0; r->R = R; r->D = 1 / R;
+        r->aref = -B * vel - K * imp * con[c].dist;
+      }
   }
   return n;
 }
@@ -321,13 +405,18 @@ static void row_eval(const crow *r, double res, double *cost, double *force, dou
   } else if (res < 0) { *cost = 0.5 * r->D * res * res; *force = -r->D * res; *curv = r->D; }
   else { *cost = 0; *force = 0; *curv = 0; }
 }
+static double jdot(const double *J, const double *a) {
+  double v = 0;
+  for (int j = 0; j < NJ; j++) v += J[j] * a[j];
+  return v;
+}
 static double total_cost(const double *M, const double *as, const crow *rows, int nr, const double *a) {
   double c = 0, d[NJ];
   for (int i = 0; i < NJ; i++) d[i] = a[i] - as[i];
   for (int i = 0; i < NJ; i++) for (int j = 0; j < NJ; j++) c += 0.5 * d[i] * M[i * NJ + j] * d[j];
   for (int k = 0; k < nr; k++) {
     double rc, f, cv;
-    row_eval(&rows[k], rows[k].sign * a[rows[k].dof] - rows[k].aref, &rc, &f, &cv);
+    row_eval(&rows[k], jdot(rows[k].J, a) - rows[k].aref, &rc, &f, &cv);
     c += rc;
   }
   return c;
@@ -336,18 +425,22 @@ static int cmp_d(const void *a, const void *b) { double x = *(const double *)a, 
 
 static int newton_solve(const double *M, const double *as, const crow *rows, int nr, double *a) {
   int it;
-  for (it = 0; it < 100; it++) {
+  for (it = 0; it < 200; it++) {
     double g[NJ], H[NJ * NJ], p[NJ], d[NJ];
     for (int i = 0; i < NJ; i++) d[i] = a[i] - as[i];
     for (int i = 0; i < NJ; i++) { g[i] = 0; for (int j = 0; j < NJ; j++) g[i] += M[i * NJ + j] * d[j]; }
     memcpy(H, M, sizeof H);
+    double fscale = 1;
     for (int k = 0; k < nr; k++) {
       double rc, f, cv;
-      row_eval(&rows[k], rows[k].sign * a[rows[k].dof] - rows[k].aref, &rc, &f, &cv);
-      g[rows[k].dof] -= rows[k].sign * f;
-      H[rows[k].dof * NJ + rows[k].dof] += cv;
+      row_eval(&rows[k], jdot(rows[k].J, a) - rows[k].aref, &rc, &f, &cv);
+      for (int i = 0; i < NJ; i++) {
+        g[i] -= rows[k].J[i] * f;
+        if (cv != 0) for (int j = 0; j < NJ; j++) H[i * NJ + j] += cv * rows[k].J[i] * rows[k].J[j];
+      }
+      fscale += fabs(f);
     }
-    double gn = 0, scale = 1;
+    double gn = 0, scale = fscale;
     for (int i = 0; i < NJ; i++) {
       double f = 0;
       for (int j = 0; j < NJ; j++) f += M[i * NJ + j] * as[j];
@@ -358,16 +451,17 @@ static int newton_solve(const double *M, const double *as, const crow *rows, int
     for (int i = 0; i < NJ; i++) g[i] = -g[i];
     chol6_solve(H, g, p);
     /* exact line search: phi'(alpha) is piecewise linear and increasing; walk its breakpoints */
-    double bp[3 * 2 * NJ + 2];
+    double bp[2 * MAX_ROWS + 2], r0[MAX_ROWS], sl[MAX_ROWS];
     int nb = 0;
     for (int k = 0; k < nr; k++) {
-      double slope = rows[k].sign * p[rows[k].dof], r0 = rows[k].sign * a[rows[k].dof] - rows[k].aref;
+      double slope = jdot(rows[k].J, p);
+      r0[k] = jdot(rows[k].J, a) - rows[k].aref; sl[k] = slope;
       if (slope == 0) continue;
       if (rows[k].friction) {
-        double rf = rows[k].R * rows[k].floss, a1 = (-rf - r0) / slope, a2 = (rf - r0) / slope;
+        double rf = rows[k].R * rows[k].floss, a1 = (-rf - r0[k]) / slope, a2 = (rf - r0[k]) / slope;
         if (a1 > 0) bp[nb++] = a1;
         if (a2 > 0) bp[nb++] = a2;
-      } else { double a1 = -r0 / slope; if (a1 > 0) bp[nb++] = a1; }
+      } else { double a1 = -r0[k] / slope; if (a1 > 0) bp[nb++] = a1; }
     }
     qsort(bp, nb, sizeof(double), cmp_d);
     bp[nb++] = INFINITY;
@@ -376,19 +470,21 @@ static int newton_solve(const double *M, const double *as, const crow *rows, int
     for (int b = 0; b < nb; b++) {
       /* derivative and curvature just inside the segment (lo, bp[b]) */
       double mid = isinf(bp[b]) ? lo + 1.0 : 0.5 * (lo + bp[b]);
-      double dphi = 0, cphi = pMp, x[NJ];
-      for (int i = 0; i < NJ; i++) { x[i] = a[i] + mid * p[i]; dphi += Mp[i] * (x[i] - as[i]); }
+      double dphi = 0, cphi = pMp;
+      for (int i = 0; i < NJ; i++) dphi += Mp[i] * (a[i] + mid * p[i] - as[i]);
       for (int k = 0; k < nr; k++) {
-        double rc, f, cv, sp = rows[k].sign * p[rows[k].dof];
-        row_eval(&rows[k], rows[k].sign * x[rows[k].dof] - rows[k].aref, &rc, &f, &cv);
-        dphi -= f * sp; cphi += cv * sp * sp;
+        double rc, f, cv;
+        row_eval(&rows[k], r0[k] + mid * sl[k], &rc, &f, &cv);
+        dphi -= f * sl[k]; cphi += cv * sl[k] * sl[k];
       }
       double root = mid - dphi / cphi; /* phi' is linear inside the segment */
       if (root <= bp[b]) { alpha = root < lo ? lo : root; break; }
       lo = bp[b]; alpha = lo;
     }
     if (!(alpha > 0)) break;
-    for (int i = 0; i < NJ; i++) a[i] += alpha * p[i];
+    double step = 0, amax = 1;
+    for (int i = 0; i < NJ; i++) { a[i] += alpha * p[i]; step = fmax(step, fabs(alpha * p[i])); amax = fmax(amax, fabs(a[i])); }
+    if (step <= 1e-15 * amax) break; /* no representable progress left (stiff contact rows put a rounding floor under |grad|) */
   }
   return it;
 }
@@ -409,8 +505,8 @@ static void forward_from_kin(const orc_sim *s, const orc_kin *k, const double *q
   memcpy(L, M, sizeof L);
   chol6(L);
   chol6_solve(L, fs, as);
-  crow rows[3 * NJ];
-  int nr = make_rows(s, qpos, qvel, rows);
+  crow rows[MAX_ROWS];
+  int nr = make_rows(s, k, qpos, qvel, rows);
   double a[NJ];
   if (warm && total_cost(M, as, rows, nr, warm) < total_cost(M, as, rows, nr, as)) memcpy(a, warm, sizeof a);
   else memcpy(a, as, sizeof a);
@@ -421,8 +517,8 @@ static void forward_from_kin(const orc_sim *s, const orc_kin *k, const double *q
     memset(qfrc_constraint, 0, sizeof(double) * NJ);
     for (int r = 0; r < nr; r++) {
       double rc, f, cv;
-      row_eval(&rows[r], rows[r].sign * a[rows[r].dof] - rows[r].aref, &rc, &f, &cv);
-      qfrc_constraint[rows[r].dof] += rows[r].sign * f;
+      row_eval(&rows[r], jdot(rows[r].J, a) - rows[r].aref, &rc, &f, &cv);
+      for (int j = 0; j < NJ; j++) qfrc_constraint[j] += rows[r].J[j] * f;
     }
   }
   if (niter_out) *niter_out = it;
@@ -527,6 +623,36 @@ orc_sim *orc_create(const orc_model *m, const orc_task_cfg *cfg) {
     s->dof_M0[j] = M[j * NJ + j];
     s->kv[j] = m->act_dampratio[j] > 0 ? m->act_dampratio[j] * 2 * sqrt(m->act_kp[j] * s->dof_M0[j]) : m->act_kv[j];
   }
+  /* body_invweight0 (mj_setConst): mean diagonal of J M^-1 J^T for the translational Jacobian of the body COM at qpos0 */
+  {
+    orc_kin k;
+    orc_fk(s, q0, &k);
+    for (int b = 0; b < NJ; b++) {
+      double tr = 0;
+      for (int c = 0; c < 3; c++) {
+        double Jr[NJ] = {0}, x[NJ];
+        for (int j = 0; j <= b; j++) {
+          double r[3], col[3];
+          for (int a = 0; a < 3; a++) r[a] = k.xipos[b][a] - k.xpos[j][a];
+          cross(k.xaxis[j], r, col);
+          Jr[j] = col[c];
+        }
+        chol6_solve(L, Jr, x);
+        for (int j = 0; j < NJ; j++) tr += Jr[j] * x[j];
+      }
+      s->body_tran[b] = fmax(MJMINVAL, tr / 3);
+    }
+  }
+  /* pad <-> floor pair (mj_contactParam): equal priority and solmix -> mean solref / solimp, max friction; then the
+     solimp clamps of getsolparam (d0, dmax, midpoint in [mjMINIMP, mjMAXIMP] = [1e-4, 0.9999], width >= 0, power >= 1) */
+  for (int i = 0; i < 2; i++) s->pc_solref[i] = 0.5 * (m->pad_solref[i] + m->floor_solref[i]);
+  for (int i = 0; i < 5; i++) s->pc_solimp[i] = 0.5 * (m->pad_solimp[i] + m->floor_solimp[i]);
+  s->pc_solimp[0] = fmin(0.9999, fmax(0.0001, s->pc_solimp[0]));
+  s->pc_solimp[1] = fmin(0.9999, fmax(0.0001, s->pc_solimp[1]));
+  s->pc_solimp[2] = fmax(0.0, s->pc_solimp[2]);
+  s->pc_solimp[3] = fmin(0.9999, fmax(0.0001, s->pc_solimp[3]));
+  s->pc_solimp[4] = fmax(1.0, s->pc_solimp[4]);
+  s->pc_mu = fmax(m->pad_friction, m->floor_friction);
   return s;
 }
 void orc_destroy(orc_sim *s) { if (s) { free(s->env); free(s); } }

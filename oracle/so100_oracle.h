@@ -26,6 +26,7 @@ extern "C" {
 
 #define ORC_NJ 6
 #define ORC_MAX_START 64
+#define ORC_MAX_PAD 8
 
 typedef struct orc_model {
   int32_t struct_size, nsubstep;
@@ -42,6 +43,12 @@ typedef struct orc_model {
   double ee_offset[3], cam_pos[3], cam_quat[4], cam_fovy_deg;
   double block_half_z, block_mass, block_friction, contact_solref[2], contact_solimp[5];
   int32_t block_ncon, _pad1;
+  /* arm <-> floor contact: primitive box colliders on the jaws against the floor plane */
+  int32_t n_pad, _pad2;
+  int32_t pad_body[ORC_MAX_PAD];
+  double pad_pos[ORC_MAX_PAD][3], pad_size[ORC_MAX_PAD][3];
+  double pad_solref[2], pad_solimp[5], pad_friction;
+  double floor_solref[2], floor_solimp[5], floor_friction;
 } orc_model;
 
 typedef struct orc_task_cfg {
@@ -98,6 +105,10 @@ void orc_set_tick(orc_sim *s, int64_t tick);
 void orc_fk(const orc_sim *s, const double *qpos, orc_kin *out);
 void orc_mass_matrix(const orc_sim *s, const double *qpos, double *M /*36 row-major, incl. armature*/);
 void orc_bias(const orc_sim *s, const double *qpos, const double *qvel, double *bias /*6*/);
+/* pad <-> floor contacts of one configuration (MuJoCo mjc_PlaneBox per pad box): returns the count and fills, per
+   contact, pos[3], dist, body (arrays sized 4 * ORC_MAX_PAD); also the body's translational body_invweight0 */
+int orc_contacts(const orc_sim *s, const double *qpos, double *pos /*[n][3]*/, double *dist, int *body);
+void orc_body_invweight0(const orc_sim *s, double *tran /*[6]*/);
 /* one mj_forward on the arm: returns qacc; optional outputs may be NULL. niter_out = Newton iterations used. */
 void orc_forward(const orc_sim *s, const double *qpos, const double *qvel, const double *ctrl,
                  const double *qacc_warm, double *qacc, double *qacc_smooth, double *qfrc_constraint, int *niter_out);

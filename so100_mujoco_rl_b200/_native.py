@@ -99,7 +99,7 @@ def lib() -> ctypes.CDLL:
         if name not in ("so100_last_error", "so100_destroy", "so100_build_id"):
             getattr(L, name).restype = ci
     L.so100_ppo_workspace_floats.restype = i64
-    if L.so100_abi_version() != 2:
+    if L.so100_abi_version() != 3:
         raise ImportError("libso100_b200.so has an unexpected ABI version; rebuild it")
     _lib = L
     return L

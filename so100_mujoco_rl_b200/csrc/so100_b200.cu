@@ -70,6 +70,7 @@ struct Consts {
   DynC<float> dyn;
   ConC<float> con;
   KinC<float> kin;
+  PadC<float> pad;
   TaskC t;
 };
 
@@ -329,7 +330,22 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
     // ~100x); afterwards qacc moves a few % per substep: 3 sweeps.  The solver adds per-lane sweeps if the last one
     // still moved qacc by > 1e-3.  (Extrapolating the warm start to save a sweep was measured: no faster, 6x less
     // accurate - profiles/r1_variants.md.)
-    float d = solve_qacc<float>(K, M, b, e.q, e.qc, e.v, e.w, sub == 0 ? 5 : 3);
+    // envs with a pad corner below the floor take the Newton path on the full problem (dense contact rows); the rest
+    // keep the per-dof Gauss-Seidel.  e.w enters both as the warm start (the previous substep's qacc).
+    const bool touch = C.pad.n > 0 && pads_touch<float>(C.dyn, C.kin, C.pad, s, c);
+    float d = 0.0f;
+    if (!touch) d = solve_qacc<float>(K, M, b, e.q, e.qc, e.v, e.w, sub == 0 ? 5 : 3);
+    else {
+      ContactIO<float> cio;
+#pragma unroll
+      for (int j = 0; j < SO_NJ; j++) { cio.s[j] = s[j]; cio.c[j] = c[j]; cio.q[j] = e.q[j]; cio.qc[j] = e.qc[j]; cio.qd[j] = e.v[j]; cio.b[j] = b[j]; cio.a[j] = e.w[j]; }
+#pragma unroll
+      for (int k = 0; k < 21; k++) cio.M[k] = M[k];
+      const int st = contact_solve<float>(C.dyn, C.kin, C.pad, C.con, cio);
+#pragma unroll
+      for (int j = 0; j < SO_NJ; j++) e.w[j] = cio.a[j];
+      if (st < 0) d = 1e30f;  // iteration cap / indefinite Hessian: counted with the Gauss-Seidel's unconverged substeps
+    }
     float amax = 1.0f;
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {
@@ -555,7 +571,16 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const __grid_constant__
     b[j] = clampf(f, t.act.frc_lo[j], t.act.frc_hi[j]) - bias[j];
   }
   float zc[SO_NJ] = {0, 0, 0, 0, 0, 0};
-  solve_qacc<float>(C.con, M, b, q, zc, v, a, 12);
+  if (C.pad.n > 0 && pads_touch<float>(C.dyn, C.kin, C.pad, s, c)) {
+    ContactIO<float> cio;
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) { cio.s[j] = s[j]; cio.c[j] = c[j]; cio.q[j] = q[j]; cio.qc[j] = 0.0f; cio.qd[j] = v[j]; cio.b[j] = b[j]; cio.a[j] = 0.0f; }
+#pragma unroll
+    for (int k = 0; k < 21; k++) cio.M[k] = M[k];
+    contact_solve<float>(C.dyn, C.kin, C.pad, C.con, cio);
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) a[j] = cio.a[j];
+  } else solve_qacc<float>(C.con, M, b, q, zc, v, a, 12);
   if (M_out)
 #pragma unroll
     for (int k = 0; k < 21; k++) M_out[k * n + i] = M[k];
@@ -643,11 +668,20 @@ struct HostModel {
   DynC<double> dyn;
   ConC<double> con;
   KinC<double> kin;
-  double dof_M0[SO_NJ], kv[SO_NJ], invw[SO_NJ];
+  PadC<double> pad;
+  double dof_M0[SO_NJ], kv[SO_NJ], invw[SO_NJ], body_tran[SO_NJ];
 };
 
 template <typename A, typename B>
 void cast_arr(const A* a, B* b, int n) { for (int i = 0; i < n; i++) b[i] = (B)a[i]; }
+void cast_pad(const PadC<double>& s, PadC<float>& d) {
+  d.n = s.n;
+  memcpy(d.first, s.first, sizeof d.first);
+  cast_arr(&s.p[0][0], &d.p[0][0], SO_MAX_PAD * 3); cast_arr(&s.A[0][0], &d.A[0][0], SO_MAX_PAD * 9); cast_arr(s.diag, d.diag, SO_MAX_PAD);
+  d.K = (float)s.K; d.B = (float)s.B; d.mu = (float)s.mu;
+  d.imp0 = (float)s.imp0; d.imp1 = (float)s.imp1; d.imp_w = (float)s.imp_w; d.imp_rw = (float)s.imp_rw; d.imp_mid = (float)s.imp_mid;
+  d.imp_rmid = (float)s.imp_rmid; d.imp_r1mid = (float)s.imp_r1mid; d.imp_pow = (float)s.imp_pow;
+}
 
 int build_host_model(const so100_model& m, HostModel& H) {
   double Pprev[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -763,7 +797,105 @@ int build_host_model(const so100_model& m, HostModel& H) {
     H.con.imp_rmid[j] = sl[3] > 0 ? 1.0 / sl[3] : 0.0;
     H.con.imp_r1mid[j] = sl[3] < 1 ? 1.0 / (1.0 - sl[3]) : 0.0;
   }
+  // body_invweight0 (mj_setConst): mean diagonal of Jv M^-1 Jv^T, Jv = translational Jacobian of the link COM at qpos0
+  {
+    double W[9], o[3], zax[SO_NJ][3], org[SO_NJ][3];
+    memcpy(W, H.kin.base_R, sizeof W);
+    memcpy(o, H.kin.base_p, sizeof o);
+    for (int i = 0; i < SO_NJ; i++) {  // q = 0: every joint rotation is the identity
+      const LinkC<double>& L = H.dyn.L[i];
+      double t[3];
+      mvec(W, L.p, t);
+      for (int k = 0; k < 3; k++) o[k] += t[k];
+      mmul(W, L.R, W);
+      for (int k = 0; k < 3; k++) { zax[i][k] = W[3 * k + 2]; org[i][k] = o[k]; }
+      double com_l[3] = {L.h[0] / L.m, L.h[1] / L.m, L.h[2] / L.m}, com[3];
+      mvec(W, com_l, com);
+      for (int k = 0; k < 3; k++) com[k] += o[k];
+      double tr = 0;
+      for (int cidx = 0; cidx < 3; cidx++) {
+        double Jr[SO_NJ] = {0}, y[SO_NJ], x[SO_NJ];
+        for (int j = 0; j <= i; j++) {
+          double d[3] = {com[0] - org[j][0], com[1] - org[j][1], com[2] - org[j][2]};
+          double col[3] = {zax[j][1] * d[2] - zax[j][2] * d[1], zax[j][2] * d[0] - zax[j][0] * d[2], zax[j][0] * d[1] - zax[j][1] * d[0]};
+          Jr[j] = col[cidx];
+        }
+        for (int a = 0; a < SO_NJ; a++) {
+          double sv = Jr[a];
+          for (int k = 0; k < a; k++) sv -= Lc[a * 6 + k] * y[k];
+          y[a] = sv / Lc[a * 6 + a];
+        }
+        for (int a = SO_NJ - 1; a >= 0; a--) {
+          double sv = y[a];
+          for (int k = a + 1; k < SO_NJ; k++) sv -= Lc[k * 6 + a] * x[k];
+          x[a] = sv / Lc[a * 6 + a];
+        }
+        for (int j = 0; j < SO_NJ; j++) tr += Jr[j] * x[j];
+      }
+      H.body_tran[i] = std::fmax(1e-15, tr / 3);
+    }
+  }
+  // arm <-> floor pads in the re-based link frames, sorted by link; pair parameters mixed like mj_contactParam
+  // (equal priority and solmix: mean solref / solimp, max friction) and clamped like getsolparam
+  {
+    PadC<double>& Pd = H.pad;
+    memset(&Pd, 0, sizeof Pd);
+    if (m.n_pad < 0 || m.n_pad > SO_MAX_PAD) return fail(SO100_ERR_MODEL, "n_pad out of range");
+    double solref[2], solimp[5];
+    for (int i = 0; i < 2; i++) solref[i] = 0.5 * (m.pad_solref[i] + m.floor_solref[i]);
+    for (int i = 0; i < 5; i++) solimp[i] = 0.5 * (m.pad_solimp[i] + m.floor_solimp[i]);
+    solimp[0] = std::fmin(0.9999, std::fmax(0.0001, solimp[0]));
+    solimp[1] = std::fmin(0.9999, std::fmax(0.0001, solimp[1]));
+    solimp[2] = std::fmax(0.0, solimp[2]);
+    solimp[3] = std::fmin(0.9999, std::fmax(0.0001, solimp[3]));
+    solimp[4] = std::fmax(1.0, solimp[4]);
+    const double mu = std::fmax(m.pad_friction, m.floor_friction);
+    double tc = solref[0], dr = solref[1], dmax = solimp[1];
+    if (tc > 0) {
+      if (tc < 2 * m.timestep) tc = 2 * m.timestep;  // refsafe
+      Pd.K = 1.0 / std::fmax(1e-15, dmax * dmax * tc * tc * dr * dr);
+      Pd.B = 2.0 / std::fmax(1e-15, dmax * tc);
+    } else { Pd.K = -solref[0] / (dmax * dmax); Pd.B = -solref[1] / dmax; }
+    Pd.mu = mu;
+    Pd.imp0 = solimp[0]; Pd.imp1 = solimp[1]; Pd.imp_w = solimp[2]; Pd.imp_mid = solimp[3]; Pd.imp_pow = solimp[4];
+    Pd.imp_rw = solimp[2] > 1e-15 ? 1.0 / solimp[2] : 0.0;
+    Pd.imp_rmid = 1.0 / solimp[3];
+    Pd.imp_r1mid = 1.0 / (1.0 - solimp[3]);
+    int k = 0;
+    for (int i = 0; i < SO_NJ; i++) {
+      Pd.first[i] = k;
+      for (int q = 0; q < m.n_pad; q++) {
+        if (m.pad_body[q] < 0 || m.pad_body[q] >= SO_NJ) return fail(SO100_ERR_MODEL, "pad_body out of range");
+        if (m.pad_body[q] != i) continue;
+        if (!(m.pad_size[q][0] > 0 && m.pad_size[q][1] > 0 && m.pad_size[q][2] > 0) || !(mu > 0)) return fail(SO100_ERR_MODEL, "pad sizes and friction must be positive");
+        double Pt[9];
+        mtrans(Pall[i], Pt);
+        mvec(Pt, m.pad_pos[q], Pd.p[k]);
+        for (int a = 0; a < 3; a++)
+          for (int r = 0; r < 3; r++) Pd.A[k][3 * r + a] = Pt[3 * r + a] * m.pad_size[q][a];  // P^T e_a size_a
+        Pd.diag[k] = 2 * mu * mu * (1 + mu * mu) * H.body_tran[i];
+        k++;
+      }
+    }
+    Pd.first[SO_NJ] = k;
+    Pd.n = k;
+  }
   return SO100_OK;
+}
+
+// fp64 -> fp32 physics constants as the kernels consume them (link constants, task kinematics, pads)
+void physics_constants_f32(const HostModel& H, Consts& C) {
+  for (int i = 0; i < SO_NJ; i++) {
+    const LinkC<double>& s = H.dyn.L[i];
+    LinkC<float>& d = C.dyn.L[i];
+    cast_arr(s.R, d.R, 9); cast_arr(s.p, d.p, 3); cast_arr(s.h, d.h, 3); cast_arr(s.I, d.I, 6);
+    d.m = (float)s.m; d.arm = (float)s.arm;
+  }
+  cast_arr(H.dyn.a0, C.dyn.a0, 3);
+  cast_arr(H.kin.base_R, C.kin.base_R, 9); cast_arr(H.kin.base_p, C.kin.base_p, 3);
+  cast_arr(H.kin.ee_off, C.kin.ee_off, 3); cast_arr(H.kin.cam_pos, C.kin.cam_pos, 3); cast_arr(H.kin.cam_R, C.kin.cam_R, 9);
+  C.kin.ee_body = H.kin.ee_body; C.kin.wrist_body = H.kin.wrist_body; C.kin.cam_body = H.kin.cam_body;
+  cast_pad(H.pad, C.pad);
 }
 
 // fp32 solver / servo constants exactly as the kernels consume them (also what so100_dyn_gen.cuh bakes in)
@@ -934,16 +1066,8 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
   // fp64 -> fp32 constants
   Consts& C = c->C;
   memset(&C, 0, sizeof C);
-  for (int i = 0; i < SO_NJ; i++) {
-    const LinkC<double>& s = c->H.dyn.L[i];
-    LinkC<float>& d = C.dyn.L[i];
-    cast_arr(s.R, d.R, 9); cast_arr(s.p, d.p, 3); cast_arr(s.h, d.h, 3); cast_arr(s.I, d.I, 6);
-    d.m = (float)s.m; d.arm = (float)s.arm;
-  }
-  cast_arr(c->H.dyn.a0, C.dyn.a0, 3);
-  cast_arr(c->H.kin.base_R, C.kin.base_R, 9); cast_arr(c->H.kin.base_p, C.kin.base_p, 3);
-  cast_arr(c->H.kin.ee_off, C.kin.ee_off, 3); cast_arr(c->H.kin.cam_pos, C.kin.cam_pos, 3); cast_arr(c->H.kin.cam_R, C.kin.cam_R, 9);
-  C.kin.ee_body = c->H.kin.ee_body; C.kin.wrist_body = c->H.kin.wrist_body; C.kin.cam_body = c->H.kin.cam_body;
+  physics_constants_f32(c->H, C);
+  if (cfg->flags & SO100_FLAG_NO_ARM_CONTACT) { C.pad.n = 0; for (int i = 0; i <= SO_NJ; i++) C.pad.first[i] = 0; }
   TaskC& t = C.t;
   t.task = cfg->task; t.n = cfg->num_envs; t.max_steps = cfg->max_episode_steps; t.n_start = cfg->n_start;
   t.lost_limit = cfg->lost_limit; t.nsub = m->nsubstep; t.flags = cfg->flags;
@@ -1392,7 +1516,39 @@ int so100_host_forward(const so100_model* m, int n, const double* qpos, const do
     double flat[SO100_N_DYN_CONSTANTS];
     flatten_dyn(H.dyn, flat);
     if (memcmp(flat, kGenDynConstants, sizeof flat) != 0) return fail(SO100_ERR_MODEL, "model differs from the constants baked into so100_dyn_gen.cuh");
-  } else if (variant != 0) return fail(SO100_ERR_ARG, "variant must be 0 (generic) or 1 (specialised)");
+  } else if (variant != 0 && variant != 2) return fail(SO100_ERR_ARG, "variant must be 0 (generic, fp64), 1 (specialised, fp64) or 2 (generic, fp32)");
+  if (variant == 2) {  // the generic recursion in fp32 on the host: what the kernels compute, without a GPU
+    static Consts Cf;  // (large: keep it off the stack)
+    memset(&Cf, 0, sizeof Cf);
+    physics_constants_f32(H, Cf);
+    ActC<float> A;
+    BlkC<float> Bk;
+    solver_constants_f32(*m, H, Cf.con, A, Bk);
+    for (int i = 0; i < n; i++) {
+      float q[SO_NJ], v[SO_NJ], s[SO_NJ], c[SO_NJ], bias[SO_NJ], M[21], b[SO_NJ], a[SO_NJ] = {0};
+      for (int j = 0; j < SO_NJ; j++) { q[j] = (float)qpos[6 * i + j]; v[j] = (float)qvel[6 * i + j]; s[j] = std::sin(q[j]); c[j] = std::cos(q[j]); }
+      dyn_bias_mass<float>(Cf.dyn, s, c, v, bias, M);
+      for (int j = 0; j < SO_NJ; j++) {
+        float cc = std::fmin(std::fmax((float)ctrl[6 * i + j], A.ctrl_lo[j]), A.ctrl_hi[j]);
+        float f = A.kp[j] * cc - A.kp[j] * q[j] - A.kv[j] * v[j];
+        b[j] = std::fmin(std::fmax(f, A.frc_lo[j]), A.frc_hi[j]) - bias[j];
+      }
+      const float zc[SO_NJ] = {0, 0, 0, 0, 0, 0};
+      int st = 0;
+      if (Cf.pad.n > 0 && pads_touch<float>(Cf.dyn, Cf.kin, Cf.pad, s, c)) {
+        ContactIO<float> cio;
+        for (int j = 0; j < SO_NJ; j++) { cio.s[j] = s[j]; cio.c[j] = c[j]; cio.q[j] = q[j]; cio.qc[j] = 0; cio.qd[j] = v[j]; cio.b[j] = b[j]; cio.a[j] = 0; }
+        memcpy(cio.M, M, sizeof M);
+        st = contact_solve<float>(Cf.dyn, Cf.kin, Cf.pad, Cf.con, cio);
+        memcpy(a, cio.a, sizeof a);
+      } else solve_qacc<float>(Cf.con, M, b, q, zc, v, a, sweeps > 0 ? sweeps : 1);
+      if (getenv("SO100_DEBUG_CONTACT")) fprintf(stderr, "sample %d: contact_solve<float> status %d\n", i, st);
+      if (M_out) for (int k = 0; k < 21; k++) M_out[21 * i + k] = M[k];
+      if (bias_out) for (int j = 0; j < SO_NJ; j++) bias_out[6 * i + j] = bias[j];
+      if (qacc_out) for (int j = 0; j < SO_NJ; j++) qacc_out[6 * i + j] = a[j];
+    }
+    return SO100_OK;
+  }
   for (int i = 0; i < n; i++) {
     const double *q = qpos + 6 * i, *v = qvel + 6 * i, *u = ctrl + 6 * i;
     double s[SO_NJ], c[SO_NJ], bias[SO_NJ], M[21], b[SO_NJ], a[SO_NJ] = {0};
@@ -1405,7 +1561,14 @@ int so100_host_forward(const so100_model* m, int n, const double* qpos, const do
       b[j] = std::fmin(std::fmax(f, m->act_forcerange[j][0]), m->act_forcerange[j][1]) - bias[j];
     }
     const double zc[SO_NJ] = {0, 0, 0, 0, 0, 0};
-    solve_qacc<double>(H.con, M, b, q, zc, v, a, sweeps > 0 ? sweeps : 1);
+    if (H.pad.n > 0 && pads_touch<double>(H.dyn, H.kin, H.pad, s, c)) {
+      ContactIO<double> cio;
+      for (int j = 0; j < SO_NJ; j++) { cio.s[j] = s[j]; cio.c[j] = c[j]; cio.q[j] = q[j]; cio.qc[j] = 0; cio.qd[j] = v[j]; cio.b[j] = b[j]; cio.a[j] = 0; }
+      memcpy(cio.M, M, sizeof M);
+      const int st = contact_solve<double>(H.dyn, H.kin, H.pad, H.con, cio);
+      if (getenv("SO100_DEBUG_CONTACT")) fprintf(stderr, "sample %d: contact_solve status %d\n", i, st);
+      memcpy(a, cio.a, sizeof a);
+    } else solve_qacc<double>(H.con, M, b, q, zc, v, a, sweeps > 0 ? sweeps : 1);
     if (M_out) memcpy(M_out + 21 * i, M, sizeof M);
     if (bias_out) memcpy(bias_out + 6 * i, bias, sizeof bias);
     if (qacc_out) memcpy(qacc_out + 6 * i, a, sizeof a);

@@ -302,6 +302,16 @@ SO_HD float so_rcp(float x) {
 }
 template <typename T>
 SO_HD T so_rcp(T x) { return T(1) / x; }
+SO_HD float so_rsqrt(float x) {
+#ifdef __CUDA_ARCH__
+  return rsqrtf(x);
+#else
+  return 1.0f / std::sqrt(x);
+#endif
+}
+SO_HD double so_rsqrt(double x) { return 1.0 / sqrt(x); }
+template <typename T>
+SO_HD T so_rsqrt(T x) { return T(1) / T(sqrt((double)x)); }
 
 // One mj_step of the block's z coordinate: soft floor contact + gravity, semi-implicit Euler.
 template <typename T>
@@ -470,3 +480,338 @@ SO_HD void task_kinematics(const DynC<T>& C, const KinC<T>& Kc, const T* s, cons
     }
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Arm <-> floor contact: the jaws' primitive box colliders ("pads", so_arm100_camera.xml:60-61, :108-111, :120-123 of
+// the reference) against the floor plane z = 0 (env01.xml:39).  MuJoCo semantics (mjc_PlaneBox, mj_instantiateContact,
+// mj_makeImpedance; DESIGN.md "Arm-floor contact"): every box corner below the plane is a contact with condim 3 and a pyramidal cone, i.e.
+// four unilateral rows  J_n +- mu J_t1, J_n +- mu J_t2  with dense Jacobians, aref = -B (J qd) - K imp(dist) dist and
+// R = (1 - imp)/imp * 2 mu^2 (1 + mu^2) body_invweight0.  The rows couple all joints with stiffness ~3e3 against an
+// inertia of ~0.1, which is what Newton's method is for: the per-dof Gauss-Seidel of solve_qacc stays the path of envs
+// that touch nothing, envs with a penetrating corner take contact_solve() instead.
+#define SO_MAX_PAD 8
+#define SO_MAX_CON (4 * SO_MAX_PAD)
+
+template <typename T>
+struct PadC {
+  int n;                     // pads, sorted by link; 0 = no arm <-> floor contact
+  int first[SO_NJ + 1];      // pads of link i are [first[i], first[i + 1])
+  T p[SO_MAX_PAD][3];        // box centre in the (re-based) link frame
+  T A[SO_MAX_PAD][9];        // half-extent vectors: A[3 r + m] = component r of box axis m times its half size
+  T diag[SO_MAX_PAD];        // 2 mu^2 (1 + mu^2) body_invweight0_trans(link):  R = (1 - imp)/imp * diag
+  T K, B, mu;                // contact reference (mixed solref, refsafe) and sliding friction of the pair
+  T imp0, imp1, imp_w, imp_rw, imp_mid, imp_rmid, imp_r1mid, imp_pow;  // mixed + clamped solimp and reciprocals
+};
+
+// Broad phase, every substep, every env: does ANY pad corner lie below the floor?  Only the z row of each link's world
+// rotation and the z of its origin are propagated (~16 operations per link), then per pad the height of its lowest
+// corner  cz - sum_m |w . A_m|.  Exact: true iff contact_solve would find at least one contact.
+template <typename T>
+SO_HD bool pads_touch(const DynC<T>& C, const KinC<T>& Kc, const PadC<T>& P, const T* s, const T* c) {
+  T w0 = Kc.base_R[6], w1 = Kc.base_R[7], w2 = Kc.base_R[8], oz = Kc.base_p[2];
+  bool touch = false;
+#pragma unroll
+  for (int i = 0; i < SO_NJ; i++) {
+    const LinkC<T>& L = C.L[i];
+    oz += w0 * L.p[0] + w1 * L.p[1] + w2 * L.p[2];
+    const T t0 = w0 * L.R[0] + w1 * L.R[3] + w2 * L.R[6], t1 = w0 * L.R[1] + w1 * L.R[4] + w2 * L.R[7],
+            t2 = w0 * L.R[2] + w1 * L.R[5] + w2 * L.R[8];
+    w0 = c[i] * t0 + s[i] * t1; w1 = c[i] * t1 - s[i] * t0; w2 = t2;
+    for (int k = P.first[i]; k < P.first[i + 1]; k++) {
+      const T cz = oz + w0 * P.p[k][0] + w1 * P.p[k][1] + w2 * P.p[k][2];
+      T ext = T(0);
+#pragma unroll
+      for (int m = 0; m < 3; m++) {
+        const T u = w0 * P.A[k][m] + w1 * P.A[k][3 + m] + w2 * P.A[k][6 + m];
+        ext += u < T(0) ? -u : u;
+      }
+      touch = touch || (cz - ext < T(0));
+    }
+  }
+  return touch;
+}
+
+template <typename T>
+struct ContactIO {  // what the contact path needs from the substep, copied once at the call site (keeps the hot path's arrays in registers)
+  T s[SO_NJ], c[SO_NJ], q[SO_NJ], qc[SO_NJ], qd[SO_NJ], M[21], b[SO_NJ];
+  T a[SO_NJ];       // in: warm start (previous qacc); out: qacc
+};
+
+// In-place Cholesky of a packed lower-triangular 6x6 SPD matrix, then solve H x = r.  Returns false if not positive definite.
+template <typename T>
+SO_HD bool chol_solve6(T* H, const T* r, T* x) {
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) {
+    T d = H[midx(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; k++) d -= H[midx(j, k)] * H[midx(j, k)];
+    if (!(d > T(0))) return false;
+    const T rd = so_rsqrt(d);
+    H[midx(j, j)] = rd;  // the diagonal holds 1 / L_jj
+#pragma unroll
+    for (int i = j + 1; i < SO_NJ; i++) {
+      T v = H[midx(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) v -= H[midx(i, k)] * H[midx(j, k)];
+      H[midx(i, j)] = v * rd;
+    }
+  }
+  T y[SO_NJ];
+#pragma unroll
+  for (int i = 0; i < SO_NJ; i++) {
+    T v = r[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) v -= H[midx(i, k)] * y[k];
+    y[i] = v * H[midx(i, i)];
+  }
+#pragma unroll
+  for (int i = SO_NJ - 1; i >= 0; i--) {
+    T v = y[i];
+#pragma unroll
+    for (int k = i + 1; k < SO_NJ; k++) v -= H[midx(k, i)] * x[k];
+    x[i] = v * H[midx(i, i)];
+  }
+  return true;
+}
+
+// qacc of an env whose pads touch the floor: primal Newton on the full convex problem
+//   min_a  1/2 a'Ma - b'a + sum_j [friction_j(a_j) + limit_j(a_j)] + sum_contacts sum_4 rows  D/2 min(0, J a - aref)^2
+// with the exact generalised Hessian, a Cholesky solve per iteration, and an exact line search: phi'(alpha) along the
+// Newton direction is piecewise linear and increasing, and it is evaluated from stored row residuals and slopes (no
+// Jacobians), so a safeguarded Newton iteration on it costs a few operations per row.  If no row switched state along
+// the step, the step ended on the minimiser of the quadratic piece it started in and the solve is finished; with the
+// warm start of the previous substep that is the common case: one evaluation, one Cholesky solve.
+// Returns the number of gradient/Hessian evaluations, negated if the iteration cap was hit or the Hessian was not
+// positive definite.
+template <typename T>
+SO_NOINLINE int contact_solve(const DynC<T>& C, const KinC<T>& Kc, const PadC<T>& P, const ConC<T>& K, ContactIO<T>& io) {
+  const T* s = io.s;
+  const T* c = io.c;
+  // ---- world kinematics: joint axes (local +z of each link), link origins; contacts of the pads on the way
+  T zax[SO_NJ][3], org[SO_NJ][3];
+  T cpos[SO_MAX_CON][3], cc0[SO_MAX_CON], cbx[SO_MAX_CON], cby[SO_MAX_CON], cD[SO_MAX_CON];
+  int cnj[SO_MAX_CON], nc = 0;
+  {
+    T W[9], o[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) W[k] = Kc.base_R[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) o[k] = Kc.base_p[k];
+#pragma unroll
+    for (int i = 0; i < SO_NJ; i++) {
+      const LinkC<T>& L = C.L[i];
+      T t[3];
+      mat_vec(W, L.p, t);
+      o[0] += t[0]; o[1] += t[1]; o[2] += t[2];
+      mat_mul(W, L.R, W);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {  // W <- W * Rz(q_i)
+        const T x = W[3 * r], y = W[3 * r + 1];
+        W[3 * r] = c[i] * x + s[i] * y;
+        W[3 * r + 1] = c[i] * y - s[i] * x;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) { zax[i][k] = W[3 * k + 2]; org[i][k] = o[k]; }
+      for (int k = P.first[i]; k < P.first[i + 1]; k++) {
+        T cw[3], h[3][3];  // box centre and half-extent vectors in the world
+        mat_vec(W, P.p[k], cw);
+        cw[0] += o[0]; cw[1] += o[1]; cw[2] += o[2];
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+          const T v[3] = {P.A[k][m], P.A[k][3 + m], P.A[k][6 + m]};
+          mat_vec(W, v, h[m]);
+        }
+        int found = 0;
+        for (int ci = 0; ci < 8 && found < 4; ci++) {  // MuJoCo mjc_PlaneBox: corners in index order, at most 4
+          const T s0 = (ci & 1) ? T(1) : T(-1), s1 = (ci & 2) ? T(1) : T(-1), s2 = (ci & 4) ? T(1) : T(-1);
+          const T ld = s0 * h[0][2] + s1 * h[1][2] + s2 * h[2][2];
+          const T dist = cw[2] + ld;
+          if (dist > T(0) || ld > T(0)) continue;
+          found++;
+          if (!(dist < T(0)) || nc >= SO_MAX_CON) continue;  // in the gap: detected, not instantiated
+          cpos[nc][0] = cw[0] + s0 * h[0][0] + s1 * h[1][0] + s2 * h[2][0];
+          cpos[nc][1] = cw[1] + s0 * h[0][1] + s1 * h[1][1] + s2 * h[2][1];
+          cpos[nc][2] = T(0.5) * dist;  // corner - n dist / 2
+          const T imp = impedance_f(P.imp0, P.imp1, P.imp_w, P.imp_rw, P.imp_mid, P.imp_rmid, P.imp_r1mid, P.imp_pow, dist);
+          T R = (T(1) - imp) * P.diag[k] / imp;
+          R = R < T(1e-15) ? T(1e-15) : R;
+          cD[nc] = T(1) / R;
+          cc0[nc] = -P.K * imp * dist;  // completed with the velocity terms below
+          cnj[nc] = i + 1;
+          nc++;
+        }
+      }
+    }
+  }
+  if (nc == 0) return 0;
+  // point Jacobian of contact k, columns j < cnj[k]:  z_j x (pos - o_j)
+  auto jac = [&](int k, T* Jx, T* Jy, T* Jz) {
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) {
+      const T dx = cpos[k][0] - org[j][0], dy = cpos[k][1] - org[j][1], dz = cpos[k][2] - org[j][2];
+      const bool on = j < cnj[k];
+      Jx[j] = on ? zax[j][1] * dz - zax[j][2] * dy : T(0);
+      Jy[j] = on ? zax[j][2] * dx - zax[j][0] * dz : T(0);
+      Jz[j] = on ? zax[j][0] * dy - zax[j][1] * dx : T(0);
+    }
+  };
+  for (int k = 0; k < nc; k++) {  // aref of row (sigma, t) = c0 - sigma b_t,  c0 = -B vz - K imp dist,  b_t = B mu v_t
+    T Jx[SO_NJ], Jy[SO_NJ], Jz[SO_NJ], vx = T(0), vy = T(0), vz = T(0);
+    jac(k, Jx, Jy, Jz);
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) { vx += Jx[j] * io.qd[j]; vy += Jy[j] * io.qd[j]; vz += Jz[j] * io.qd[j]; }
+    cc0[k] -= P.B * vz;
+    cbx[k] = P.B * P.mu * vx;
+    cby[k] = P.B * P.mu * vy;
+  }
+  // per-dof rows (the ones solve_qacc handles): friction loss, and the limit row of a joint outside its range
+  T af[SO_NJ], xl[SO_NJ], sDl[SO_NJ];
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) {
+    af[j] = -K.fr_B[j] * io.qd[j];
+    xl[j] = T(0); sDl[j] = T(0);
+    if ((io.q[j] - K.lo[j]) - io.qc[j] < T(0) || (K.hi[j] - io.q[j]) + io.qc[j] < T(0)) {
+      T rm2, kap2;
+      limit_row(K, j, io.M[midx(j, j)], io.q[j], io.qc[j], io.qd[j], xl[j], sDl[j], rm2, kap2);
+    }
+  }
+  // gradient and generalised Hessian (packed lower triangle) at x; the contact residuals (e, ty, tx) are kept for the
+  // line search: rows of contact k are  e + ty, e - ty, e + tx, e - tx, each active iff < 0
+  T ce[SO_MAX_CON], cty[SO_MAX_CON], ctx[SO_MAX_CON];
+  auto eval = [&](const T* x, T* g, T* H) {
+#pragma unroll
+    for (int k = 0; k < 21; k++) H[k] = io.M[k];
+#pragma unroll
+    for (int i = 0; i < SO_NJ; i++) {
+      T v = -io.b[i];
+#pragma unroll
+      for (int j = 0; j < SO_NJ; j++) v += (j <= i ? io.M[midx(i, j)] : io.M[midx(j, i)]) * x[j];
+      const T t = K.fr_D[i] * (x[i] - af[i]);  // Huber friction row: force -clamp(D r, +-loss)
+      if (t > -K.fr_loss[i] && t < K.fr_loss[i]) { v += t; H[midx(i, i)] += K.fr_D[i]; }
+      else v += t < T(0) ? -K.fr_loss[i] : K.fr_loss[i];
+      if (sDl[i] != T(0) && sDl[i] * (x[i] - xl[i]) < T(0)) {  // limit row active
+        const T Dl = sDl[i] < T(0) ? -sDl[i] : sDl[i];
+        v += Dl * (x[i] - xl[i]);
+        H[midx(i, i)] += Dl;
+      }
+      g[i] = v;
+    }
+    for (int k = 0; k < nc; k++) {
+      T Jx[SO_NJ], Jy[SO_NJ], Jz[SO_NJ], jx = T(0), jy = T(0), jz = T(0);
+      jac(k, Jx, Jy, Jz);
+#pragma unroll
+      for (int j = 0; j < SO_NJ; j++) { jx += Jx[j] * x[j]; jy += Jy[j] * x[j]; jz += Jz[j] * x[j]; }
+      const T e = jz - cc0[k], ty = P.mu * jy + cby[k], tx = P.mu * jx + cbx[k];
+      ce[k] = e; cty[k] = ty; ctx[k] = tx;
+      const T r1 = e + ty, r2 = e - ty, r3 = e + tx, r4 = e - tx;
+      const T a1 = r1 < T(0) ? T(1) : T(0), a2 = r2 < T(0) ? T(1) : T(0), a3 = r3 < T(0) ? T(1) : T(0), a4 = r4 < T(0) ? T(1) : T(0);
+      const T nact = a1 + a2 + a3 + a4;
+      if (nact == T(0)) continue;
+      const T D = cD[k], mu = P.mu;
+      const T gz = D * (a1 * r1 + a2 * r2 + a3 * r3 + a4 * r4), gy = D * mu * (a1 * r1 - a2 * r2), gx = D * mu * (a3 * r3 - a4 * r4);
+      const T hzz = D * nact, hzy = D * mu * (a1 - a2), hyy = D * mu * mu * (a1 + a2), hzx = D * mu * (a3 - a4), hxx = D * mu * mu * (a3 + a4);
+#pragma unroll
+      for (int i = 0; i < SO_NJ; i++) {
+        g[i] += gz * Jz[i] + gy * Jy[i] + gx * Jx[i];
+        const T uz = hzz * Jz[i] + hzy * Jy[i] + hzx * Jx[i], uy = hzy * Jz[i] + hyy * Jy[i], ux = hzx * Jz[i] + hxx * Jx[i];
+#pragma unroll
+        for (int j = 0; j <= i; j++) H[midx(i, j)] += uz * Jz[j] + uy * Jy[j] + ux * Jx[j];
+      }
+    }
+  };
+  const T tol = sizeof(T) == 8 ? T(1e-13) : T(1e-4);    // relative size of the last Newton step (quadratic convergence: the error is its square)
+  const T lstol = sizeof(T) == 8 ? T(1e-12) : T(1e-5);  // |phi'(alpha)| / |phi'(0)| at which the line search stops
+  T x[SO_NJ], g[SO_NJ], H[21];
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) x[j] = io.a[j];
+  int evals = 0;
+  bool ok = false;
+  for (int it = 0; it < 40 && !ok; it++) {
+    eval(x, g, H);
+    evals++;
+    T p[SO_NJ], ng[SO_NJ], Mp[SO_NJ], d0 = T(0), pMp = T(0), ds = T(0), pmax = T(0), xmax = T(1);
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) ng[j] = -g[j];
+    if (!chol_solve6(H, ng, p)) { evals = -evals; break; }
+#pragma unroll
+    for (int i = 0; i < SO_NJ; i++) {
+      T v = T(0), w = -io.b[i];
+#pragma unroll
+      for (int j = 0; j < SO_NJ; j++) {
+        const T mij = j <= i ? io.M[midx(i, j)] : io.M[midx(j, i)];
+        v += mij * p[j]; w += mij * x[j];
+      }
+      Mp[i] = v;
+      pMp += p[i] * v;
+      ds += w * p[i];  // smooth part of phi'(0)
+      d0 += g[i] * p[i];
+      const T ap = p[i] < T(0) ? -p[i] : p[i], ax = x[i] < T(0) ? -x[i] : x[i];
+      pmax = ap > pmax ? ap : pmax; xmax = ax > xmax ? ax : xmax;
+    }
+    if (!(d0 < T(0))) { ok = true; break; }  // stationary to rounding
+    // slopes of the contact residuals along p
+    T se[SO_MAX_CON], sty[SO_MAX_CON], stx[SO_MAX_CON];
+    for (int k = 0; k < nc; k++) {
+      T Jx[SO_NJ], Jy[SO_NJ], Jz[SO_NJ], jx = T(0), jy = T(0), jz = T(0);
+      jac(k, Jx, Jy, Jz);
+#pragma unroll
+      for (int j = 0; j < SO_NJ; j++) { jx += Jx[j] * p[j]; jy += Jy[j] * p[j]; jz += Jz[j] * p[j]; }
+      se[k] = jz; sty[k] = P.mu * jy; stx[k] = P.mu * jx;
+    }
+    // phi'(alpha) and phi''(alpha): phi' is piecewise linear and increasing, so Newton on it is exact within a piece.
+    // `same` reports whether every row is in the state it had at alpha = 0.
+    auto dphi = [&](T al, T& curv, bool& same) -> T {
+      T d = ds + al * pMp, cv = pMp;
+      same = true;
+#pragma unroll
+      for (int j = 0; j < SO_NJ; j++) {
+        const T r0 = x[j] - af[j], t0 = K.fr_D[j] * r0, t = K.fr_D[j] * (r0 + al * p[j]);
+        const bool q0 = t0 > -K.fr_loss[j] && t0 < K.fr_loss[j], q1 = t > -K.fr_loss[j] && t < K.fr_loss[j];
+        if (q1) { d += t * p[j]; cv += K.fr_D[j] * p[j] * p[j]; }
+        else d += (t < T(0) ? -K.fr_loss[j] : K.fr_loss[j]) * p[j];
+        same = same && (q0 == q1) && (q1 || ((t0 < T(0)) == (t < T(0))));
+        if (sDl[j] != T(0)) {
+          const T l0 = x[j] - xl[j], l1 = l0 + al * p[j];
+          const bool b0 = sDl[j] * l0 < T(0), b1 = sDl[j] * l1 < T(0);
+          if (b1) { const T Dl = sDl[j] < T(0) ? -sDl[j] : sDl[j]; d += Dl * l1 * p[j]; cv += Dl * p[j] * p[j]; }
+          same = same && (b0 == b1);
+        }
+      }
+      for (int k = 0; k < nc; k++) {
+        const T e = ce[k] + al * se[k], ty = cty[k] + al * sty[k], tx = ctx[k] + al * stx[k];
+        const T r[4] = {e + ty, e - ty, e + tx, e - tx};
+        const T r00[4] = {ce[k] + cty[k], ce[k] - cty[k], ce[k] + ctx[k], ce[k] - ctx[k]};
+        const T sl[4] = {se[k] + sty[k], se[k] - sty[k], se[k] + stx[k], se[k] - stx[k]};
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          if (r[m] < T(0)) { d += cD[k] * r[m] * sl[m]; cv += cD[k] * sl[m] * sl[m]; }
+          same = same && ((r[m] < T(0)) == (r00[m] < T(0)));
+        }
+      }
+      curv = cv;
+      return d;
+    };
+    T lo = T(0), dlo = d0, hi = T(-1), dhi = T(0), alpha = T(1);
+    bool same = false;
+    for (int ls = 0; ls < 30; ls++) {
+      T cv;
+      const T d = dphi(alpha, cv, same);
+      const T ad = d < T(0) ? -d : d;
+      if (ad <= lstol * -d0) break;
+      if (d < T(0)) { lo = alpha; dlo = d; } else { hi = alpha; dhi = d; }
+      T an = alpha - d / cv;                                        // exact if no row switches in between
+      const bool inside = an > lo && (hi < T(0) || an < hi);
+      if (!inside) an = hi < T(0) ? T(2) * alpha : lo + (hi - lo) * (-dlo) / (dhi - dlo);
+      alpha = an;
+    }
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) x[j] += alpha * p[j];
+    // the minimiser of the quadratic piece x started in, reached without any row switching state: done
+    ok = same || alpha * pmax <= tol * xmax;
+  }
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) io.a[j] = x[j];
+  if (evals > 0 && !ok) evals = -evals;
+  return evals;
+}
+

@@ -22,6 +22,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 NJ = 6
+MAX_PAD = 8
 PREFIX = "so100_"  # reference: MUJOCO_SO100_PREFIX, envs/utils.py:7
 JOINT_NAMES = ["Rotation", "Pitch", "Elbow", "Wrist_Pitch", "Wrist_Roll", "Jaw"]
 BODY_NAMES = ["Rotation_Pitch", "Upper_Arm", "Lower_Arm", "Wrist_Pitch_Roll", "Fixed_Jaw", "Moving_Jaw"]
@@ -111,6 +112,17 @@ class So100Model(ctypes.Structure):
         ("contact_solimp", ctypes.c_double * 5),
         ("block_ncon", ctypes.c_int32),
         ("_pad1", ctypes.c_int32),
+        ("n_pad", ctypes.c_int32),
+        ("_pad2", ctypes.c_int32),
+        ("pad_body", ctypes.c_int32 * MAX_PAD),
+        ("pad_pos", (ctypes.c_double * 3) * MAX_PAD),
+        ("pad_size", (ctypes.c_double * 3) * MAX_PAD),
+        ("pad_solref", ctypes.c_double * 2),
+        ("pad_solimp", ctypes.c_double * 5),
+        ("pad_friction", ctypes.c_double),
+        ("floor_solref", ctypes.c_double * 2),
+        ("floor_solimp", ctypes.c_double * 5),
+        ("floor_friction", ctypes.c_double),
     ]
 
 
@@ -156,6 +168,17 @@ class ModelSpec:
     contact_solref: np.ndarray = field(default_factory=lambda: np.array(_DEF_SOLREF))
     contact_solimp: np.ndarray = field(default_factory=lambda: np.array(_DEF_SOLIMP))
     block_ncon: int = 4  # bottom corners of a flat box on a plane (mjc_PlaneBox); 0 = the pair does not collide
+    # arm <-> floor: the jaws' primitive box colliders (so_arm100_camera.xml:60-61, 108-111, 120-123) and the floor geom
+    pad_body: list = field(default_factory=list)          # body index per pad (4 = Fixed_Jaw, 5 = Moving_Jaw)
+    pad_names: list = field(default_factory=list)
+    pad_pos: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))
+    pad_size: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))
+    pad_solref: np.ndarray = field(default_factory=lambda: np.array(_DEF_SOLREF))
+    pad_solimp: np.ndarray = field(default_factory=lambda: np.array(_DEF_SOLIMP))
+    pad_friction: float = 1.0
+    floor_solref: np.ndarray = field(default_factory=lambda: np.array(_DEF_SOLREF))
+    floor_solimp: np.ndarray = field(default_factory=lambda: np.array(_DEF_SOLIMP))
+    floor_friction: float = 1.0
     joint_names: list = field(default_factory=lambda: list(JOINT_NAMES))
     source: str = ""
 
@@ -185,6 +208,14 @@ class ModelSpec:
                      "act_kp", "act_dampratio", "act_kv", "act_ctrlrange", "act_forcerange", "ee_offset",
                      "cam_pos", "cam_quat", "contact_solref", "contact_solimp"):
             put(getattr(m, name), getattr(self, name))
+        m.n_pad = len(self.pad_body)
+        for k, b in enumerate(self.pad_body):
+            m.pad_body[k] = int(b)
+        put(m.pad_pos, np.asarray(self.pad_pos, dtype=np.float64).reshape(-1, 3))
+        put(m.pad_size, np.asarray(self.pad_size, dtype=np.float64).reshape(-1, 3))
+        for name in ("pad_solref", "pad_solimp", "floor_solref", "floor_solimp"):
+            put(getattr(m, name), getattr(self, name))
+        m.pad_friction, m.floor_friction = float(self.pad_friction), float(self.floor_friction)
         return m
 
 
@@ -307,6 +338,7 @@ def load_model(path: str | None = None) -> ModelSpec:
     childclass = base_el.get("childclass")
     cur = base_el
     joint_names = []
+    pad_geoms = []   # (body index, resolved geom attributes) of the arm's primitive (box) colliders
     for i, bname in enumerate(BODY_NAMES):
         nxt = None
         for b in cur.findall("body"):
@@ -358,6 +390,10 @@ def load_model(path: str | None = None) -> ModelSpec:
             v = _floats(ja["solimpfriction"])
             spec.dof_solimp_friction[i, :len(v)] = v
         joint_names.append(strip(j.get("name")))
+        for g in cur.findall("geom"):
+            ga = defaults.resolve("geom", g.get("class") or childclass, dict(g.attrib))
+            if ga.get("type", "sphere") == "box" and (int(ga.get("contype", "1")) or int(ga.get("conaffinity", "1"))):
+                pad_geoms.append((i, ga))
         cam = cur.find("camera")
         if cam is not None and strip(cam.get("name")) in ("end_point_camera",):
             spec.cam_body = i
@@ -365,6 +401,7 @@ def load_model(path: str | None = None) -> ModelSpec:
             spec.cam_quat = _orientation(cam, radians)
             spec.cam_fovy_deg = float(cam.get("fovy", "45"))
     spec.joint_names = joint_names
+    _read_pads(pad_geoms, defaults, spec)
     spec.ee_body = BODY_NAMES.index("Fixed_Jaw")
     spec.wrist_body = BODY_NAMES.index("Wrist_Pitch_Roll")
 
@@ -393,6 +430,38 @@ def load_model(path: str | None = None) -> ModelSpec:
     return spec
 
 
+def _geom_par(ga: dict, name: str, default) -> np.ndarray:
+    v = _floats(ga[name]) if ga.get(name) else []
+    return np.array(v + list(default[len(v):]), dtype=np.float64)
+
+
+def _read_pads(pad_geoms, defaults: "_Defaults", spec: ModelSpec) -> None:
+    """The arm's primitive box colliders (`finger_collision` pads on the jaws).  Mesh colliders are skipped: the STL
+    files are not in the checkout.  All pads must share one set of contact parameters."""
+    if not pad_geoms:
+        return
+    if len(pad_geoms) > MAX_PAD:
+        raise ValueError(f"more than {MAX_PAD} primitive colliders on the arm")
+    pos, size, par = [], [], None
+    for body, ga in pad_geoms:
+        if ga.get("quat") or ga.get("euler") or ga.get("axisangle") or ga.get("zaxis") or ga.get("xyaxes"):
+            raise ValueError("rotated box colliders are not supported")
+        if int(ga.get("condim", "3")) != 3 or int(ga.get("priority", "0")) != 0 or float(ga.get("solmix", "1")) != 1.0 \
+                or float(ga.get("margin", "0")) != 0.0 or float(ga.get("gap", "0")) != 0.0:
+            raise ValueError("box colliders must use condim 3 and default priority / solmix / margin / gap")
+        pos.append(_floats(ga.get("pos", "0 0 0")))
+        size.append(_floats(ga["size"]))
+        p = (tuple(_geom_par(ga, "solref", _DEF_SOLREF)), tuple(_geom_par(ga, "solimp", _DEF_SOLIMP)),
+             float(_geom_par(ga, "friction", (1.0, 0.005, 0.0001))[0]))
+        if par is not None and p != par:
+            raise ValueError("box colliders with different contact parameters are not supported")
+        par = p
+        spec.pad_body.append(body)
+        spec.pad_names.append(ga.get("name", ""))
+    spec.pad_pos, spec.pad_size = np.array(pos), np.array(size)
+    spec.pad_solref, spec.pad_solimp, spec.pad_friction = np.array(par[0]), np.array(par[1]), par[2]
+
+
 def _read_block(root, spec: ModelSpec) -> None:
     """The free block and the floor plane of the SCENE file (env01.xml:29-39): box half-size, mass, contact parameters.
 
@@ -410,6 +479,14 @@ def _read_block(root, spec: ModelSpec) -> None:
         for g in wb.findall("geom"):
             if g.get("type") == "plane":
                 floor = g
+    if floor is not None:
+        if any(abs(v) > 0 for v in _floats(floor.get("pos", "0 0 0"))) or floor.get("quat") or floor.get("euler"):
+            raise ValueError("only the z = 0 floor plane is supported")
+        spec.floor_solref = _geom_par(floor.attrib, "solref", _DEF_SOLREF)
+        spec.floor_solimp = _geom_par(floor.attrib, "solimp", _DEF_SOLIMP)
+        spec.floor_friction = float(_geom_par(floor.attrib, "friction", (1.0, 0.005, 0.0001))[0])
+    else:  # no floor: nothing for the pads to touch
+        spec.pad_body, spec.pad_names, spec.pad_pos, spec.pad_size = [], [], np.zeros((0, 3)), np.zeros((0, 3))
     if blk is None or floor is None:
         spec.block_ncon = 0
         return

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported(native_lib):
 
 
 def test_abi_version_and_dims(native_lib):
-    assert native_lib.so100_abi_version() == 2
+    assert native_lib.so100_abi_version() == 3
     assert native_lib.so100_obs_dim(1) == 15 and native_lib.so100_obs_dim(2) == 15 and native_lib.so100_obs_dim(5) == 8
     assert native_lib.so100_act_dim(5) == 6 and native_lib.so100_obs_dim(6) == 15
     assert native_lib.so100_obs_dim(3) < 0

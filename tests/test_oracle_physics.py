@@ -152,7 +152,8 @@ def test_newton_reaches_the_unique_minimiser(orc, spec):
         M = orc.mass_matrix(q)
         assert np.abs(M @ (a - a_s) - fc).max() < 1e-10 * (1 + np.abs(M @ a_s).max())
         inside = (q >= spec.jnt_range[:, 0]) & (q <= spec.jnt_range[:, 1])
-        assert (np.abs(fc[inside]) <= 0.1 + 1e-12).all()   # friction-loss bound where no limit row is active
+        if len(orc.contacts(q)[1]) == 0:                     # (pad-floor contact rows add their own joint torques)
+            assert (np.abs(fc[inside]) <= 0.1 + 1e-12).all()   # friction-loss bound where no limit row is active
 
 
 def test_against_real_mujoco_if_available(orc):
