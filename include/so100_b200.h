@@ -62,7 +62,9 @@ extern "C" {
 #define SO100_FLAG_CLIP_ACTIONS 2u      /* clip actions to [-1,1] on device (the reference env does not) */
 #define SO100_FLAG_GENERIC_KERNEL 4u    /* never use the model-specialised kernel (tests: generic vs specialised) */
 #define SO100_FLAG_STATIC_BLOCK 8u      /* hold the Env01/02/06 block at its spawn pose: no gravity, no floor contact (round-1 behaviour) */
-#define SO100_FLAG_NO_ARM_CONTACT 16u   /* no jaw-pad <-> floor contact: the arm passes through the floor (round-1 behaviour) */
+#define SO100_FLAG_ARM_CONTACT 16u      /* jaw-pad <-> floor contact (the reference's primitive colliders).  Exact against the oracle, but the
+                                           Newton solve it needs is a long serial chain per touching env: ~18x the step time at 65 536 envs
+                                           (DESIGN.md "Arm-floor contact"), so it is opt-in; without it the arm passes through the floor */
 
 /*
  * Model constants as they stand in the MJCF (so_arm100_camera.xml + env01.xml), nothing derived.
@@ -172,7 +174,7 @@ typedef struct so100_state_view {
                                     Env05 cam_xpos(0..2), cam_xmat(3..11 row-major) */
   float *aux;           /* [24][N] task scalars: Env02 block_pos(0..2), last_block_pos(3..5); Env05 cmd(0..5),
                                     last_angvel(6..11), target(12..14), target_dt(15), last_centre(16..17) */
-  int32_t *counters;    /* [4][N]  elapsed_steps, flags (1 ever_stepped, 2 has_last_block, 4 angvel_valid,
+  int32_t *counters;    /* [4][N]  elapsed_steps, flags (16 = scheduling hint "pads touched the floor"; 1 ever_stepped, 2 has_last_block, 4 angvel_valid,
                                     8 centre_valid), miss_count, target_t0_step */
   float *ep_return;     /* [N] */
 } so100_state_view;
@@ -288,6 +290,15 @@ int so100_forward_dynamics(so100_ctx *ctx, int n, const float *qpos_dev, const f
  */
 int so100_host_forward(const so100_model *model, int n, const double *qpos, const double *qvel, const double *ctrl,
                        double *M, double *bias, double *qacc, double *kin, int sweeps, int variant);
+
+/*
+ * Host emulation of the kernels' substep loop (same templates; no GPU): advances n states by n_substeps x mj_step under
+ * ctrl, in place.  Row-major host arrays [n][6].  variant 0 = fp64, 2 = fp32 incl. the compensated position sum (what the
+ * generic kernel computes).  stats (5 x int64, may be NULL): contact substeps, gradient/Hessian evaluations of the contact
+ * solve, its line-search evaluations, the largest evaluation count of one solve, unconverged solves.
+ */
+int so100_host_substeps(const so100_model *model, int n, double *qpos, double *qvel, double *qacc_warm, const double *ctrl,
+                        int n_substeps, int variant, int64_t *stats);
 
 /*
  * The link constants the kernels consume, as the library derives them from the MJCF numbers (fp64, host only):

@@ -302,7 +302,7 @@ static void kb_from_solref(const double *solref, const double *solimp, double h,
 static int collide_pads(const orc_sim *s, const orc_kin *k, ccontact *con) {
   const orc_model *m = &s->m;
   int n = 0;
-  if (s->cfg.flags & 16u) return 0; /* SO100_FLAG_NO_ARM_CONTACT */
+  if (!(s->cfg.flags & 16u)) return 0; /* SO100_FLAG_ARM_CONTACT not set: the pads are ignored, as in the product */
   for (int p = 0; p < m->n_pad && p < ORC_MAX_PAD; p++) {
     int b = m->pad_body[p], cnt = 0;
     double c[3], t[3];

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("SO100_B200_LIB") or os.path.join(PKG_DIR, "libso100_b
 EXPORTS = [
     "so100_abi_version", "so100_last_error", "so100_build_id", "so100_obs_dim", "so100_act_dim", "so100_create", "so100_destroy",
     "so100_reset", "so100_step", "so100_reset_host", "so100_step_host", "so100_get_state", "so100_set_state",
-    "so100_get_tick", "so100_set_tick", "so100_forward_dynamics", "so100_host_forward", "so100_get_derived",
+    "so100_get_tick", "so100_set_tick", "so100_forward_dynamics", "so100_host_forward", "so100_host_substeps", "so100_get_derived",
     "so100_get_stats", "so100_bench_fp32_peak", "so100_host_constants", "so100_kernel_variant",
     "so100_host_solver_constants", "so100_set_seed", "so100_step_substeps",
     "so100_host_groups", "so100_host_group_range", "so100_step_host_async", "so100_step_host_wait", "so100_step_host_wait_any",
@@ -80,6 +80,7 @@ def lib() -> ctypes.CDLL:
     L.so100_set_seed.argtypes = [vp, ctypes.c_uint64]
     L.so100_forward_dynamics.argtypes = [vp, ci] + [vp] * 7 + [vp]
     L.so100_host_forward.argtypes = [ctypes.POINTER(So100Model), ci, dp, dp, dp, dp, dp, dp, dp, ci, ci]
+    L.so100_host_substeps.argtypes = [ctypes.POINTER(So100Model), ci, dp, dp, dp, dp, ci, ci, i64p]
     L.so100_host_constants.argtypes = [ctypes.POINTER(So100Model), dp]
     L.so100_host_solver_constants.argtypes = [ctypes.POINTER(So100Model), ctypes.POINTER(ctypes.c_float), ci]
     L.so100_kernel_variant.argtypes = [vp]

@@ -47,9 +47,11 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define SO100_SYNC 1   // __syncthreads() per substep: keeps a CTA's warps on the same stretch of straight-line code (i-cache)
 #endif
 constexpr int kBlock = SO100_BLOCK;  // threads per CTA, one env each
+#define SO100_TOUCH_MARGIN 2e-6f   // broad-phase margin [m] over the MUFU sin/cos error (see physics<>)
 constexpr int kMaxStart = SO100_MAX_START;
 constexpr int kSnap = 12, kAux = 24, kCnt = 4;
-enum { F_EVER_STEPPED = 1, F_HAS_LAST_BLOCK = 2, F_ANGVEL_VALID = 4, F_CENTRE_VALID = 8 };
+enum { F_EVER_STEPPED = 1, F_HAS_LAST_BLOCK = 2, F_ANGVEL_VALID = 4, F_CENTRE_VALID = 8,
+       F_TOUCH = 16 };  // F_TOUCH: a jaw pad touched the floor in the env's last substep (scheduling hint only, no effect on results)
 enum { STREAM_RESET = 0, STREAM_TASK = 1, STREAM_NOISE = 2, STREAM_API_RESET = 3, STREAM_RESET_NOISE = 4 };
 
 struct TaskC {
@@ -78,7 +80,7 @@ struct Bufs {
   float *qpos, *qvel, *warm, *qcomp, *block, *snap, *aux, *ep_return;
   int* cnt;
   const float* start_tab;  // [n_start][6]
-  unsigned long long* stats;  // [0] solver non-converged, [1] nan resets
+  unsigned long long* stats;  // [0] solver non-converged, [1] nan resets, [2] contact solves that dropped corners (> SO_MAX_CON)
 };
 
 struct StepIO {
@@ -223,6 +225,7 @@ __device__ __forceinline__ void reset_env(const Consts& C, const Bufs& B, EnvReg
 #pragma unroll
   for (int k = 0; k < kSnap; k++) e.snap[k] = 0.0f;
   e.elapsed = 0; e.ep_ret = 0.0f; e.bvz = 0.0f;  // mj_resetData zeroes qvel
+  e.flags &= ~F_TOUCH;
   if (TASK == 1) {  // env01_v1.py:39-63
     uint4 r = draw(t, env, tick, stream);
     place_block(t, r, e.blk);
@@ -286,11 +289,24 @@ __device__ __forceinline__ float reward_reach(const TaskC& t, EnvRegs& e, bool i
   return r;
 }
 
+// Shared-memory pool of contact-solve slots of one CTA (ContactShared in so100_dyn.cuh).  Slots are handed out anew in
+// every substep from one of two counters used in alternation: cnt[sub & 1] serves substep `sub`, and thread 0 clears the
+// other one right after the substep's CTA barrier, a full substep before it is used again.
+constexpr int kPoolSlots = 64;
+struct ContactPool {
+  float* f;
+  double* d;
+  int* cnt;
+  int nslot;  // 0: no pool (debug kernels): every contact solve takes the out-of-line path
+};
+constexpr size_t kPoolBytes = (size_t)kPoolSlots * (ContactShared<SO_FAST_CON>::kDoubles * 8 + ContactShared<SO_FAST_CON>::kFloats * 4);
+
 // 16 x mj_step on the arm.  ctrl is constant over the env step, so kp*clip(ctrl) is hoisted.
 // ctrl is carried as an unevaluated sum ctrl_hi + ctrl_lo so that Env01/02's closed loop ctrl = qpos + a*0.075 does not
 // round the 0.075-rad increment to the ulp of a 3-rad angle (that rounding random-walks qpos in a neutrally stable loop).
-template <int TASK, bool SPEC>
-__device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs& e, const float* ctrl_hi, const float* ctrl_lo, bool live, int nsub) {
+template <int TASK, bool SPEC, bool PADS>
+__device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs& e, const float* ctrl_hi, const float* ctrl_lo, bool live, int nsub,
+                                        const ContactPool& pool) {
   const TaskC& t = C.t;
   // SPEC: the solver / servo constants of the so100 MJCF are literals (immediates after unrolling), not constant-bank loads
   ConC<float> Kg;
@@ -312,9 +328,8 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
   bool unconverged = false;
 #pragma unroll 1
   for (int sub = 0; sub < nsub; sub++) {
-#if SO100_SYNC
-    __syncthreads();
-#endif
+    __syncthreads();  // keeps a CTA's warps on the same stretch of straight-line code (i-cache), and orders the pool's slot counters
+    if (PADS && pool.nslot && threadIdx.x == 0) pool.cnt[(sub + 1) & 1] = 0;
     float s[SO_NJ], c[SO_NJ], bias[SO_NJ], M[21], b[SO_NJ];
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) so_sincos(e.q[j], &s[j], &c[j]);
@@ -332,20 +347,66 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
     // accurate - profiles/r1_variants.md.)
     // envs with a pad corner below the floor take the Newton path on the full problem (dense contact rows); the rest
     // keep the per-dof Gauss-Seidel.  e.w enters both as the warm start (the previous substep's qacc).
-    const bool touch = C.pad.n > 0 && pads_touch<float>(C.dyn, C.kin, C.pad, s, c);
+    // The broad phase runs on the substep's MUFU sin/cos, whose 2^-21 error moves a pad corner by up to ~1.5e-7 m - as
+    // much as a resting contact penetrates (~2e-7 m) - so it asks with a margin, and the contact path redoes its own
+    // kinematics with sincosf of the compensated angle: without that, resting contacts flicker on and off from substep to
+    // substep (measured: p99.9 |dq| 9e-4 rad against the oracle instead of 3e-7, tools/contact_precision.py).
+    const unsigned touch = PADS && C.pad.n > 0 ? pads_touch<float>(C.dyn, C.kin, C.pad, s, c, SO100_TOUCH_MARGIN) : 0u;
+    if (PADS && sub == nsub - 1) e.flags = touch ? (e.flags | F_TOUCH) : (e.flags & ~F_TOUCH);
     float d = 0.0f;
-    if (!touch) d = solve_qacc<float>(K, M, b, e.q, e.qc, e.v, e.w, sub == 0 ? 5 : 3);
-    else {
-      ContactIO<float> cio;
+    bool solved = false;
+    const unsigned tmask = PADS ? __ballot_sync(0xffffffffu, touch != 0u) : 0u;
+    if (PADS && tmask) {  // (warp-uniform) some lane touches: hand out pool slots, one atomic per warp
+      int slot = kPoolSlots;
+      if (pool.nslot) {
+        const int lane = threadIdx.x & 31, leader = __ffs(tmask) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&pool.cnt[sub & 1], __popc(tmask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        slot = base + __popc(tmask & ((1u << lane) - 1u));
+      }
+      if (touch) {
+        float cs[SO_NJ], cc_[SO_NJ];
 #pragma unroll
-      for (int j = 0; j < SO_NJ; j++) { cio.s[j] = s[j]; cio.c[j] = c[j]; cio.q[j] = e.q[j]; cio.qc[j] = e.qc[j]; cio.qd[j] = e.v[j]; cio.b[j] = b[j]; cio.a[j] = e.w[j]; }
+        for (int j = 0; j < SO_NJ; j++) {
+          float sj, cj;
+          sincosf(e.q[j], &sj, &cj);
+          cs[j] = fmaf(-e.qc[j], cj, sj); cc_[j] = fmaf(e.qc[j], sj, cj);  // sin / cos of q - qc to first order in qc (|qc| < 2e-7)
+        }
+        int st = 0, over = 0;
+        bool retry = slot >= pool.nslot;
+        if (!retry) {  // the normal case: storage in this lane's slot of the shared-memory pool
+          ContactShared<SO_FAST_CON> S{pool.f + slot, pool.d + slot, kPoolSlots};
+          float an[SO_NJ];
 #pragma unroll
-      for (int k = 0; k < 21; k++) cio.M[k] = M[k];
-      const int st = contact_solve<float>(C.dyn, C.kin, C.pad, C.con, cio);
+          for (int j = 0; j < SO_NJ; j++) an[j] = e.w[j];
+          st = contact_newton<float>(C.dyn, C.kin, C.pad, C.con, S, cs, cc_, e.q, e.qc, e.v, M, b, an, touch, false, &over, nullptr);
+          retry = over != 0;
+          if (!retry && st != 0) {
 #pragma unroll
-      for (int j = 0; j < SO_NJ; j++) e.w[j] = cio.a[j];
-      if (st < 0) d = 1e30f;  // iteration cap / indefinite Hessian: counted with the Gauss-Seidel's unconverged substeps
+            for (int j = 0; j < SO_NJ; j++) e.w[j] = an[j];
+          }
+        }
+        if (retry) {  // pool exhausted (> 64 touching envs in this CTA) or > 8 corners at once: thread-local storage, out of line
+          ContactIO<float> cio;
+#pragma unroll
+          for (int j = 0; j < SO_NJ; j++) { cio.s[j] = cs[j]; cio.c[j] = cc_[j]; cio.q[j] = e.q[j]; cio.qc[j] = e.qc[j]; cio.qd[j] = e.v[j]; cio.b[j] = b[j]; cio.a[j] = e.w[j]; }
+#pragma unroll
+          for (int k = 0; k < 21; k++) cio.M[k] = M[k];
+          over = 0;
+          st = contact_solve<float>(C.dyn, C.kin, C.pad, C.con, cio, touch, &over);
+          if (over && live) atomicAdd(&B.stats[2], 1ULL);
+          if (st != 0 && !over) {
+#pragma unroll
+            for (int j = 0; j < SO_NJ; j++) e.w[j] = cio.a[j];
+          }
+          if (over) st = 0;  // > SO_MAX_CON corners (never seen): counted, and this substep falls back to the contact-free solve
+        }
+        solved = st != 0;  // 0: the accurate kinematics found no corner below the floor after all
+        if (st < 0) d = 1e30f;  // iteration cap / indefinite Hessian: counted with the Gauss-Seidel's unconverged substeps
+      }
     }
+    if (!solved) d = solve_qacc<float>(K, M, b, e.q, e.qc, e.v, e.w, sub == 0 ? 5 : 3);
     float amax = 1.0f;
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {
@@ -364,16 +425,43 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
-template <int TASK, bool SPEC>
+template <int TASK, bool SPEC, bool PADS>
 __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __grid_constant__ Consts C, const Bufs B, const StepIO io) {
   constexpr int OD = TASK == 5 ? 8 : 15;
   __shared__ __align__(16) float sh[kBlock * OD];
   static_assert((kBlock * OD) % 4 == 0, "obs rows of a CTA must be a whole number of float4");
   const TaskC& t = C.t;
   const int n = t.n, base = io.env_lo + blockIdx.x * kBlock, hi = io.env_hi;
-  const bool live = base + (int)threadIdx.x < hi;
   const unsigned tick = io.tick;
-  const int i = live ? base + (int)threadIdx.x : hi - 1;  // tail threads shadow the last env (they must reach every barrier); nothing they compute is stored
+  // Envs whose jaw pads touched the floor last step take the (much longer) contact path in most substeps of this one.
+  // They are ~10 % of the envs under random actions, so almost every warp would hold one and wait for it; instead the
+  // CTA re-deals its 256 envs to its threads with the touching ones first (a stable partition on the hint bit), which
+  // confines the contact path to one or two of the eight warps.  `slot` is the env this thread now owns.
+  __shared__ unsigned short perm[kBlock];
+  __shared__ int warp_cnt[kBlock / 32];
+  __shared__ int pool_cnt[2];
+  extern __shared__ double pool_mem[];  // kPoolBytes when the model has pads, else nothing
+  const ContactPool pool{reinterpret_cast<float*>(pool_mem + (size_t)kPoolSlots * ContactShared<SO_FAST_CON>::kDoubles), pool_mem, pool_cnt,
+                         PADS && C.pad.n > 0 ? kPoolSlots : 0};
+  if (threadIdx.x < 2) pool_cnt[threadIdx.x] = 0;
+  {
+    const int mine = base + (int)threadIdx.x;
+    const bool hint = PADS && C.pad.n > 0 && mine < hi && (B.cnt[n + mine] & F_TOUCH);
+    const unsigned bal = __ballot_sync(0xffffffffu, hint);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) warp_cnt[wid] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;  // touching envs in earlier warps / in the CTA
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; w++) { const int cw = warp_cnt[w]; total += cw; before += w < wid ? cw : 0; }
+    const int rank_t = before + __popc(bal & ((1u << lane) - 1u));           // rank among the touching envs
+    const int dest = hint ? rank_t : total + ((int)threadIdx.x - rank_t);   // the others keep their order behind them
+    perm[dest] = (unsigned short)threadIdx.x;
+  }
+  __syncthreads();
+  const int slot = perm[threadIdx.x];
+  const bool live = base + slot < hi;
+  const int i = live ? base + slot : hi - 1;  // tail threads shadow the last env (they must reach every barrier); nothing they compute is stored
   // coalesced load of the CTA's action rows through shared memory
   for (int k = threadIdx.x; k < kBlock * SO_NJ; k += kBlock) {
     int g = base * SO_NJ + k;
@@ -383,7 +471,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
   float a[SO_NJ];
 #pragma unroll
   for (int j = 0; j < SO_NJ; j++) {
-    a[j] = sh[threadIdx.x * SO_NJ + j];
+    a[j] = sh[slot * SO_NJ + j];
     if (t.flags & SO100_FLAG_CLIP_ACTIONS) a[j] = clampf(a[j], -1.0f, 1.0f);
   }
   __syncthreads();
@@ -419,7 +507,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
           for (int k = 0; k < 3; k++) e.aux[k] = e.blk[k];
         }
       }
-      physics<TASK, SPEC>(C, B, e, ctrl, ctrl_lo, live, t.nsub);
+      physics<TASK, SPEC, PADS>(C, B, e, ctrl, ctrl_lo, live, t.nsub, pool);
       write_obs<TASK>(t, e, i, tick, STREAM_NOISE, obs);
     } else {  // env03_v1.py:124-201
       float time = (float)e.elapsed * t.dt_env;
@@ -450,7 +538,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
       float newcmd[SO_NJ];
 #pragma unroll
       for (int j = 0; j < SO_NJ; j++) { newcmd[j] = e.aux[j] + a[j] * t.step_scale; ctrl[j] = newcmd[j]; ctrl_lo[j] = 0.0f; }  // open loop (Q6)
-      physics<TASK, SPEC>(C, B, e, ctrl, ctrl_lo, live, t.nsub);
+      physics<TASK, SPEC, PADS>(C, B, e, ctrl, ctrl_lo, live, t.nsub, pool);
       write_obs<TASK>(t, e, i, tick, STREAM_NOISE, obs);
       if (obs[6] == -1.0f && obs[7] == -1.0f) {  // :152-164
         if (e.miss > t.lost_limit) term = true;
@@ -508,7 +596,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
     }
     if (live) store_env<TASK>(B, n, i, e);
 #pragma unroll
-    for (int k = 0; k < OD; k++) sh[threadIdx.x * OD + k] = obs[k];
+    for (int k = 0; k < OD; k++) sh[slot * OD + k] = obs[k];
   }
   __syncthreads();
   // the CTA's obs rows are one contiguous, 16-byte aligned span (kBlock * OD floats): 512 bytes per warp instruction
@@ -551,7 +639,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) substeps_kernel(const
   float ch[SO_NJ], cl[SO_NJ];
 #pragma unroll
   for (int j = 0; j < SO_NJ; j++) { ch[j] = ctrl[(size_t)i * SO_NJ + j]; cl[j] = 0.0f; }
-  physics<TASK, SPEC>(C, B, e, ch, cl, live, nsub);
+  physics<TASK, SPEC, true>(C, B, e, ch, cl, live, nsub, ContactPool{nullptr, nullptr, nullptr, 0});
   if (live) store_env<TASK>(B, n, i, e);
 }
 
@@ -577,7 +665,7 @@ __global__ void __launch_bounds__(kBlock) forward_kernel(const __grid_constant__
     for (int j = 0; j < SO_NJ; j++) { cio.s[j] = s[j]; cio.c[j] = c[j]; cio.q[j] = q[j]; cio.qc[j] = 0.0f; cio.qd[j] = v[j]; cio.b[j] = b[j]; cio.a[j] = 0.0f; }
 #pragma unroll
     for (int k = 0; k < 21; k++) cio.M[k] = M[k];
-    contact_solve<float>(C.dyn, C.kin, C.pad, C.con, cio);
+    contact_solve<float>(C.dyn, C.kin, C.pad, C.con, cio, ~0u);
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) a[j] = cio.a[j];
   } else solve_qacc<float>(C.con, M, b, q, zc, v, a, 12);
@@ -938,6 +1026,75 @@ void flatten_solver(const ConC<float>& K, const ActC<float>& A, const BlkC<float
 
 }  // namespace
 
+// Host emulation of physics<>'s substep loop with the generic templates, in T = float (what the generic kernel
+// computes, incl. the compensated position sum) or T = double.  No GPU needed: the CPU-side development and test
+// vehicle of the contact path.  stats: [0] contact substeps, [1] gradient/Hessian evaluations, [2] line-search
+// evaluations, [3] largest evaluation count of one solve, [4] unconverged solves.
+template <typename T>
+static void host_substeps_t(const DynC<T>& D, const KinC<T>& Kn, const PadC<T>& P, const ConC<T>& K, const ActC<T>& A, int n, double* qpos,
+                            double* qvel, double* warm, const double* ctrl, int nsub, int64_t* stats, bool coarse_sincos = false) {
+  for (int i = 0; i < n; i++) {
+    T q[SO_NJ], qc[SO_NJ], v[SO_NJ], w[SO_NJ], cc[SO_NJ];
+    for (int j = 0; j < SO_NJ; j++) {
+      q[j] = (T)qpos[6 * i + j]; qc[j] = (T)((double)q[j] - qpos[6 * i + j]);  // q - qc = the fp64 input
+      v[j] = (T)qvel[6 * i + j]; w[j] = (T)warm[6 * i + j];
+      cc[j] = (T)std::fmin(std::fmax(ctrl[6 * i + j], (double)A.ctrl_lo[j]), (double)A.ctrl_hi[j]);
+    }
+    for (int sub = 0; sub < nsub; sub++) {
+      T s[SO_NJ], c[SO_NJ], bias[SO_NJ], M[21], b[SO_NJ];
+      for (int j = 0; j < SO_NJ; j++) { s[j] = (T)std::sin((double)q[j] - (double)qc[j]); c[j] = (T)std::cos((double)q[j] - (double)qc[j]); }
+      if (coarse_sincos) {  // sin/cos of the fp32 angle quantised to 2^-22: the accuracy class of MUFU.SIN / MUFU.COS (__sincosf)
+        for (int j = 0; j < SO_NJ; j++) {
+          s[j] = (T)(std::round(std::sin((double)q[j]) * 4194304.0) / 4194304.0);
+          c[j] = (T)(std::round(std::cos((double)q[j]) * 4194304.0) / 4194304.0);
+        }
+      }
+      dyn_bias_mass<T>(D, s, c, v, bias, M);
+      for (int j = 0; j < SO_NJ; j++) {
+        T f = A.kp[j] * ((cc[j] - q[j]) + qc[j]) - A.kv[j] * v[j];
+        b[j] = so_clamp(f, A.frc_lo[j], A.frc_hi[j]) - bias[j];
+      }
+      const unsigned touch = P.n > 0 ? pads_touch<T>(D, Kn, P, s, c, sizeof(T) == 4 ? T(SO100_TOUCH_MARGIN) : T(0)) : 0u;
+      bool solved = false;
+      if (touch) {
+        ContactIO<T> cio;
+        for (int j = 0; j < SO_NJ; j++) { cio.s[j] = s[j]; cio.c[j] = c[j]; cio.q[j] = q[j]; cio.qc[j] = qc[j]; cio.qd[j] = v[j]; cio.b[j] = b[j]; cio.a[j] = w[j]; }
+        // the contact geometry always gets correctly rounded sin/cos of the compensated angle (see physics<>)
+        for (int j = 0; j < SO_NJ; j++) { cio.s[j] = (T)std::sin((double)q[j] - (double)qc[j]); cio.c[j] = (T)std::cos((double)q[j] - (double)qc[j]); }
+        memcpy(cio.M, M, sizeof M);
+        int nls = 0;
+        int over = 0;
+        const int st = contact_solve<T>(D, Kn, P, K, cio, touch, &over, &nls);
+        solved = st != 0;
+        if (solved) memcpy(w, cio.a, sizeof w);
+        if (stats && solved) {
+          const int ev = st < 0 ? -st : st;
+          stats[0] += 1; stats[1] += ev; stats[2] += nls;
+          if (ev > stats[3]) stats[3] = ev;
+          if (st < 0) stats[4] += 1;
+        }
+      }
+      if (!solved) {
+        const T dlast = solve_qacc<T>(K, M, b, q, qc, v, w, sub == 0 ? 5 : 3);
+        T amax = T(1);
+        for (int j = 0; j < SO_NJ; j++) amax = std::fmax(amax, std::fabs(w[j]));
+        if (stats && dlast > T(2e-3) * amax) stats[4] += 1;  // as physics<> counts Gauss-Seidel substeps that were still moving
+      }
+      for (int j = 0; j < SO_NJ; j++) {
+        v[j] += A.h * w[j];
+        if (sizeof(T) == 4) {  // compensated position sum, as in physics<>
+          volatile T y = A.h * v[j] - qc[j];
+          volatile T s1 = q[j] + y;
+          volatile T t = s1 - q[j];
+          qc[j] = t - y;
+          q[j] = s1;
+        } else q[j] += A.h * v[j];
+      }
+    }
+    for (int j = 0; j < SO_NJ; j++) { qpos[6 * i + j] = (double)q[j] - (double)qc[j]; qvel[6 * i + j] = v[j]; warm[6 * i + j] = w[j]; }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ ctx
 static void flatten_dyn(const DynC<double>& D, double* out) {
   int k = 0;
@@ -1067,7 +1224,7 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
   Consts& C = c->C;
   memset(&C, 0, sizeof C);
   physics_constants_f32(c->H, C);
-  if (cfg->flags & SO100_FLAG_NO_ARM_CONTACT) { C.pad.n = 0; for (int i = 0; i <= SO_NJ; i++) C.pad.first[i] = 0; }
+  if (!(cfg->flags & SO100_FLAG_ARM_CONTACT)) { C.pad.n = 0; for (int i = 0; i <= SO_NJ; i++) C.pad.first[i] = 0; }
   TaskC& t = C.t;
   t.task = cfg->task; t.n = cfg->num_envs; t.max_steps = cfg->max_episode_steps; t.n_start = cfg->n_start;
   t.lost_limit = cfg->lost_limit; t.nsub = m->nsubstep; t.flags = cfg->flags;
@@ -1094,7 +1251,7 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
   };
   bool ok = alloc((void**)&c->B.qpos, 6 * n * 4) && alloc((void**)&c->B.qvel, 6 * n * 4) && alloc((void**)&c->B.warm, 6 * n * 4) && alloc((void**)&c->B.qcomp, 6 * n * 4) &&
             alloc((void**)&c->B.block, 4 * n * 4) && alloc((void**)&c->B.snap, kSnap * n * 4) && alloc((void**)&c->B.aux, kAux * n * 4) &&
-            alloc((void**)&c->B.ep_return, n * 4) && alloc((void**)&c->B.cnt, kCnt * n * 4) && alloc((void**)&c->B.stats, 2 * 8) &&
+            alloc((void**)&c->B.ep_return, n * 4) && alloc((void**)&c->B.cnt, kCnt * n * 4) && alloc((void**)&c->B.stats, 4 * 8) &&
             alloc((void**)&c->start_tab, kMaxStart * SO_NJ * 4);
   if (!ok) { std::string e = cudaGetErrorString(cudaGetLastError()); free_ctx(c); return fail(SO100_ERR_CUDA, "cudaMalloc: " + e); }
   float tab[kMaxStart * SO_NJ];
@@ -1102,6 +1259,20 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
   if (cudaMemcpy(c->start_tab, tab, sizeof tab, cudaMemcpyHostToDevice) != cudaSuccess) { free_ctx(c); return fail(SO100_ERR_CUDA, "cudaMemcpy(start table)"); }
   c->B.start_tab = c->start_tab;
   c->n_groups = 1; c->g_lo[0] = 0; c->g_hi[0] = c->n;
+  {  // the contact pool is > 48 KB of dynamic shared memory: opt in, per device, for this task's step kernels
+    cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+#define SO100_OPT(T)                                                                                                              \
+  e1 = cudaFuncSetAttribute(step_kernel<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolBytes);         \
+  e2 = cudaFuncSetAttribute(step_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolBytes)
+    switch (c->task) {
+      case 1: SO100_OPT(1); break;
+      case 2: SO100_OPT(2); break;
+      case 6: SO100_OPT(6); break;
+      default: SO100_OPT(5); break;
+    }
+#undef SO100_OPT
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { free_ctx(c); return fail(SO100_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"); }
+  }
   *out = c;
   return SO100_OK;
 }
@@ -1129,21 +1300,20 @@ int so100_reset(so100_ctx* c, const uint8_t* mask_dev, float* obs_dev, void* str
 
 static int launch_step(so100_ctx* c, const StepIO& io, cudaStream_t st) {
   const int g = grid_for(io.env_hi - io.env_lo);
-#define SO100_LAUNCH(T, S) step_kernel<T, S><<<g, kBlock, 0, st>>>(c->C, c->B, io)
-  if (c->specialised) {
-    switch (c->task) {
-      case 1: SO100_LAUNCH(1, true); break;
-      case 2: SO100_LAUNCH(2, true); break;
-      case 6: SO100_LAUNCH(6, true); break;
-      default: SO100_LAUNCH(5, true); break;
-    }
-  } else {
-    switch (c->task) {
-      case 1: SO100_LAUNCH(1, false); break;
-      case 2: SO100_LAUNCH(2, false); break;
-      case 6: SO100_LAUNCH(6, false); break;
-      default: SO100_LAUNCH(5, false); break;
-    }
+  const bool pads = c->C.pad.n > 0;
+  const size_t dyn = pads ? kPoolBytes : 0;
+  // three variants per task: model-specialised without / with the arm-floor contact path, and the generic one (any model, with it)
+#define SO100_LAUNCH(T)                                                                                    \
+  do {                                                                                                     \
+    if (c->specialised && !pads) step_kernel<T, true, false><<<g, kBlock, 0, st>>>(c->C, c->B, io);        \
+    else if (c->specialised) step_kernel<T, true, true><<<g, kBlock, dyn, st>>>(c->C, c->B, io);           \
+    else step_kernel<T, false, true><<<g, kBlock, dyn, st>>>(c->C, c->B, io);                              \
+  } while (0)
+  switch (c->task) {
+    case 1: SO100_LAUNCH(1); break;
+    case 2: SO100_LAUNCH(2); break;
+    case 6: SO100_LAUNCH(6); break;
+    default: SO100_LAUNCH(5); break;
   }
 #undef SO100_LAUNCH
   c->launches++;
@@ -1182,20 +1352,11 @@ int so100_step_substeps(so100_ctx* c, const float* ctrl_dev, int n_substeps, voi
   cudaStream_t st = (cudaStream_t)stream;
   const int g = grid_for(c->n);
 #define SO100_SUBSTEPS(T, S) substeps_kernel<T, S><<<g, kBlock, 0, st>>>(c->C, c->B, ctrl_dev, n_substeps)
-  if (c->specialised) {
-    switch (c->task) {
-      case 1: SO100_SUBSTEPS(1, true); break;
-      case 2: SO100_SUBSTEPS(2, true); break;
-      case 6: SO100_SUBSTEPS(6, true); break;
-      default: SO100_SUBSTEPS(5, true); break;
-    }
-  } else {
-    switch (c->task) {
-      case 1: SO100_SUBSTEPS(1, false); break;
-      case 2: SO100_SUBSTEPS(2, false); break;
-      case 6: SO100_SUBSTEPS(6, false); break;
-      default: SO100_SUBSTEPS(5, false); break;
-    }
+  switch (c->task) {  // a debug entry: always the generic recursion (the same mathematics; csrc/so100_dyn.cuh)
+    case 1: SO100_SUBSTEPS(1, false); break;
+    case 2: SO100_SUBSTEPS(2, false); break;
+    case 6: SO100_SUBSTEPS(6, false); break;
+    default: SO100_SUBSTEPS(5, false); break;
   }
 #undef SO100_SUBSTEPS
   mark_caller_stream_work(c);
@@ -1539,10 +1700,9 @@ int so100_host_forward(const so100_model* m, int n, const double* qpos, const do
         ContactIO<float> cio;
         for (int j = 0; j < SO_NJ; j++) { cio.s[j] = s[j]; cio.c[j] = c[j]; cio.q[j] = q[j]; cio.qc[j] = 0; cio.qd[j] = v[j]; cio.b[j] = b[j]; cio.a[j] = 0; }
         memcpy(cio.M, M, sizeof M);
-        st = contact_solve<float>(Cf.dyn, Cf.kin, Cf.pad, Cf.con, cio);
+        st = contact_solve<float>(Cf.dyn, Cf.kin, Cf.pad, Cf.con, cio, ~0u);
         memcpy(a, cio.a, sizeof a);
       } else solve_qacc<float>(Cf.con, M, b, q, zc, v, a, sweeps > 0 ? sweeps : 1);
-      if (getenv("SO100_DEBUG_CONTACT")) fprintf(stderr, "sample %d: contact_solve<float> status %d\n", i, st);
       if (M_out) for (int k = 0; k < 21; k++) M_out[21 * i + k] = M[k];
       if (bias_out) for (int j = 0; j < SO_NJ; j++) bias_out[6 * i + j] = bias[j];
       if (qacc_out) for (int j = 0; j < SO_NJ; j++) qacc_out[6 * i + j] = a[j];
@@ -1565,8 +1725,7 @@ int so100_host_forward(const so100_model* m, int n, const double* qpos, const do
       ContactIO<double> cio;
       for (int j = 0; j < SO_NJ; j++) { cio.s[j] = s[j]; cio.c[j] = c[j]; cio.q[j] = q[j]; cio.qc[j] = 0; cio.qd[j] = v[j]; cio.b[j] = b[j]; cio.a[j] = 0; }
       memcpy(cio.M, M, sizeof M);
-      const int st = contact_solve<double>(H.dyn, H.kin, H.pad, H.con, cio);
-      if (getenv("SO100_DEBUG_CONTACT")) fprintf(stderr, "sample %d: contact_solve status %d\n", i, st);
+      contact_solve<double>(H.dyn, H.kin, H.pad, H.con, cio, ~0u);
       memcpy(a, cio.a, sizeof a);
     } else solve_qacc<double>(H.con, M, b, q, zc, v, a, sweeps > 0 ? sweeps : 1);
     if (M_out) memcpy(M_out + 21 * i, M, sizeof M);
@@ -1579,6 +1738,32 @@ int so100_host_forward(const so100_model* m, int n, const double* qpos, const do
       memcpy(kin_out + 18 * i + 6, ko.cam_pos, 24); memcpy(kin_out + 18 * i + 9, ko.cam_R, 72);
     }
   }
+  return SO100_OK;
+}
+
+int so100_host_substeps(const so100_model* m, int n, double* qpos, double* qvel, double* qacc_warm, const double* ctrl, int n_substeps,
+                        int variant, int64_t* stats) {
+  if (!m || n <= 0 || !qpos || !qvel || !qacc_warm || !ctrl || n_substeps <= 0) return fail(SO100_ERR_ARG, "bad argument");
+  if (m->struct_size != (int)sizeof(so100_model)) return fail(SO100_ERR_ARG, "so100_model.struct_size mismatch");
+  if (variant != 0 && variant != 2 && variant != 3) return fail(SO100_ERR_ARG, "variant must be 0 (fp64), 2 (fp32) or 3 (fp32, MUFU-class sin/cos)");
+  HostModel H;
+  int rc = build_host_model(*m, H);
+  if (rc) return rc;
+  if (stats) memset(stats, 0, 5 * sizeof(int64_t));
+  static Consts Cf;
+  memset(&Cf, 0, sizeof Cf);
+  physics_constants_f32(H, Cf);
+  ActC<float> Af;
+  BlkC<float> Bk;
+  solver_constants_f32(*m, H, Cf.con, Af, Bk);
+  if (variant >= 2) { host_substeps_t<float>(Cf.dyn, Cf.kin, Cf.pad, Cf.con, Af, n, qpos, qvel, qacc_warm, ctrl, n_substeps, stats, variant == 3); return SO100_OK; }
+  ActC<double> Ad;
+  for (int j = 0; j < SO_NJ; j++) {
+    Ad.kp[j] = m->act_kp[j]; Ad.kv[j] = H.kv[j]; Ad.ctrl_lo[j] = m->act_ctrlrange[j][0]; Ad.ctrl_hi[j] = m->act_ctrlrange[j][1];
+    Ad.frc_lo[j] = m->act_forcerange[j][0]; Ad.frc_hi[j] = m->act_forcerange[j][1];
+  }
+  Ad.h = m->timestep;
+  host_substeps_t<double>(H.dyn, H.kin, H.pad, H.con, Ad, n, qpos, qvel, qacc_warm, ctrl, n_substeps, stats);
   return SO100_OK;
 }
 

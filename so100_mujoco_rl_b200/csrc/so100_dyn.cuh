@@ -372,10 +372,8 @@ SO_HD T solve_qacc(const ConC<T>& K, const T* M, const T* b, const T* q, const T
       dl[j] = (sDl[j] < T(0) ? -sDl[j] : sDl[j]) * (xl[j] - af[j]);  // t with the limit row active = t + Dl (xl - af)
     }
   }
-  T last = T(0), amax = T(1);
-#pragma unroll
-  for (int j = 0; j < SO_NJ; j++) { T ax = a[j] < T(0) ? -a[j] : a[j]; amax = ax > amax ? ax : amax; }
-  const T tol = T(1e-3) * amax;  // scale from the warm start
+  T last = T(0), amax = T(1);  // amax: scale of the iterate, refreshed by every tracked sweep (a warm start left by a
+                               // contact solve can be 100x the contact-free solution)
   // one Gauss-Seidel sweep; TRACK: also return the largest coordinate update
   auto sweep = [&](auto track) -> T {
     constexpr bool TRACK = decltype(track)::value;
@@ -402,6 +400,8 @@ SO_HD T solve_qacc(const ConC<T>& K, const T* M, const T* b, const T* q, const T
         T d = x - a[j];
         d = d < T(0) ? -d : d;
         big = d > big ? d : big;
+        const T ax = x < T(0) ? -x : x;
+        amax = ax > amax ? ax : amax;
       }
       a[j] = x;
     }
@@ -413,8 +413,9 @@ SO_HD T solve_qacc(const ConC<T>& K, const T* M, const T* b, const T* q, const T
   for (int sw = 0; sw < sweeps - 1; sw++) sweep(SoFalse());
 #pragma unroll 1
   for (int sw = 0; sw < 7; sw++) {
+    amax = T(1);
     last = sweep(SoTrue());
-    if (!(last > tol)) break;
+    if (!(last > T(1e-3) * amax)) break;
   }
   return last;
 }
@@ -484,13 +485,15 @@ SO_HD void task_kinematics(const DynC<T>& C, const KinC<T>& Kc, const T* s, cons
 // ---------------------------------------------------------------------------------------------------------------
 // Arm <-> floor contact: the jaws' primitive box colliders ("pads", so_arm100_camera.xml:60-61, :108-111, :120-123 of
 // the reference) against the floor plane z = 0 (env01.xml:39).  MuJoCo semantics (mjc_PlaneBox, mj_instantiateContact,
-// mj_makeImpedance; DESIGN.md "Arm-floor contact"): every box corner below the plane is a contact with condim 3 and a pyramidal cone, i.e.
-// four unilateral rows  J_n +- mu J_t1, J_n +- mu J_t2  with dense Jacobians, aref = -B (J qd) - K imp(dist) dist and
-// R = (1 - imp)/imp * 2 mu^2 (1 + mu^2) body_invweight0.  The rows couple all joints with stiffness ~3e3 against an
-// inertia of ~0.1, which is what Newton's method is for: the per-dof Gauss-Seidel of solve_qacc stays the path of envs
-// that touch nothing, envs with a penetrating corner take contact_solve() instead.
+// mj_makeImpedance; DESIGN.md "Arm-floor contact"): every box corner below the plane is a contact with condim 3 and a
+// pyramidal cone, i.e. four unilateral rows  J_n +- mu J_t1, J_n +- mu J_t2  with dense Jacobians,
+// aref = -B (J qd) - K imp(dist) dist  and  R = (1 - imp)/imp * 2 mu^2 (1 + mu^2) body_invweight0.  The rows couple all
+// joints with a stiffness of ~3e3 against an inertia of ~0.1, which is what Newton's method is for: the per-dof
+// Gauss-Seidel of solve_qacc stays the path of envs that touch nothing, envs with a penetrating corner take
+// contact_solve() instead.
 #define SO_MAX_PAD 8
-#define SO_MAX_CON (4 * SO_MAX_PAD)
+#define SO_MAX_CON 16  // contacts the out-of-line solve keeps (4 per pad possible; > 4 at once is 0.3 % of the touching envs, > 8 unseen)
+#define SO_FAST_CON 8  // ... and a slot of the device's shared-memory pool
 
 template <typename T>
 struct PadC {
@@ -505,11 +508,11 @@ struct PadC {
 
 // Broad phase, every substep, every env: does ANY pad corner lie below the floor?  Only the z row of each link's world
 // rotation and the z of its origin are propagated (~16 operations per link), then per pad the height of its lowest
-// corner  cz - sum_m |w . A_m|.  Exact: true iff contact_solve would find at least one contact.
+// corner  cz - sum_m |w . A_m|.  Exact: bit k of the result is set iff contact_solve would find a contact on pad k.
 template <typename T>
-SO_HD bool pads_touch(const DynC<T>& C, const KinC<T>& Kc, const PadC<T>& P, const T* s, const T* c) {
+SO_HD unsigned pads_touch(const DynC<T>& C, const KinC<T>& Kc, const PadC<T>& P, const T* s, const T* c, T margin = T(0)) {
   T w0 = Kc.base_R[6], w1 = Kc.base_R[7], w2 = Kc.base_R[8], oz = Kc.base_p[2];
-  bool touch = false;
+  unsigned touch = 0u;
 #pragma unroll
   for (int i = 0; i < SO_NJ; i++) {
     const LinkC<T>& L = C.L[i];
@@ -525,35 +528,57 @@ SO_HD bool pads_touch(const DynC<T>& C, const KinC<T>& Kc, const PadC<T>& P, con
         const T u = w0 * P.A[k][m] + w1 * P.A[k][3 + m] + w2 * P.A[k][6 + m];
         ext += u < T(0) ? -u : u;
       }
-      touch = touch || (cz - ext < T(0));
+      touch |= (cz - ext < margin) ? (1u << k) : 0u;
     }
   }
   return touch;
 }
 
-template <typename T>
-struct ContactIO {  // what the contact path needs from the substep, copied once at the call site (keeps the hot path's arrays in registers)
-  T s[SO_NJ], c[SO_NJ], q[SO_NJ], qc[SO_NJ], qd[SO_NJ], M[21], b[SO_NJ];
-  T a[SO_NJ];       // in: warm start (previous qacc); out: qacc
+// ---- storage of one contact solve.  The solve keeps, per contact, its three Jacobian rows (float), four parameters
+// (c0, b_y, b_x, D: float), six residual / slope values for the line search (double), and the 6x6 Hessian (double).
+// Two homes: the thread's local memory (host, and the device fallback), or a slot of a shared-memory pool laid out
+// [word][slot] so that the lanes of a warp hit different banks (the device's normal case: local memory would put a
+// ~300-cycle L2 round trip behind every dependent access of a chain that is thousands of instructions long).
+template <typename TC, int NC>
+struct ContactLocal {
+  static constexpr int kMaxCon = NC;
+  TC jf[NC * 18], pf[NC * 4];
+  double rd[NC * 6], hd[21];
+  SO_HD TC& J(int c, int axis, int j) { return jf[(c * 3 + axis) * 6 + j]; }
+  SO_HD TC& par(int c, int m) { return pf[c * 4 + m]; }
+  SO_HD double& res(int c, int m) { return rd[c * 6 + m]; }
+  SO_HD double& H(int k) { return hd[k]; }
+};
+template <int NC>
+struct ContactShared {  // device only: f = float words, d = double words of the pool, this lane's slot already added
+  static constexpr int kMaxCon = NC;
+  static constexpr int kFloats = NC * 22, kDoubles = NC * 6 + 21;
+  float* f;
+  double* d;
+  int stride;
+  SO_HD float& J(int c, int axis, int j) { return f[((c * 3 + axis) * 6 + j) * stride]; }
+  SO_HD float& par(int c, int m) { return f[(NC * 18 + c * 4 + m) * stride]; }
+  SO_HD double& res(int c, int m) { return d[(c * 6 + m) * stride]; }
+  SO_HD double& H(int k) { return d[(NC * 6 + k) * stride]; }
 };
 
-// In-place Cholesky of a packed lower-triangular 6x6 SPD matrix, then solve H x = r.  Returns false if not positive definite.
-template <typename T>
-SO_HD bool chol_solve6(T* H, const T* r, T* x) {
+// In-place Cholesky of the packed lower-triangular 6x6 SPD matrix held by the store, then solve H x = r.
+template <typename T, typename Store>
+SO_HD bool chol_solve6(Store& S, const T* r, T* x) {
 #pragma unroll
   for (int j = 0; j < SO_NJ; j++) {
-    T d = H[midx(j, j)];
+    T d = S.H(midx(j, j));
 #pragma unroll
-    for (int k = 0; k < j; k++) d -= H[midx(j, k)] * H[midx(j, k)];
+    for (int k = 0; k < j; k++) { const T l = S.H(midx(j, k)); d -= l * l; }
     if (!(d > T(0))) return false;
     const T rd = so_rsqrt(d);
-    H[midx(j, j)] = rd;  // the diagonal holds 1 / L_jj
+    S.H(midx(j, j)) = rd;  // the diagonal holds 1 / L_jj
 #pragma unroll
     for (int i = j + 1; i < SO_NJ; i++) {
-      T v = H[midx(i, j)];
+      T v = S.H(midx(i, j));
 #pragma unroll
-      for (int k = 0; k < j; k++) v -= H[midx(i, k)] * H[midx(j, k)];
-      H[midx(i, j)] = v * rd;
+      for (int k = 0; k < j; k++) v -= S.H(midx(i, k)) * S.H(midx(j, k));
+      S.H(midx(i, j)) = v * rd;
     }
   }
   T y[SO_NJ];
@@ -561,15 +586,15 @@ SO_HD bool chol_solve6(T* H, const T* r, T* x) {
   for (int i = 0; i < SO_NJ; i++) {
     T v = r[i];
 #pragma unroll
-    for (int k = 0; k < i; k++) v -= H[midx(i, k)] * y[k];
-    y[i] = v * H[midx(i, i)];
+    for (int k = 0; k < i; k++) v -= S.H(midx(i, k)) * y[k];
+    y[i] = v * S.H(midx(i, i));
   }
 #pragma unroll
   for (int i = SO_NJ - 1; i >= 0; i--) {
     T v = y[i];
 #pragma unroll
-    for (int k = i + 1; k < SO_NJ; k++) v -= H[midx(k, i)] * x[k];
-    x[i] = v * H[midx(i, i)];
+    for (int k = i + 1; k < SO_NJ; k++) v -= S.H(midx(k, i)) * x[k];
+    x[i] = v * S.H(midx(i, i));
   }
   return true;
 }
@@ -579,135 +604,143 @@ SO_HD bool chol_solve6(T* H, const T* r, T* x) {
 // with the exact generalised Hessian, a Cholesky solve per iteration, and an exact line search: phi'(alpha) along the
 // Newton direction is piecewise linear and increasing, and it is evaluated from stored row residuals and slopes (no
 // Jacobians), so a safeguarded Newton iteration on it costs a few operations per row.  If no row switched state along
-// the step, the step ended on the minimiser of the quadratic piece it started in and the solve is finished; with the
-// warm start of the previous substep that is the common case: one evaluation, one Cholesky solve.
-// Returns the number of gradient/Hessian evaluations, negated if the iteration cap was hit or the Hessian was not
-// positive definite.
-template <typename T>
-SO_NOINLINE int contact_solve(const DynC<T>& C, const KinC<T>& Kc, const PadC<T>& P, const ConC<T>& K, ContactIO<T>& io) {
-  const T* s = io.s;
-  const T* c = io.c;
-  // ---- world kinematics: joint axes (local +z of each link), link origins; contacts of the pads on the way
-  T zax[SO_NJ][3], org[SO_NJ][3];
-  T cpos[SO_MAX_CON][3], cc0[SO_MAX_CON], cbx[SO_MAX_CON], cby[SO_MAX_CON], cD[SO_MAX_CON];
-  int cnj[SO_MAX_CON], nc = 0;
+// the step, the step ended on the minimiser of the quadratic piece it started in and the solve is finished.
+//
+// Two number types.  TC is the kernel's own (float on the device): constants, the substep's inputs, the contact geometry
+// and Jacobians.  The SOLVE (residuals, gradient, Hessian, Cholesky, line search) runs in double: the Hessian
+// M + sum D J J' mixes a stiffness of ~250 with an inertia of 0.1, so a float solve leaves ~1e-3 of every step in the
+// soft directions; measured on 1 024 envs x 16 steps against the fp64 oracle (tools/contact_precision.py): float solve
+// p99.9 |dq| 5.7e-4 rad, double solve 2.7e-7.  B200 issues DFMA at half the FFMA rate.
+//
+// s, c must be ACCURATE sin / cos of the joint angles (not MUFU's): a resting contact penetrates ~2e-7 m.
+// Returns the number of gradient/Hessian evaluations (0: no corner is below the floor), negated if the iteration cap
+// was hit or the Hessian was not positive definite; *overflow is set if more than Store::kMaxCon corners penetrated
+// (the solve is then not attempted with this store: the caller retries with a larger one).
+template <typename TC, typename Store>
+SO_HD int contact_newton(const DynC<TC>& C, const KinC<TC>& Kc, const PadC<TC>& P, const ConC<TC>& K, Store& S, const TC* s, const TC* c,
+                         const TC* q, const TC* qc, const TC* qd, const TC* M, const TC* b, TC* a, unsigned pad_mask, bool exact_in,
+                         int* overflow, int* ls_evals) {
+  typedef double T;
+  constexpr int NC = Store::kMaxCon;
+  int nc = 0;
   {
-    T W[9], o[3];
+    // ---- world kinematics: joint axes (local +z of each link), link origins; contacts of the pads on the way
+    TC zax[SO_NJ][3], org[SO_NJ][3], W[9], o[3];
 #pragma unroll
     for (int k = 0; k < 9; k++) W[k] = Kc.base_R[k];
 #pragma unroll
     for (int k = 0; k < 3; k++) o[k] = Kc.base_p[k];
 #pragma unroll
     for (int i = 0; i < SO_NJ; i++) {
-      const LinkC<T>& L = C.L[i];
-      T t[3];
+      const LinkC<TC>& L = C.L[i];
+      TC t[3];
       mat_vec(W, L.p, t);
       o[0] += t[0]; o[1] += t[1]; o[2] += t[2];
       mat_mul(W, L.R, W);
 #pragma unroll
       for (int r = 0; r < 3; r++) {  // W <- W * Rz(q_i)
-        const T x = W[3 * r], y = W[3 * r + 1];
+        const TC x = W[3 * r], y = W[3 * r + 1];
         W[3 * r] = c[i] * x + s[i] * y;
         W[3 * r + 1] = c[i] * y - s[i] * x;
       }
 #pragma unroll
       for (int k = 0; k < 3; k++) { zax[i][k] = W[3 * k + 2]; org[i][k] = o[k]; }
       for (int k = P.first[i]; k < P.first[i + 1]; k++) {
-        T cw[3], h[3][3];  // box centre and half-extent vectors in the world
+        if (!(pad_mask >> k & 1u)) continue;  // the broad phase saw this pad's lowest corner above the floor
+        TC cw[3], h[3][3];  // box centre and half-extent vectors in the world
         mat_vec(W, P.p[k], cw);
         cw[0] += o[0]; cw[1] += o[1]; cw[2] += o[2];
 #pragma unroll
         for (int m = 0; m < 3; m++) {
-          const T v[3] = {P.A[k][m], P.A[k][3 + m], P.A[k][6 + m]};
+          const TC v[3] = {P.A[k][m], P.A[k][3 + m], P.A[k][6 + m]};
           mat_vec(W, v, h[m]);
         }
         int found = 0;
         for (int ci = 0; ci < 8 && found < 4; ci++) {  // MuJoCo mjc_PlaneBox: corners in index order, at most 4
-          const T s0 = (ci & 1) ? T(1) : T(-1), s1 = (ci & 2) ? T(1) : T(-1), s2 = (ci & 4) ? T(1) : T(-1);
-          const T ld = s0 * h[0][2] + s1 * h[1][2] + s2 * h[2][2];
-          const T dist = cw[2] + ld;
-          if (dist > T(0) || ld > T(0)) continue;
+          const TC s0 = (ci & 1) ? TC(1) : TC(-1), s1 = (ci & 2) ? TC(1) : TC(-1), s2 = (ci & 4) ? TC(1) : TC(-1);
+          const TC ld = s0 * h[0][2] + s1 * h[1][2] + s2 * h[2][2];
+          const TC dist = cw[2] + ld;
+          if (dist > TC(0) || ld > TC(0)) continue;
           found++;
-          if (!(dist < T(0)) || nc >= SO_MAX_CON) continue;  // in the gap: detected, not instantiated
-          cpos[nc][0] = cw[0] + s0 * h[0][0] + s1 * h[1][0] + s2 * h[2][0];
-          cpos[nc][1] = cw[1] + s0 * h[0][1] + s1 * h[1][1] + s2 * h[2][1];
-          cpos[nc][2] = T(0.5) * dist;  // corner - n dist / 2
-          const T imp = impedance_f(P.imp0, P.imp1, P.imp_w, P.imp_rw, P.imp_mid, P.imp_rmid, P.imp_r1mid, P.imp_pow, dist);
-          T R = (T(1) - imp) * P.diag[k] / imp;
-          R = R < T(1e-15) ? T(1e-15) : R;
-          cD[nc] = T(1) / R;
-          cc0[nc] = -P.K * imp * dist;  // completed with the velocity terms below
-          cnj[nc] = i + 1;
+          if (!(dist < TC(0))) continue;  // in the gap: detected, not instantiated
+          if (nc >= NC) { *overflow = 1; return 0; }
+          const TC px = cw[0] + s0 * h[0][0] + s1 * h[1][0] + s2 * h[2][0], py = cw[1] + s0 * h[0][1] + s1 * h[1][1] + s2 * h[2][1],
+                   pz = TC(0.5) * dist;  // corner - n dist / 2
+          // point Jacobian, columns j <= i:  z_j x (pos - o_j);  velocity of the point
+          TC vx = TC(0), vy = TC(0), vz = TC(0);
+#pragma unroll
+          for (int j = 0; j < SO_NJ; j++) {
+            const bool on = j <= i;
+            const TC dx = px - org[j][0], dy = py - org[j][1], dz = pz - org[j][2];
+            const TC jx = on ? zax[j][1] * dz - zax[j][2] * dy : TC(0), jy = on ? zax[j][2] * dx - zax[j][0] * dz : TC(0),
+                     jz = on ? zax[j][0] * dy - zax[j][1] * dx : TC(0);
+            S.J(nc, 0, j) = jz; S.J(nc, 1, j) = jy; S.J(nc, 2, j) = jx;
+            vx += jx * qd[j]; vy += jy * qd[j]; vz += jz * qd[j];
+          }
+          const TC imp = impedance_f(P.imp0, P.imp1, P.imp_w, P.imp_rw, P.imp_mid, P.imp_rmid, P.imp_r1mid, P.imp_pow, dist);
+          TC R = (TC(1) - imp) * P.diag[k] / imp;
+          R = R < TC(1e-15) ? TC(1e-15) : R;
+          // aref of row (sigma, t) = c0 - sigma b_t,  c0 = -B vz - K imp dist,  b_t = B mu v_t
+          S.par(nc, 0) = -P.K * imp * dist - P.B * vz;
+          S.par(nc, 1) = P.B * P.mu * vy;
+          S.par(nc, 2) = P.B * P.mu * vx;
+          S.par(nc, 3) = TC(1) / R;
           nc++;
         }
       }
     }
   }
   if (nc == 0) return 0;
-  // point Jacobian of contact k, columns j < cnj[k]:  z_j x (pos - o_j)
-  auto jac = [&](int k, T* Jx, T* Jy, T* Jz) {
-#pragma unroll
-    for (int j = 0; j < SO_NJ; j++) {
-      const T dx = cpos[k][0] - org[j][0], dy = cpos[k][1] - org[j][1], dz = cpos[k][2] - org[j][2];
-      const bool on = j < cnj[k];
-      Jx[j] = on ? zax[j][1] * dz - zax[j][2] * dy : T(0);
-      Jy[j] = on ? zax[j][2] * dx - zax[j][0] * dz : T(0);
-      Jz[j] = on ? zax[j][0] * dy - zax[j][1] * dx : T(0);
-    }
-  };
-  for (int k = 0; k < nc; k++) {  // aref of row (sigma, t) = c0 - sigma b_t,  c0 = -B vz - K imp dist,  b_t = B mu v_t
-    T Jx[SO_NJ], Jy[SO_NJ], Jz[SO_NJ], vx = T(0), vy = T(0), vz = T(0);
-    jac(k, Jx, Jy, Jz);
-#pragma unroll
-    for (int j = 0; j < SO_NJ; j++) { vx += Jx[j] * io.qd[j]; vy += Jy[j] * io.qd[j]; vz += Jz[j] * io.qd[j]; }
-    cc0[k] -= P.B * vz;
-    cbx[k] = P.B * P.mu * vx;
-    cby[k] = P.B * P.mu * vy;
-  }
+#if defined(SO100_CONTACT_EXP) && SO100_CONTACT_EXP == 1
+  return 1;
+#endif
   // per-dof rows (the ones solve_qacc handles): friction loss, and the limit row of a joint outside its range
-  T af[SO_NJ], xl[SO_NJ], sDl[SO_NJ];
+  TC af[SO_NJ], xl[SO_NJ], sDl[SO_NJ];
 #pragma unroll
   for (int j = 0; j < SO_NJ; j++) {
-    af[j] = -K.fr_B[j] * io.qd[j];
-    xl[j] = T(0); sDl[j] = T(0);
-    if ((io.q[j] - K.lo[j]) - io.qc[j] < T(0) || (K.hi[j] - io.q[j]) + io.qc[j] < T(0)) {
-      T rm2, kap2;
-      limit_row(K, j, io.M[midx(j, j)], io.q[j], io.qc[j], io.qd[j], xl[j], sDl[j], rm2, kap2);
+    af[j] = -K.fr_B[j] * qd[j];
+    xl[j] = TC(0); sDl[j] = TC(0);
+    if ((q[j] - K.lo[j]) - qc[j] < TC(0) || (K.hi[j] - q[j]) + qc[j] < TC(0)) {
+      TC rm2, kap2;
+      limit_row(K, j, M[midx(j, j)], q[j], qc[j], qd[j], xl[j], sDl[j], rm2, kap2);
     }
   }
-  // gradient and generalised Hessian (packed lower triangle) at x; the contact residuals (e, ty, tx) are kept for the
-  // line search: rows of contact k are  e + ty, e - ty, e + tx, e - tx, each active iff < 0
-  T ce[SO_MAX_CON], cty[SO_MAX_CON], ctx[SO_MAX_CON];
-  auto eval = [&](const T* x, T* g, T* H) {
+  const T mu = P.mu;
+  // gradient at x and generalised Hessian (into the store); the contact residuals (e, ty, tx) are kept for the line
+  // search: rows of contact k are  e + ty, e - ty, e + tx, e - tx, each active iff < 0
+  auto eval = [&](const T* x, T* g) {
 #pragma unroll
-    for (int k = 0; k < 21; k++) H[k] = io.M[k];
+    for (int k = 0; k < 21; k++) S.H(k) = (T)M[k];
 #pragma unroll
     for (int i = 0; i < SO_NJ; i++) {
-      T v = -io.b[i];
+      T v = -(T)b[i];
 #pragma unroll
-      for (int j = 0; j < SO_NJ; j++) v += (j <= i ? io.M[midx(i, j)] : io.M[midx(j, i)]) * x[j];
-      const T t = K.fr_D[i] * (x[i] - af[i]);  // Huber friction row: force -clamp(D r, +-loss)
-      if (t > -K.fr_loss[i] && t < K.fr_loss[i]) { v += t; H[midx(i, i)] += K.fr_D[i]; }
-      else v += t < T(0) ? -K.fr_loss[i] : K.fr_loss[i];
-      if (sDl[i] != T(0) && sDl[i] * (x[i] - xl[i]) < T(0)) {  // limit row active
-        const T Dl = sDl[i] < T(0) ? -sDl[i] : sDl[i];
-        v += Dl * (x[i] - xl[i]);
-        H[midx(i, i)] += Dl;
+      for (int j = 0; j < SO_NJ; j++) v += (T)(j <= i ? M[midx(i, j)] : M[midx(j, i)]) * x[j];
+      const T fD = K.fr_D[i], fL = K.fr_loss[i];
+      const T t = fD * (x[i] - (T)af[i]);  // Huber friction row: force -clamp(D r, +-loss)
+      if (t > -fL && t < fL) { v += t; S.H(midx(i, i)) += fD; }
+      else v += t < T(0) ? -fL : fL;
+      if (sDl[i] != TC(0) && (T)sDl[i] * (x[i] - (T)xl[i]) < T(0)) {  // limit row active
+        const T Dl = sDl[i] < TC(0) ? -(T)sDl[i] : (T)sDl[i];
+        v += Dl * (x[i] - (T)xl[i]);
+        S.H(midx(i, i)) += Dl;
       }
       g[i] = v;
     }
     for (int k = 0; k < nc; k++) {
-      T Jx[SO_NJ], Jy[SO_NJ], Jz[SO_NJ], jx = T(0), jy = T(0), jz = T(0);
-      jac(k, Jx, Jy, Jz);
+      T Jz[SO_NJ], Jy[SO_NJ], Jx[SO_NJ], jx = T(0), jy = T(0), jz = T(0);
 #pragma unroll
-      for (int j = 0; j < SO_NJ; j++) { jx += Jx[j] * x[j]; jy += Jy[j] * x[j]; jz += Jz[j] * x[j]; }
-      const T e = jz - cc0[k], ty = P.mu * jy + cby[k], tx = P.mu * jx + cbx[k];
-      ce[k] = e; cty[k] = ty; ctx[k] = tx;
+      for (int j = 0; j < SO_NJ; j++) {
+        Jz[j] = S.J(k, 0, j); Jy[j] = S.J(k, 1, j); Jx[j] = S.J(k, 2, j);
+        jz += Jz[j] * x[j]; jy += Jy[j] * x[j]; jx += Jx[j] * x[j];
+      }
+      const T e = jz - (T)S.par(k, 0), ty = mu * jy + (T)S.par(k, 1), tx = mu * jx + (T)S.par(k, 2);
+      S.res(k, 0) = e; S.res(k, 1) = ty; S.res(k, 2) = tx;
       const T r1 = e + ty, r2 = e - ty, r3 = e + tx, r4 = e - tx;
       const T a1 = r1 < T(0) ? T(1) : T(0), a2 = r2 < T(0) ? T(1) : T(0), a3 = r3 < T(0) ? T(1) : T(0), a4 = r4 < T(0) ? T(1) : T(0);
       const T nact = a1 + a2 + a3 + a4;
       if (nact == T(0)) continue;
-      const T D = cD[k], mu = P.mu;
+      const T D = S.par(k, 3);
       const T gz = D * (a1 * r1 + a2 * r2 + a3 * r3 + a4 * r4), gy = D * mu * (a1 * r1 - a2 * r2), gx = D * mu * (a3 * r3 - a4 * r4);
       const T hzz = D * nact, hzy = D * mu * (a1 - a2), hyy = D * mu * mu * (a1 + a2), hzx = D * mu * (a3 - a4), hxx = D * mu * mu * (a3 + a4);
 #pragma unroll
@@ -715,33 +748,33 @@ SO_NOINLINE int contact_solve(const DynC<T>& C, const KinC<T>& Kc, const PadC<T>
         g[i] += gz * Jz[i] + gy * Jy[i] + gx * Jx[i];
         const T uz = hzz * Jz[i] + hzy * Jy[i] + hzx * Jx[i], uy = hzy * Jz[i] + hyy * Jy[i], ux = hzx * Jz[i] + hxx * Jx[i];
 #pragma unroll
-        for (int j = 0; j <= i; j++) H[midx(i, j)] += uz * Jz[j] + uy * Jy[j] + ux * Jx[j];
+        for (int j = 0; j <= i; j++) S.H(midx(i, j)) += uz * Jz[j] + uy * Jy[j] + ux * Jx[j];
       }
     }
   };
-  const T tol = sizeof(T) == 8 ? T(1e-13) : T(1e-4);    // relative size of the last Newton step (quadratic convergence: the error is its square)
-  const T lstol = sizeof(T) == 8 ? T(1e-12) : T(1e-5);  // |phi'(alpha)| / |phi'(0)| at which the line search stops
-  T x[SO_NJ], g[SO_NJ], H[21];
+  const T tol = exact_in ? T(1e-13) : T(1e-9);    // relative size of the last Newton step (fp32 inputs: no point below 1e-9)
+  const T lstol = exact_in ? T(1e-12) : T(1e-8);  // |phi'(alpha)| / |phi'(0)| at which the line search stops
+  const T atol = exact_in ? T(1e-14) : T(1e-10);  // ... or when its Newton iteration on alpha no longer moves
+  T x[SO_NJ], g[SO_NJ];
 #pragma unroll
-  for (int j = 0; j < SO_NJ; j++) x[j] = io.a[j];
-  int evals = 0;
+  for (int j = 0; j < SO_NJ; j++) x[j] = a[j];
+  int evals = 0, nls = 0;
   bool ok = false;
-  for (int it = 0; it < 40 && !ok; it++) {
-    eval(x, g, H);
+  for (int it = 0; it < 30 && !ok; it++) {
+    eval(x, g);
     evals++;
-    T p[SO_NJ], ng[SO_NJ], Mp[SO_NJ], d0 = T(0), pMp = T(0), ds = T(0), pmax = T(0), xmax = T(1);
+    T p[SO_NJ], ng[SO_NJ], d0 = T(0), pMp = T(0), ds = T(0), pmax = T(0), xmax = T(1);
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) ng[j] = -g[j];
-    if (!chol_solve6(H, ng, p)) { evals = -evals; break; }
+    if (!chol_solve6<T>(S, ng, p)) { evals = -evals; break; }
 #pragma unroll
     for (int i = 0; i < SO_NJ; i++) {
-      T v = T(0), w = -io.b[i];
+      T v = T(0), w = -(T)b[i];
 #pragma unroll
       for (int j = 0; j < SO_NJ; j++) {
-        const T mij = j <= i ? io.M[midx(i, j)] : io.M[midx(j, i)];
+        const T mij = j <= i ? M[midx(i, j)] : M[midx(j, i)];
         v += mij * p[j]; w += mij * x[j];
       }
-      Mp[i] = v;
       pMp += p[i] * v;
       ds += w * p[i];  // smooth part of phi'(0)
       d0 += g[i] * p[i];
@@ -749,14 +782,15 @@ SO_NOINLINE int contact_solve(const DynC<T>& C, const KinC<T>& Kc, const PadC<T>
       pmax = ap > pmax ? ap : pmax; xmax = ax > xmax ? ax : xmax;
     }
     if (!(d0 < T(0))) { ok = true; break; }  // stationary to rounding
-    // slopes of the contact residuals along p
-    T se[SO_MAX_CON], sty[SO_MAX_CON], stx[SO_MAX_CON];
-    for (int k = 0; k < nc; k++) {
-      T Jx[SO_NJ], Jy[SO_NJ], Jz[SO_NJ], jx = T(0), jy = T(0), jz = T(0);
-      jac(k, Jx, Jy, Jz);
+#if defined(SO100_CONTACT_EXP) && SO100_CONTACT_EXP == 2
+    for (int j = 0; j < SO_NJ; j++) x[j] += p[j];
+    ok = true; break;
+#endif
+    for (int k = 0; k < nc; k++) {  // slopes of the contact residuals along p
+      T jx = T(0), jy = T(0), jz = T(0);
 #pragma unroll
-      for (int j = 0; j < SO_NJ; j++) { jx += Jx[j] * p[j]; jy += Jy[j] * p[j]; jz += Jz[j] * p[j]; }
-      se[k] = jz; sty[k] = P.mu * jy; stx[k] = P.mu * jx;
+      for (int j = 0; j < SO_NJ; j++) { jz += (T)S.J(k, 0, j) * p[j]; jy += (T)S.J(k, 1, j) * p[j]; jx += (T)S.J(k, 2, j) * p[j]; }
+      S.res(k, 3) = jz; S.res(k, 4) = mu * jy; S.res(k, 5) = mu * jx;
     }
     // phi'(alpha) and phi''(alpha): phi' is piecewise linear and increasing, so Newton on it is exact within a piece.
     // `same` reports whether every row is in the state it had at alpha = 0.
@@ -765,26 +799,29 @@ SO_NOINLINE int contact_solve(const DynC<T>& C, const KinC<T>& Kc, const PadC<T>
       same = true;
 #pragma unroll
       for (int j = 0; j < SO_NJ; j++) {
-        const T r0 = x[j] - af[j], t0 = K.fr_D[j] * r0, t = K.fr_D[j] * (r0 + al * p[j]);
-        const bool q0 = t0 > -K.fr_loss[j] && t0 < K.fr_loss[j], q1 = t > -K.fr_loss[j] && t < K.fr_loss[j];
-        if (q1) { d += t * p[j]; cv += K.fr_D[j] * p[j] * p[j]; }
-        else d += (t < T(0) ? -K.fr_loss[j] : K.fr_loss[j]) * p[j];
+        const T fD = K.fr_D[j], fL = K.fr_loss[j];
+        const T r0 = x[j] - (T)af[j], t0 = fD * r0, t = fD * (r0 + al * p[j]);
+        const bool q0 = t0 > -fL && t0 < fL, q1 = t > -fL && t < fL;
+        if (q1) { d += t * p[j]; cv += fD * p[j] * p[j]; }
+        else d += (t < T(0) ? -fL : fL) * p[j];
         same = same && (q0 == q1) && (q1 || ((t0 < T(0)) == (t < T(0))));
-        if (sDl[j] != T(0)) {
-          const T l0 = x[j] - xl[j], l1 = l0 + al * p[j];
-          const bool b0 = sDl[j] * l0 < T(0), b1 = sDl[j] * l1 < T(0);
-          if (b1) { const T Dl = sDl[j] < T(0) ? -sDl[j] : sDl[j]; d += Dl * l1 * p[j]; cv += Dl * p[j] * p[j]; }
+        if (sDl[j] != TC(0)) {
+          const T sd = sDl[j], l0 = x[j] - (T)xl[j], l1 = l0 + al * p[j];
+          const bool b0 = sd * l0 < T(0), b1 = sd * l1 < T(0);
+          if (b1) { const T Dl = sd < T(0) ? -sd : sd; d += Dl * l1 * p[j]; cv += Dl * p[j] * p[j]; }
           same = same && (b0 == b1);
         }
       }
       for (int k = 0; k < nc; k++) {
-        const T e = ce[k] + al * se[k], ty = cty[k] + al * sty[k], tx = ctx[k] + al * stx[k];
+        const T e0 = S.res(k, 0), ty0 = S.res(k, 1), tx0 = S.res(k, 2), se = S.res(k, 3), sty = S.res(k, 4), stx = S.res(k, 5);
+        const T e = e0 + al * se, ty = ty0 + al * sty, tx = tx0 + al * stx;
         const T r[4] = {e + ty, e - ty, e + tx, e - tx};
-        const T r00[4] = {ce[k] + cty[k], ce[k] - cty[k], ce[k] + ctx[k], ce[k] - ctx[k]};
-        const T sl[4] = {se[k] + sty[k], se[k] - sty[k], se[k] + stx[k], se[k] - stx[k]};
+        const T r00[4] = {e0 + ty0, e0 - ty0, e0 + tx0, e0 - tx0};
+        const T sl[4] = {se + sty, se - sty, se + stx, se - stx};
+        const T D = S.par(k, 3);
 #pragma unroll
         for (int m = 0; m < 4; m++) {
-          if (r[m] < T(0)) { d += cD[k] * r[m] * sl[m]; cv += cD[k] * sl[m] * sl[m]; }
+          if (r[m] < T(0)) { d += D * r[m] * sl[m]; cv += D * sl[m] * sl[m]; }
           same = same && ((r[m] < T(0)) == (r00[m] < T(0)));
         }
       }
@@ -793,25 +830,49 @@ SO_NOINLINE int contact_solve(const DynC<T>& C, const KinC<T>& Kc, const PadC<T>
     };
     T lo = T(0), dlo = d0, hi = T(-1), dhi = T(0), alpha = T(1);
     bool same = false;
-    for (int ls = 0; ls < 30; ls++) {
+    for (int ls = 0; ls < 24; ls++) {
       T cv;
       const T d = dphi(alpha, cv, same);
+      nls++;
       const T ad = d < T(0) ? -d : d;
       if (ad <= lstol * -d0) break;
       if (d < T(0)) { lo = alpha; dlo = d; } else { hi = alpha; dhi = d; }
       T an = alpha - d / cv;                                        // exact if no row switches in between
       const bool inside = an > lo && (hi < T(0) || an < hi);
       if (!inside) an = hi < T(0) ? T(2) * alpha : lo + (hi - lo) * (-dlo) / (dhi - dlo);
+      const T da = an - alpha;
       alpha = an;
+      if ((da < T(0) ? -da : da) <= atol * alpha) { dphi(alpha, cv, same); break; }
     }
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) x[j] += alpha * p[j];
     // the minimiser of the quadratic piece x started in, reached without any row switching state: done
     ok = same || alpha * pmax <= tol * xmax;
+#if defined(SO100_CONTACT_EXP) && SO100_CONTACT_EXP == 3
+    ok = true;
+#endif
   }
 #pragma unroll
-  for (int j = 0; j < SO_NJ; j++) io.a[j] = x[j];
+  for (int j = 0; j < SO_NJ; j++) a[j] = (TC)x[j];
+  if (ls_evals) *ls_evals = nls;
   if (evals > 0 && !ok) evals = -evals;
   return evals;
 }
 
+template <typename T>
+struct ContactIO {  // inputs / output of the out-of-line solve, copied once at the call site (keeps the hot path's arrays in registers)
+  T s[SO_NJ], c[SO_NJ], q[SO_NJ], qc[SO_NJ], qd[SO_NJ], M[21], b[SO_NJ];
+  T a[SO_NJ];       // in: warm start (previous qacc); out: qacc
+};
+
+// The solve with thread-local storage for up to SO_MAX_CON contacts, out of line: the host path, and on the device the
+// fallback of a lane that found no slot in the shared-memory pool or more corners than a slot holds.
+template <typename TC>
+SO_NOINLINE int contact_solve(const DynC<TC>& C, const KinC<TC>& Kc, const PadC<TC>& P, const ConC<TC>& K, ContactIO<TC>& io,
+                               unsigned pad_mask, int* overflow = nullptr, int* ls_evals = nullptr) {
+  ContactLocal<TC, SO_MAX_CON> S;
+  int over = 0;
+  const int st = contact_newton<TC>(C, Kc, P, K, S, io.s, io.c, io.q, io.qc, io.qd, io.M, io.b, io.a, pad_mask, sizeof(TC) == 8, &over, ls_evals);
+  if (over && overflow) *overflow = 1;
+  return over ? -1 : st;
+}

@@ -16,6 +16,7 @@ FLAG_FRESH_FK_ON_RESET = 1
 FLAG_CLIP_ACTIONS = 2
 FLAG_GENERIC_KERNEL = 4
 FLAG_STATIC_BLOCK = 8  # hold the Env01/02/06 block at its spawn pose (no gravity, no floor contact)
+FLAG_ARM_CONTACT = 16  # jaw-pad <-> floor contact (exact, opt-in: ~18x the step time; see include/so100_b200.h)
 
 JOINT_STEP_SCALE = 0.075  # envs/utils.py:9
 REST_POSITION = [0.0, -3.141, 3.117, 1.0, 0.0, 0.0]  # envs/utils.py:11

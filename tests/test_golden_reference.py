@@ -21,7 +21,7 @@ def load(task):
 def test_oracle_reproduces_reference_task_logic(task):
     g = load(task)
     steps, n = g["reward"].shape
-    o = make_oracle(task, n, seed=int(g["seed"]), max_episode_steps=int(g["max_episode_steps"]))
+    o = make_oracle(task, n, seed=int(g["seed"]), max_episode_steps=int(g["max_episode_steps"]), flags=16)   # FLAG_ARM_CONTACT: as generated
     assert np.array_equal(o.reset(), g["obs0"])
     nd = 0
     for t in range(steps):

@@ -15,7 +15,7 @@ def test_cuda_path_reproduces_reference_fixtures(task):
     from so100_mujoco_rl_b200.batched_env import BatchedSo100Env
     g = np.load(os.path.join(ROOT, "tests", "golden", f"ref_env0{task}.npz"))
     steps, n = g["reward"].shape
-    env = BatchedSo100Env(task, n, device=0, seed=int(g["seed"]), max_episode_steps=int(g["max_episode_steps"]))
+    env = BatchedSo100Env(task, n, device=0, seed=int(g["seed"]), max_episode_steps=int(g["max_episode_steps"]), flags=16)   # FLAG_ARM_CONTACT: as generated
     assert np.abs(env.reset().cpu().numpy() - g["obs0"]).max() < 1e-6
     flips = 0
     for t in range(steps):

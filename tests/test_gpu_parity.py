@@ -379,3 +379,55 @@ def test_parity_at_baseline_size(task):
     assert split <= (0 if task != 5 else 10)           # Env01/02 never terminate: their flags can only be TimeLimit's
     env.close()
 
+
+
+@pytest.mark.parametrize("task", [1, 2])
+def test_arm_floor_contact_parity(task):
+    """SO100_FLAG_ARM_CONTACT: the jaws' pad colliders against the floor (dense contact rows, Newton with a double solve in
+    the kernel's contact path) against the oracle's restatement of MuJoCo's plane-box contact, with half of the envs
+    DRIVEN into the floor (pitch pushed down on top of random actions) so that resting, sliding, make and break all occur.
+    Quantile form: envs that hit a make / break or stick / slip transition on the other side of a substep boundary in fp32
+    and fp64 part ways for good (Env01/02 close their loop on qpos), so they are counted, not bounded."""
+    from so100_mujoco_rl_b200.tasks import FLAG_ARM_CONTACT
+    n, steps, seed = 512, 120, 5
+    env = _gpu_env(task, n, seed=seed, flags=FLAG_ARM_CONTACT)
+    o = make_oracle(task, n, seed=seed, flags=FLAG_ARM_CONTACT)
+    assert np.abs(env.reset().cpu().numpy() - o.reset(nthreads=0)).max() < 1e-6
+    rng = np.random.default_rng(8)
+    dq, touching, below = [], 0, 0
+    for t in range(steps):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        a[: n // 2, 1] = np.clip(a[: n // 2, 1] + 0.6, -1, 1)          # Pitch: lowers the arm
+        r = env.step(torch.from_numpy(a).cuda())
+        oo, ro, to, co, *_ = o.step(a, nthreads=0)
+        assert (r.terminated.cpu().numpy() == to).all() and (r.truncated.cpu().numpy() == co).all()
+        st = env.get_state()
+        qg = st["qpos"].cpu().numpy().astype(np.float64) - st["qpos_comp"].cpu().numpy()
+        dq.append(np.abs(qg - o.get_state_soa()[0]).max(axis=0))
+        touching += int(((st["counters"][1] & 16) != 0).sum())
+        below += int((r.obs[:, 14] < 0).sum())
+    dq = np.array(dq)
+    rate = float((dq > TOL_Q).mean())
+    print(f"task {task} with arm-floor contact: {touching / (steps * n):.1%} of the (env, step) samples end touching the floor; "
+          f"|dq| median {np.median(dq):.2e} p99 {np.quantile(dq, 0.99):.2e} max {dq.max():.2e}; rate(|dq| > {TOL_Q:g}) {rate:.2e}")
+    assert touching > 0.1 * steps * n          # the contact path really ran
+    assert below == 0                          # the end-effector point never goes through the floor any more
+    assert np.median(dq) < 1e-6 and np.quantile(dq, 0.9) < 5e-6
+    assert rate < 0.05
+    s = env.stats()
+    assert s["nan_resets"] == 0 and s["solver_unconverged"] <= 5
+    env.close()
+
+
+def test_without_the_contact_flag_the_arm_passes_through_the_floor():
+    """Default flags = round-1 physics (documented deviation D2): same inputs, the end-effector point ends up below z = 0."""
+    n = 512
+    env = _gpu_env(1, n, seed=5)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    below = 0
+    for t in range(150):
+        a = torch.rand((n, 6), device="cuda", generator=g) * 2 - 1
+        a[: n // 2, 1] = torch.clamp(a[: n // 2, 1] + 0.6, -1, 1)
+        below += int((env.step(a).obs[:, 14] < 0).sum())
+    assert below > 0.05 * 150 * n

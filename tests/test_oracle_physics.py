@@ -255,3 +255,85 @@ def test_static_block_flag_restores_the_held_block(spec):
     o.reset()
     o.step(np.zeros((3, 6), dtype=np.float32))
     assert (o.gather("block")[:, 2] == 0.0).all() and (o.gather("block_vz") == 0.0).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# arm <-> floor contact: the jaws' primitive pad colliders (reference so_arm100_camera.xml:60-61, :108-111, :120-123)
+def _pad_corner_heights(o, spec, q):
+    """World z of all 64 pad-box corners at configuration q (from the oracle's own kinematics)."""
+    k = o.fk(q)
+    zs = []
+    for b, pos, size in zip(spec.pad_body, spec.pad_pos, spec.pad_size):
+        R, p = k["xmat"][b].reshape(3, 3), k["xpos"][b]
+        for i in range(8):
+            v = np.array([size[0] if i & 1 else -size[0], size[1] if i & 2 else -size[1], size[2] if i & 4 else -size[2]])
+            zs.append((p + R @ (pos + v))[2])
+    return np.array(zs)
+
+
+def test_pad_model_and_body_invweight(spec):
+    o = make_oracle(1, 1, flags=16)
+    assert len(spec.pad_body) == 8 and spec.pad_body == [4, 4, 4, 4, 5, 5, 5, 5]
+    assert np.allclose(spec.pad_solimp, [2, 1, 0.01, 0.5, 2]) and np.allclose(spec.pad_solref, [0.01, 1]) and spec.pad_friction == 1.0
+    w = o.body_invweight0()
+    # translational inverse inertia grows along the chain (longer lever arms over 0.1 of armature) and is ~1/kg at the jaws
+    assert (np.diff(w) > 0).all() and 0.5 < w[4] < 1.0 and 0.5 < w[5] < 1.2
+
+
+def test_contacts_are_the_pad_corners_below_the_floor(spec):
+    o = make_oracle(1, 1, flags=16)
+    rng = np.random.default_rng(5)
+    seen = 0
+    for _ in range(300):
+        q = rng.uniform(spec.jnt_range[:, 0], spec.jnt_range[:, 1])
+        pos, dist, body = o.contacts(q)
+        z = _pad_corner_heights(o, spec, q)
+        below = np.sort(z[z < 0])
+        # every contact is a penetrating corner (dist = its height, pos half way up to the plane), at most 4 per pad
+        assert len(dist) <= len(below) and len(dist) <= 32
+        assert all(np.abs(below - d).min() < 1e-12 for d in dist)
+        assert np.allclose(pos[:, 2], dist / 2) if len(dist) else True
+        assert set(body) <= {4, 5}
+        seen += len(dist) > 0
+    assert seen > 20
+    assert len(make_oracle(1, 1).contacts(q)[1]) == 0      # without SO100_FLAG_ARM_CONTACT the pads are ignored
+
+
+def test_arm_pushed_into_the_floor_rests_on_its_pads(spec):
+    """Servo targets 0.3 rad "below the floor": the arm comes to rest on the pads, micrometres deep (impedance 0.9999),
+    the contact forces only push (unilateral rows) and balance servo + gravity, and the end-effector point stays above
+    the plane - where without the pads it ends up centimetres below."""
+    o = make_oracle(1, 1, flags=16)
+    q = np.array([0.0, -1.0, 1.1, 1.3, 0.0, 0.3])            # jaw tip 2.5 cm above the floor
+    assert _pad_corner_heights(o, spec, q).min() > 0.005
+    ctrl = q.copy(); ctrl[1] += 0.3                        # pitch the arm down through the floor
+    qq, v, w = o.substeps(q, np.zeros(6), np.zeros(6), ctrl, 3000)
+    assert np.abs(v).max() < 2e-3                          # at rest up to a slow creep along the floor
+    zmin = _pad_corner_heights(o, spec, qq).min()
+    assert -2e-6 < zmin < 0                                # resting penetration ~1e-7 m
+    a, a_s, fc, it = o.forward(qq, v, ctrl, warm=w)
+    assert np.abs(a).max() < 0.1
+    M = o.mass_matrix(qq)
+    assert np.abs(M @ (a - a_s) - fc).max() < 1e-9        # constraint forces = what the solve added to the smooth dynamics
+    assert np.abs(fc).max() > 0.5                          # and they are substantial (N m): the floor carries the servo's push
+    free = make_oracle(1, 1)
+    qf, vf, _ = free.substeps(q, np.zeros(6), np.zeros(6), ctrl, 1500)
+    assert free.fk(qf)["end_pos"][2] < -0.01 < 0 < o.fk(qq)["end_pos"][2]
+
+
+def test_random_actions_no_longer_go_through_the_floor():
+    """VERDICT r1: without arm-floor contact the end-effector point is below z = 0 in 20-36 % of random-action steps;
+    with the pads it never is."""
+    n, steps = 128, 250
+    frac = {}
+    for flags in (0, 16):
+        o = make_oracle(1, n, seed=1, flags=flags)
+        o.reset()
+        rng = np.random.default_rng(0)
+        below = tot = 0
+        for t in range(steps):
+            obs, *_ = o.step(rng.uniform(-1, 1, (n, 6)).astype(np.float32), nthreads=0)
+            if t >= 5:
+                below += int((obs[:, 14] < 0).sum()); tot += n
+        frac[flags] = below / tot
+    assert frac[0] > 0.1 and frac[16] == 0.0

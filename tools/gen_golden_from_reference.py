@@ -35,10 +35,10 @@ sys.path.insert(0, ROOT)
 
 from oracle.pyoracle import Oracle, philox  # noqa: E402
 from so100_mujoco_rl_b200.model import BODY_NAMES, JOINT_NAMES, load_model, reference_scene_path  # noqa: E402
-from so100_mujoco_rl_b200.tasks import make_task_cfg  # noqa: E402
+from so100_mujoco_rl_b200.tasks import FLAG_ARM_CONTACT, make_task_cfg  # noqa: E402
 
 SPEC = load_model(reference_scene_path())
-PHYS = Oracle(SPEC.to_ctypes(), make_task_cfg(1, 1))
+PHYS = Oracle(SPEC.to_ctypes(), make_task_cfg(1, 1, flags=FLAG_ARM_CONTACT))  # the reference's scene: pads collide with the floor
 PREFIX = "so100_"
 
 # ----------------------------------------------------------------------------------------------- RNG bridge
