@@ -47,6 +47,10 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define SO100_SYNC 1   // __syncthreads() per substep: keeps a CTA's warps on the same stretch of straight-line code (i-cache)
 #endif
 constexpr int kBlock = SO100_BLOCK;  // threads per CTA, one env each
+#ifndef SO100_SWEEPS_FIRST
+#define SO100_SWEEPS_FIRST 5  // Gauss-Seidel sweeps scheduled on the first substep of an env step (ctrl has just jumped) ...
+#define SO100_SWEEPS_REST 3   // ... and on the other 15 (warm start within a few %); more follow per lane while a sweep still moves qacc by > 1e-3
+#endif
 #define SO100_TOUCH_MARGIN 2e-6f   // broad-phase margin [m] over the MUFU sin/cos error (see physics<>)
 constexpr int kMaxStart = SO100_MAX_START;
 constexpr int kSnap = 12, kAux = 24, kCnt = 4;
@@ -406,7 +410,7 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
         if (st < 0) d = 1e30f;  // iteration cap / indefinite Hessian: counted with the Gauss-Seidel's unconverged substeps
       }
     }
-    if (!solved) d = solve_qacc<float>(K, M, b, e.q, e.qc, e.v, e.w, sub == 0 ? 5 : 3);
+    if (!solved) d = solve_qacc<float>(K, M, b, e.q, e.qc, e.v, e.w, sub == 0 ? SO100_SWEEPS_FIRST : SO100_SWEEPS_REST);
     float amax = 1.0f;
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {
@@ -1075,7 +1079,8 @@ static void host_substeps_t(const DynC<T>& D, const KinC<T>& Kn, const PadC<T>& 
         }
       }
       if (!solved) {
-        const T dlast = solve_qacc<T>(K, M, b, q, qc, v, w, sub == 0 ? 5 : 3);
+        static const int sw0 = getenv("SO100_SWEEPS0") ? atoi(getenv("SO100_SWEEPS0")) : SO100_SWEEPS_FIRST, sw1 = getenv("SO100_SWEEPS1") ? atoi(getenv("SO100_SWEEPS1")) : SO100_SWEEPS_REST;
+        const T dlast = solve_qacc<T>(K, M, b, q, qc, v, w, sub == 0 ? sw0 : sw1);
         T amax = T(1);
         for (int j = 0; j < SO_NJ; j++) amax = std::fmax(amax, std::fabs(w[j]));
         if (stats && dlast > T(2e-3) * amax) stats[4] += 1;  // as physics<> counts Gauss-Seidel substeps that were still moving

@@ -410,7 +410,7 @@ def test_arm_floor_contact_parity(task):
     rate = float((dq > TOL_Q).mean())
     print(f"task {task} with arm-floor contact: {touching / (steps * n):.1%} of the (env, step) samples end touching the floor; "
           f"|dq| median {np.median(dq):.2e} p99 {np.quantile(dq, 0.99):.2e} max {dq.max():.2e}; rate(|dq| > {TOL_Q:g}) {rate:.2e}")
-    assert touching > 0.1 * steps * n          # the contact path really ran
+    assert touching > 0.05 * steps * n         # the contact path really ran
     assert below == 0                          # the end-effector point never goes through the floor any more
     assert np.median(dq) < 1e-6 and np.quantile(dq, 0.9) < 5e-6
     assert rate < 0.05
