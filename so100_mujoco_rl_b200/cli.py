@@ -99,22 +99,37 @@ def _load_policy(path, obs_dim, device):
     return policy.to(device)
 
 
-def _evaluate(ctx, environment, num_envs, device, steps):
+def _evaluate(ctx, environment, num_envs, device, steps, video_dir=None):
+    """Deterministic policy for `steps` steps; with `video_dir` env 0 is rasterised every step (render.py) into
+    `<video_dir>/rec-<env>-step-0-to-step-<steps>.mp4`, the file name VecVideoRecorder gives it in the reference."""
     import torch
     from .batched_env import BatchedSo100Env
-    from .ppo import MlpPolicy
+    from .ppo import MlpPolicy  # noqa: F401  (torch.load of a pickled policy needs the class importable)
     if not ctx.obj["MODEL_PATH"]:
         raise click.UsageError("-m/--model is required")
     env = BatchedSo100Env(environment, num_envs, device=device, seed=123)
     policy = _load_policy(ctx.obj["MODEL_PATH"], env.obs_dim, env.device)
     obs, total = env.reset(), torch.zeros(num_envs, device=env.device)
+    sink = renderer = None
+    if video_dir:
+        from .render import SceneRenderer, VideoSink
+        renderer = SceneRenderer(env.spec)
+        sink = VideoSink(video_dir, f"rec-{environment}", 0, steps, renderer.w, renderer.h)
     with torch.no_grad():
-        for _ in range(steps):
+        for t in range(steps):
             a, _, _ = policy.act(obs, deterministic=True)
             r = env.step(torch.clamp(a, -1, 1))
             obs = r.obs
             total += r.reward
-    click.echo(json.dumps({"env": environment, "steps": steps, "mean_return": float(total.mean()), "mean_step_reward": float(total.mean()) / steps}))
+            if sink is not None:
+                st = env.get_state()
+                sink.write(renderer.render(st["qpos"][:, 0].cpu().numpy(), st["block"][:3, 0].cpu().numpy(),
+                                           text=f"{environment}  step {t + 1}  return {float(total[0]):.2f}"))
+    out = {"env": environment, "steps": steps, "mean_return": float(total.mean()), "mean_step_reward": float(total.mean()) / steps}
+    if sink is not None:
+        sink.close()
+        out["video"] = sink.path
+    click.echo(json.dumps(out))
 
 
 @cli.command()
@@ -122,20 +137,24 @@ def _evaluate(ctx, environment, num_envs, device, steps):
 @click.option("--num-envs", default=256, show_default=True)
 @click.option("--device", default=0, show_default=True)
 @click.option("--steps", default=3000, show_default=True)
+@click.option("--video-dir", default=None, help="also rasterise env 0 into a video in this directory")
 @click.pass_context
-def test(ctx, environment, num_envs, device, steps):
-    """Head-less stand-in for main.py:78-124 (the reference opens a MuJoCo viewer): deterministic policy, mean return."""
-    _evaluate(ctx, environment, num_envs, device, steps)
+def test(ctx, environment, num_envs, device, steps, video_dir):
+    """main.py:78-124 opens an interactive MuJoCo viewer and loops predict -> step; head-less here: the deterministic
+    policy's mean return over --steps steps, optionally with the rasterised video of env 0."""
+    _evaluate(ctx, environment, num_envs, device, steps, video_dir)
 
 
 @cli.command()
 @click.option("-e", "--environment", required=True)
-@click.option("--num-envs", default=256, show_default=True)
+@click.option("--num-envs", default=1, show_default=True)
 @click.option("--device", default=0, show_default=True)
+@click.option("--video-dir", default="recordings", show_default=True, help="RECORDING_DIR of the reference (main.py:30)")
 @click.pass_context
-def record(ctx, environment, num_envs, device):
-    """main.py:127-171 renders 3000 steps to video; rendering is out of scope, so this reports the same 3000 steps' returns."""
-    _evaluate(ctx, environment, num_envs, device, 3000)
+def record(ctx, environment, num_envs, device, video_dir):
+    """main.py:127-171: 3000 steps of the policy recorded to `recordings/rec-<env>-step-0-to-step-3000.mp4`, drawn by the
+    head-less software rasteriser (render.py) instead of MuJoCo's GL renderer."""
+    _evaluate(ctx, environment, num_envs, device, 3000, video_dir)
 
 
 if __name__ == "__main__":
