@@ -429,20 +429,20 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
-template <int TASK, bool SPEC, bool PADS, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, SO100_MINBLOCKS) step_kernel(const __grid_constant__ Consts C, const Bufs B, const StepIO io) {
+template <int TASK, bool SPEC, bool PADS>
+__global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __grid_constant__ Consts C, const Bufs B, const StepIO io) {
   constexpr int OD = TASK == 5 ? 8 : 15;
-  __shared__ __align__(16) float sh[BLOCK * OD];
-  static_assert((BLOCK * OD) % 4 == 0, "obs rows of a CTA must be a whole number of float4");
+  __shared__ __align__(16) float sh[kBlock * OD];
+  static_assert((kBlock * OD) % 4 == 0, "obs rows of a CTA must be a whole number of float4");
   const TaskC& t = C.t;
-  const int n = t.n, base = io.env_lo + blockIdx.x * BLOCK, hi = io.env_hi;
+  const int n = t.n, base = io.env_lo + blockIdx.x * kBlock, hi = io.env_hi;
   const unsigned tick = io.tick;
   // Envs whose jaw pads touched the floor last step take the (much longer) contact path in most substeps of this one.
   // They are ~10 % of the envs under random actions, so almost every warp would hold one and wait for it; instead the
   // CTA re-deals its 256 envs to its threads with the touching ones first (a stable partition on the hint bit), which
   // confines the contact path to one or two of the eight warps.  `slot` is the env this thread now owns.
-  __shared__ unsigned short perm[BLOCK];
-  __shared__ int warp_cnt[BLOCK / 32];
+  __shared__ unsigned short perm[kBlock];
+  __shared__ int warp_cnt[kBlock / 32];
   __shared__ int pool_cnt[2];
   extern __shared__ double pool_mem[];  // kPoolBytes when the model has pads, else nothing
   const ContactPool pool{reinterpret_cast<float*>(pool_mem + (size_t)kPoolSlots * ContactShared<SO_FAST_CON>::kDoubles), pool_mem, pool_cnt,
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(BLOCK, SO100_MINBLOCKS) step_kernel(const __gr
     __syncthreads();
     int before = 0, total = 0;  // touching envs in earlier warps / in the CTA
 #pragma unroll
-    for (int w = 0; w < BLOCK / 32; w++) { const int cw = warp_cnt[w]; total += cw; before += w < wid ? cw : 0; }
+    for (int w = 0; w < kBlock / 32; w++) { const int cw = warp_cnt[w]; total += cw; before += w < wid ? cw : 0; }
     const int rank_t = before + __popc(bal & ((1u << lane) - 1u));           // rank among the touching envs
     const int dest = hint ? rank_t : total + ((int)threadIdx.x - rank_t);   // the others keep their order behind them
     perm[dest] = (unsigned short)threadIdx.x;
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(BLOCK, SO100_MINBLOCKS) step_kernel(const __gr
   const bool live = base + slot < hi;
   const int i = live ? base + slot : hi - 1;  // tail threads shadow the last env (they must reach every barrier); nothing they compute is stored
   // coalesced load of the CTA's action rows through shared memory
-  for (int k = threadIdx.x; k < BLOCK * SO_NJ; k += BLOCK) {
+  for (int k = threadIdx.x; k < kBlock * SO_NJ; k += kBlock) {
     int g = base * SO_NJ + k;
     sh[k] = g < hi * SO_NJ ? io.actions[g] : 0.0f;
   }
@@ -603,14 +603,14 @@ __global__ void __launch_bounds__(BLOCK, SO100_MINBLOCKS) step_kernel(const __gr
     for (int k = 0; k < OD; k++) sh[slot * OD + k] = obs[k];
   }
   __syncthreads();
-  // the CTA's obs rows are one contiguous, 16-byte aligned span (BLOCK * OD floats): 512 bytes per warp instruction
+  // the CTA's obs rows are one contiguous, 16-byte aligned span (kBlock * OD floats): 512 bytes per warp instruction
   // (on the host path these stores cross the link; larger write bursts pack into fuller PCIe packets)
-  if (base + BLOCK <= hi) {
+  if (base + kBlock <= hi) {
     float4* dst = reinterpret_cast<float4*>(io.obs + (size_t)base * OD);
     const float4* src = reinterpret_cast<const float4*>(sh);
-    for (int k = threadIdx.x; k < BLOCK * OD / 4; k += BLOCK) dst[k] = src[k];
+    for (int k = threadIdx.x; k < kBlock * OD / 4; k += kBlock) dst[k] = src[k];
   } else {
-    for (int k = threadIdx.x; k < BLOCK * OD; k += BLOCK) {
+    for (int k = threadIdx.x; k < kBlock * OD; k += kBlock) {
       size_t g = (size_t)base * OD + k;
       if (g < (size_t)hi * OD) io.obs[g] = sh[k];
     }
@@ -1117,7 +1117,6 @@ static void flatten_dyn(const DynC<double>& D, double* out) {
 
 struct so100_ctx {
   int device = 0, n = 0, task = 0, obs_dim = 0;
-  int block = kBlock;  // threads (= envs) per CTA of the step kernel, chosen at creation so that the grid fills whole waves
   Consts C;
   HostModel H;
   Bufs B{};
@@ -1174,26 +1173,6 @@ static void free_ctx(so100_ctx* c) {
   delete c;
 }
 
-// CTA size of the step kernel.  The kernel is latency-bound, two CTAs of 128-register threads fill an SM, and a step costs
-// about the same whether an SM's schedulers hold 3.5 or 4 warps each - what matters is that no SM sits a wave out:
-// 65 536 envs are 256 CTAs of 256 threads on 296 slots (40 SMs run one CTA while the rest run two), but 293 CTAs of 224
-// threads, one balanced wave.  Pick, among the compiled sizes, the one with the fewest waves, then the most even fill.
-// SO100_BLOCK_OVERRIDE=256|224 forces one (experiments).
-static int choose_block(int n, int device) {
-  if (const char* e = getenv("SO100_BLOCK_OVERRIDE")) { const int v = atoi(e); if (v == 256 || v == 224) return v; }
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const int slots = sms * SO100_MINBLOCKS;
-  int best = kBlock;
-  double best_cost = 1e30;
-  for (int b : {256, 224}) {
-    const int ctas = (n + b - 1) / b, waves = (ctas + slots - 1) / slots;
-    const double cost = (double)waves * (b == 256 ? 1.0 : 0.93);  // a wave of 224-thread CTAs is ~7 % shorter (14 instead of 16 warps per SM)
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = b; }
-  }
-  return best;
-}
-
 static void mark_caller_stream_work(so100_ctx* c) {
   for (int g = 0; g < so100_ctx::kMaxGroups; g++) c->g_fork_needed[g] = true;
 }
@@ -1233,7 +1212,6 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
   c->device = device; c->n = cfg->num_envs; c->task = cfg->task; c->obs_dim = so100_obs_dim(cfg->task);
   int rc = build_host_model(*m, c->H);
   if (rc != SO100_OK) { delete c; return rc; }
-  c->block = choose_block(c->n, device);  // (224 only exists for the specialised contact-free kernel: fixed up below)
   {
     double flat[SO100_N_DYN_CONSTANTS];
     flatten_dyn(c->H.dyn, flat);
@@ -1285,13 +1263,12 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
   for (int i = 0; i < kMaxStart; i++) for (int j = 0; j < SO_NJ; j++) tab[i * SO_NJ + j] = (float)cfg->start_positions[i][j];
   if (cudaMemcpy(c->start_tab, tab, sizeof tab, cudaMemcpyHostToDevice) != cudaSuccess) { free_ctx(c); return fail(SO100_ERR_CUDA, "cudaMemcpy(start table)"); }
   c->B.start_tab = c->start_tab;
-  if (!c->specialised || c->C.pad.n > 0) c->block = kBlock;
   c->n_groups = 1; c->g_lo[0] = 0; c->g_hi[0] = c->n;
   {  // the contact pool is > 48 KB of dynamic shared memory: opt in, per device, for this task's step kernels
     cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
 #define SO100_OPT(T)                                                                                                              \
-  e1 = cudaFuncSetAttribute(step_kernel<T, true, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolBytes);    \
-  e2 = cudaFuncSetAttribute(step_kernel<T, false, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolBytes)
+  e1 = cudaFuncSetAttribute(step_kernel<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolBytes);         \
+  e2 = cudaFuncSetAttribute(step_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoolBytes)
     switch (c->task) {
       case 1: SO100_OPT(1); break;
       case 2: SO100_OPT(2); break;
@@ -1327,17 +1304,15 @@ int so100_reset(so100_ctx* c, const uint8_t* mask_dev, float* obs_dev, void* str
 }
 
 static int launch_step(so100_ctx* c, const StepIO& io, cudaStream_t st) {
-  const int g = (io.env_hi - io.env_lo + c->block - 1) / c->block;
+  const int g = grid_for(io.env_hi - io.env_lo);
   const bool pads = c->C.pad.n > 0;
   const size_t dyn = pads ? kPoolBytes : 0;
-  // variants per task: model-specialised without the arm-floor contact path (CTA size 256 or 224), model-specialised with
-  // it, and the generic one (any model, with it)
-#define SO100_LAUNCH(T)                                                                                          \
-  do {                                                                                                           \
-    if (c->specialised && !pads && c->block == 224) step_kernel<T, true, false, 224><<<g, 224, 0, st>>>(c->C, c->B, io); \
-    else if (c->specialised && !pads) step_kernel<T, true, false, 256><<<g, 256, 0, st>>>(c->C, c->B, io);       \
-    else if (c->specialised) step_kernel<T, true, true, 256><<<g, 256, dyn, st>>>(c->C, c->B, io);               \
-    else step_kernel<T, false, true, 256><<<g, 256, dyn, st>>>(c->C, c->B, io);                                  \
+  // three variants per task: model-specialised without / with the arm-floor contact path, and the generic one (any model, with it)
+#define SO100_LAUNCH(T)                                                                                    \
+  do {                                                                                                     \
+    if (c->specialised && !pads) step_kernel<T, true, false><<<g, kBlock, 0, st>>>(c->C, c->B, io);        \
+    else if (c->specialised) step_kernel<T, true, true><<<g, kBlock, dyn, st>>>(c->C, c->B, io);           \
+    else step_kernel<T, false, true><<<g, kBlock, dyn, st>>>(c->C, c->B, io);                              \
   } while (0)
   switch (c->task) {
     case 1: SO100_LAUNCH(1); break;
@@ -1447,7 +1422,7 @@ static int enqueue_host_pipeline(so100_ctx* c, cudaStream_t st, const float* act
   const size_t od = (size_t)c->obs_dim;
   // chunks are multiples of the CTA size; small batches are not worth splitting
   int nchunk = c->n >= 4 * 4096 ? c->n_chunks : 1;
-  int per = ((c->n + nchunk - 1) / nchunk + c->block - 1) / c->block * c->block;
+  int per = ((c->n + nchunk - 1) / nchunk + kBlock - 1) / kBlock * kBlock;
   CU(cudaMemsetAsync(c->d_any_done, 0, sizeof(int), st));
   CU(cudaEventRecord(c->ev_start, st));
   for (int k = 0; k < nchunk; k++) {
@@ -1542,11 +1517,11 @@ int so100_step_host(so100_ctx* c, const float* actions_host, float* obs_host, fl
 int so100_host_groups(so100_ctx* c, int n_groups) {
   if (!c || n_groups < 1 || n_groups > so100_ctx::kMaxGroups) return fail(SO100_ERR_ARG, "n_groups out of range");
   if (int rc = groups_in_step(c)) return rc;
-  const int ctas = (c->n + c->block - 1) / c->block;
+  const int ctas = grid_for(c->n);
   if (n_groups > ctas) return fail(SO100_ERR_ARG, "more groups than CTAs of envs");
   for (int g = 0; g < n_groups; g++) {  // balanced, CTA-aligned, contiguous
-    c->g_lo[g] = (int)((int64_t)ctas * g / n_groups) * c->block;
-    int hi = (int)((int64_t)ctas * (g + 1) / n_groups) * c->block;
+    c->g_lo[g] = (int)((int64_t)ctas * g / n_groups) * kBlock;
+    int hi = (int)((int64_t)ctas * (g + 1) / n_groups) * kBlock;
     c->g_hi[g] = hi < c->n ? hi : c->n;
   }
   c->n_groups = n_groups;
