@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--e2e-groups", type=int, default=8, help="env groups of the pipelined host path (so100_step_host_async)")
     ap.add_argument("--no-tasks", action="store_true", help="skip the Env02 / Env05 records (BASELINE configs 3, 4)")
     ap.add_argument("--no-ppo", action="store_true", help="skip the Env05 PPO record (BASELINE config 5)")
+    ap.add_argument("--no-contact", action="store_true", help="skip the record of the opt-in arm-floor contact physics (SO100_FLAG_ARM_CONTACT)")
     ap.add_argument("--flags", type=int, default=0, help="SO100_FLAG_* bits for the env (e.g. 16 = no arm-floor contact)")
     return ap.parse_args()
 
@@ -323,11 +324,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def fresh_env(t, seed=0):
+    def fresh_env(t, seed=0, flags=None):
         """Env-sharded (no collective on the step path), started from a DECORRELATED state: episode clocks staggered over
         the whole TimeLimit, then 64 untimed steps, so truncations + in-kernel resets run inside the timed region at
         their steady rate and no env is in its post-reset transient."""
-        e = BatchedSo100Env(t, n, device=local_rank, seed=seed, env_offset=rank * n, flags=args.flags)
+        e = BatchedSo100Env(t, n, device=local_rank, seed=seed, env_offset=rank * n, flags=args.flags if flags is None else flags)
         e.reset()
         e.stagger_episodes()
         for w in range(64):
@@ -443,6 +444,24 @@ def main():
             tasks_rec[name] = rec
             e.close()
 
+    # ---- the opt-in arm-floor contact physics (the reference's jaw-pad colliders): what the same workload costs with it
+    contact_rec = None
+    if not args.no_contact and not (args.flags & 16):
+        e = fresh_env(task, seed=0, flags=args.flags | 16)
+        ksteps = 10
+        evc, resc = timed_steps(e, ring, ksteps, flush, torch)
+        torch.cuda.synchronize(dev)
+        ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evc), dev)
+        touching = float(((e.get_state()["counters"][1] & 16) != 0).float().mean())
+        below = float((resc[-1].obs[:, 14] < 0).float().mean()) if task != 5 else None
+        below_off = float((res[-1].obs[:, 14] < 0).float().mean()) if task != 5 else None
+        st_c = e.stats()
+        contact_rec = {"flag": "SO100_FLAG_ARM_CONTACT", "ms_per_step": ms / ksteps, "env_steps_per_s": n * world * ksteps / (ms * 1e-3),
+                       "slowdown_vs_default": (ms / ksteps) / (total_ms / steps), "envs_touching_floor_frac": touching,
+                       "end_effector_below_floor_frac": below, "end_effector_below_floor_frac_without_contact": below_off,
+                       "solver_unconverged": st_c["solver_unconverged"], "nan_resets": st_c["nan_resets"]}
+        e.close()
+
     # ---- BASELINE config 5: Env05 PPO rollout + update (fused learner), env-sharded, one flat all-reduce per minibatch
     ppo_rec = None
     if not args.no_ppo:
@@ -522,6 +541,8 @@ def main():
             line["tasks"] = tasks_rec
         if ppo_rec:
             line["ppo"] = ppo_rec
+        if contact_rec:
+            line["arm_floor_contact"] = contact_rec
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             ncpu = args.cpu_envs or 256 * threads

@@ -46,17 +46,23 @@ def load_sb3_zip(path: str) -> dict:
 
 @torch.no_grad()
 def evaluate_policy(policy, env, n_steps: int) -> dict:
-    """Deterministic roll-out of `policy` (an MlpPolicy) on `env` (BatchedSo100Env-like) for n_steps env steps: mean
-    return of the episodes that finished, and the mean reward per step (EvalCallback's mean_reward analogue)."""
+    """Deterministic roll-out of `policy` (an MlpPolicy) on `env` (BatchedSo100Env-like) for n_steps env steps.
+    The score (`mean_return`) is ONE quantity whatever the episode length: every env's reward accumulated over the fixed
+    horizon, averaged over envs (episodes that end inside the horizon simply continue into their next episode).  With
+    n_steps = the task's TimeLimit this is EvalCallback's mean episode reward for tasks that never terminate early."""
     obs = env.reset()
-    tot, ers, cnt = 0.0, 0.0, 0.0
+    total = torch.zeros(env.num_envs, device=obs.device)
+    ers, cnt = 0.0, 0.0
     for _ in range(n_steps):
         a, _, _ = policy.act(obs, deterministic=True)
         r = env.step(torch.clamp(a, -1.0, 1.0))
         done = (r.terminated.bool() | r.truncated.bool()).float()
-        tot += float(r.reward.mean()); ers += float((r.ep_return * done).sum()); cnt += float(done.sum())
+        total += r.reward
+        ers += float((r.ep_return * done).sum()); cnt += float(done.sum())
         obs = r.obs
-    return {"mean_step_reward": tot / n_steps, "mean_ep_return": ers / cnt if cnt else None, "episodes": int(cnt)}
+    mean_return = float(total.mean())
+    return {"mean_return": mean_return, "mean_step_reward": mean_return / n_steps, "mean_ep_return": ers / cnt if cnt else None,
+            "episodes": int(cnt)}
 
 
 class TrainCallbacks:
@@ -85,8 +91,11 @@ class TrainCallbacks:
         pol = self.learner.policy
         base = os.path.join(self.folder, name)
         ckpt = {"policy": pol.state_dict(), "samples": self.learner.stats.samples}
-        if hasattr(self.learner, "state_dict"):  # optimizer moments and counters: `-m <file>.pt` resumes exactly
+        if hasattr(self.learner, "state_dict"):  # optimizer moments and counters
             ckpt["learner"] = self.learner.state_dict()
+        env = getattr(self.learner, "env", None)
+        if env is not None and hasattr(env, "get_state") and hasattr(env, "tick"):  # simulator state: the resumed run continues the same episodes
+            ckpt["env"] = {"state": {k: v.cpu() for k, v in env.get_state().items()}, "tick": env.tick, "num_envs": env.num_envs}
         torch.save(ckpt, base + ".pt")
         export_sb3_zip(base + ".zip", pol.state_dict_sb3(), {"num_timesteps": self.learner.stats.samples})
         return base
@@ -106,7 +115,7 @@ class TrainCallbacks:
         if self.eval_env is not None and self.eval_freq and n >= self._next_eval:  # EvalCallback
             self._next_eval += self.eval_freq * max(1, (n - self._next_eval) // self.eval_freq + 1)
             ev = evaluate_policy(self.learner.policy, self.eval_env, self.eval_steps)
-            score = ev["mean_ep_return"] if ev["mean_ep_return"] is not None else ev["mean_step_reward"] * self.eval_steps
+            score = ev["mean_return"]   # fixed-horizon return: the same quantity at every evaluation
             self.n_evals += 1
             self.evals.append({"samples": n, "score": score, **ev})
             if self.tb is not None:

@@ -40,7 +40,7 @@ def cli(ctx, algorithm, model_path):
               help="fused = hand-written PPO kernels (include/so100_ppo.h); torch = the PyTorch reference learner")
 @click.option("--eval-freq", default=2_000_000, show_default=True, help="samples between evaluations (main.py:221 uses 20000 for its single env)")
 @click.option("--eval-envs", default=64, show_default=True, help="envs of the evaluation simulator (0 = no evaluation)")
-@click.option("--eval-steps", default=4000, show_default=True, help="env steps per evaluation (one Env01 episode)")
+@click.option("--eval-steps", default=0, show_default=True, help="env steps per evaluation (0 = the task's TimeLimit: one full episode per env)")
 @click.option("--save-freq", default=4_000_000, show_default=True, help="samples between checkpoints (main.py:228 uses 40000 for its single env)")
 @click.option("--tensorboard-log", default="logs", show_default=True, help="TensorBoard folder (main.py:30, :62); empty = off")
 @click.pass_context
@@ -69,17 +69,28 @@ def train(ctx, environment, num_envs, device, trainer, total_timesteps, n_steps,
     learner = FusedPPO(env, cfg) if learner_kind == "fused" else PPO(env, cfg)
     if ctx.obj["MODEL_PATH"]:  # main.py:201-207: continue from a saved model (weights; a .pt also restores Adam and the counters)
         path = ctx.obj["MODEL_PATH"]
-        full = torch.load(path, map_location="cpu").get("learner") if path.endswith(".pt") else None
+        ckpt = torch.load(path, map_location="cpu") if path.endswith(".pt") else {}
+        full = ckpt.get("learner")
         if full is not None:
             learner.load_state_dict(full)
         else:
             learner.load_policy(_load_policy(path, env.obs_dim, env.device))
+        # the simulator continues where the checkpoint left it (same episodes, same RNG tick) when it has the same shape;
+        # otherwise the run restarts its envs under a different seed so that it does not replay the original draws
+        es = ckpt.get("env")
+        if es is not None and es.get("num_envs") == env.num_envs:
+            env.set_state(es["state"]); env.tick = int(es["tick"])
+            learner.obs = env.obs   # (stale by one step at most: refreshed by the first env.step of the next rollout)
+        else:
+            env.seed(seed + 1_000_003)
+            learner.obs = env.reset() if learner_kind == "fused" else env.reset().clone()
     # main.py:211-232: EvalCallback(eval_freq=20000) + reward threshold 6000 + no-improvement stop, CheckpointCallback(40000)
     eval_env = BatchedSo100Env(environment, eval_envs, device=device, seed=seed + 1) if eval_envs > 0 else None
+    eval_steps = eval_steps or env.max_episode_steps
     cb = TrainCallbacks(learner, folder, f"{environment}_{algo}", eval_env=eval_env, eval_freq=eval_freq, eval_steps=eval_steps,
                         save_freq=save_freq, tensorboard_dir=tensorboard_log or None)
     t0 = time.time()
-    stats = learner.learn(total_timesteps, log_every=0, callback=cb)
+    stats = learner.learn(total_timesteps, log_every=0, callback=cb, additional=bool(ctx.obj["MODEL_PATH"]))  # SB3 restarts its count per learn() call
     cb.save("final_model")
     cb.close()
     click.echo(json.dumps({"samples": stats.samples, "wall_s": time.time() - t0, "rollout_s": stats.rollout_s, "update_s": stats.update_s,

@@ -783,6 +783,18 @@ int64_t so100_ppo_workspace_floats(int obs_dim) {
   return n < 0 ? n : (int64_t)SO100_PPO_MAX_CTAS * (n + 4) + 4 * ppo::kStatCtas;
 }
 
+// The learner's buffers say which GPU they live on: make it current (the entry points take no device argument, and the
+// caller's current device need not be the one its tensors are on).
+static int ppo_use_device_of(const void* dev_ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, dev_ptr) != cudaSuccess || a.type != cudaMemoryTypeDevice) {
+    cudaGetLastError();
+    return fail(SO100_ERR_ARG, "expected a device pointer");
+  }
+  CU(cudaSetDevice(a.device));
+  return SO100_OK;
+}
+
 static int ppo_smem_optin(const void* fn, int floats) {  // per device; the call is cheap, so it is simply repeated
   CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, floats * 4));
   return SO100_OK;
@@ -792,7 +804,9 @@ int so100_ppo_act(int obs_dim, const float* params, const float* obs, int n, uin
                   int deterministic, float* act_raw, float* act_clip, float* logp, float* value, float* obs_copy, void* stream) {
   if (so100_ppo_param_count(obs_dim) < 0) return SO100_ERR_ARG;
   if (!params || !obs || n <= 0) return fail(SO100_ERR_ARG, "bad argument");
-  int rc = ppo_smem_optin((const void*)ppo::act_kernel, ppo::kActSmemFloats);
+  int rc = ppo_use_device_of(params);
+  if (rc) return rc;
+  rc = ppo_smem_optin((const void*)ppo::act_kernel, ppo::kActSmemFloats);
   if (rc) return rc;
   int dev = 0, sms = 0;
   CU(cudaGetDevice(&dev));
@@ -811,6 +825,7 @@ int so100_ppo_post_step(int obs_dim, const float* params, int n, const float* re
   if (so100_ppo_param_count(obs_dim) < 0) return SO100_ERR_ARG;
   if (!params || n <= 0 || !reward || !terminated || !truncated || !terminal_obs || !ep_return || !ep_len || !reward_out || !done_out || !acc)
     return fail(SO100_ERR_ARG, "bad argument");
+  if (int rc = ppo_use_device_of(params)) return rc;
   ppo::post_step_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ppo::make_layout(obs_dim), params, n, reward, terminated, truncated,
                                                                            terminal_obs, ep_return, ep_len, gamma, reward_out, done_out, acc);
   CU(cudaGetLastError());
@@ -820,6 +835,7 @@ int so100_ppo_post_step(int obs_dim, const float* params, int n, const float* re
 int so100_ppo_gae(const float* rew, const float* val, const float* done, const float* last_val, int T, int N, float gamma, float lam,
                   float* adv, float* ret, void* stream) {
   if (!rew || !val || !done || !last_val || !adv || !ret || T <= 0 || N <= 0) return fail(SO100_ERR_ARG, "bad argument");
+  if (int rc = ppo_use_device_of(rew)) return rc;
   ppo::gae_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rew, val, done, last_val, T, N, gamma, lam, adv, ret);
   CU(cudaGetLastError());
   return SO100_OK;
@@ -827,6 +843,7 @@ int so100_ppo_gae(const float* rew, const float* val, const float* done, const f
 
 int so100_ppo_permutation(int n, uint64_t key, int64_t* idx_out, void* stream) {
   if (n <= 0 || !idx_out) return fail(SO100_ERR_ARG, "bad argument");
+  if (int rc = ppo_use_device_of(idx_out)) return rc;
   int bits = 1;
   while ((1ll << bits) < (long long)n) bits++;
   const int half_bits = (bits + 1) / 2;
@@ -841,7 +858,9 @@ int so100_ppo_grad(int obs_dim, const float* params, const float* obs, const flo
   if (so100_ppo_param_count(obs_dim) < 0) return SO100_ERR_ARG;
   if (!params || !obs || !act || !logp_old || !adv || !ret || !idx || mb <= 0 || !workspace || !grad) return fail(SO100_ERR_ARG, "bad argument");
   const ppo::Layout L = ppo::make_layout(obs_dim);
-  int rc = ppo_smem_optin((const void*)ppo::grad_kernel, ppo::kGradSmemFloats);
+  int rc = ppo_use_device_of(params);
+  if (rc) return rc;
+  rc = ppo_smem_optin((const void*)ppo::grad_kernel, ppo::kGradSmemFloats);
   if (rc) return rc;
   int dev = 0, sms = 0;
   CU(cudaGetDevice(&dev));
@@ -863,6 +882,7 @@ int so100_ppo_grad(int obs_dim, const float* params, const float* obs, const flo
 int so100_ppo_adam(int n_params, float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int32_t* step_count, float grad_scale,
                    float max_grad_norm, float lr, float beta1, float beta2, float eps, void* stream) {
   if (n_params <= 0 || !params || !grad || !exp_avg || !exp_avg_sq || !step_count) return fail(SO100_ERR_ARG, "bad argument");
+  if (int rc = ppo_use_device_of(params)) return rc;
   ppo::adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n_params, params, grad, exp_avg, exp_avg_sq, step_count, grad_scale, max_grad_norm, lr,
                                                           beta1, beta2, eps);
   CU(cudaGetLastError());

@@ -174,8 +174,12 @@ class _LearnLoop:
         if self.device.type == "cuda":
             torch.cuda.synchronize(self.device)
 
-    def learn(self, total_samples: int, log_every: int = 10, callback=None) -> PPOStats:
+    def learn(self, total_samples: int, log_every: int = 10, callback=None, additional: bool = False) -> PPOStats:
+        """Run until `stats.samples` reaches total_samples; with additional=True until total_samples MORE have been drawn
+        (SB3's `learn(total_timesteps)` restarts its count on every call: what a resumed `train -m ...` wants)."""
         per_iter = self.cfg.n_steps * self.env.num_envs * self.world
+        if additional:
+            total_samples = self.stats.samples + total_samples
         while self.stats.samples < total_samples:
             self._sync(); t0 = time.perf_counter()
             adv, ret = self.collect()
@@ -214,6 +218,9 @@ class PPO(_LearnLoop):
         if self.world > 1:  # identical initial weights on every rank
             for p in self.policy.parameters():
                 dist.broadcast(p.data, src=0)
+            # ... but different exploration noise: every rank owns different envs (the fused learner keys its noise by the
+            # global env id; here torch's generator is re-seeded per rank once the shared initialisation is done)
+            torch.manual_seed(self.cfg.seed + 7919 * (dist.get_rank() + 1))
         self.obs = env.reset().clone()
         self.stats = PPOStats()
         n, T, od, ad = env.num_envs, self.cfg.n_steps, env.obs_dim, env.act_dim
