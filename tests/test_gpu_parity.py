@@ -29,6 +29,18 @@ def _gpu_env(task, n, **kw):
     return BatchedSo100Env(task, n, device=0, **kw)
 
 
+def _record(name, **numbers):
+    """Keep the measured numbers of a passing test (pytest -q swallows stdout): gpurun_out/parity/<name>.json."""
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity")
+    try:
+        os.makedirs(d, exist_ok=True)
+        json.dump({k: (float(v) if hasattr(v, "__float__") else v) for k, v in numbers.items()}, open(os.path.join(d, name + ".json"), "w"))
+    except OSError:
+        pass
+
+
 def _oracle_soa(o, field):
     return o.gather(field).T  # [k, N]
 
@@ -99,6 +111,7 @@ def test_trajectory_parity(task, steps):
     if task != 5:
         assert (blk[2] > 0.0098).all() and (blk[2] < 0.01).all()            # resting ~0.1 mm inside the plane
     print(f"task {task}: max|dq| {dq:.2e} max|dv| {dv:.2e} max|dobs| {worst['obs']:.2e} max|drew| {worst['rew']:.2e} pixel flips {pix}")
+    _record(f"trajectory_task{task}", envs=n, steps=steps, dq_max=dq, dv_max=dv, dobs_max=worst["obs"], drew_max=worst["rew"], pixel_flips=pix)
     assert dq < TOL_Q and dv < TOL_V
     assert worst["obs"] < TOL_OBS
     assert worst["rew"] < (TOL_R if task != 5 else 2e-3)
@@ -372,6 +385,8 @@ def test_parity_at_baseline_size(task):
     print(f"task {task} @ {n} envs x {K} steps: |dq| median {np.median(dq):.2e} p99.9 {np.quantile(dq, 0.999):.2e} max {dq.max():.2e}; "
           f"rate(|dq| > {TOL_Q:g}) {rate:.2e}; |dv| p99.9 {np.quantile(dv, 0.999):.2e}; |drew| p99.9 {np.quantile(drew, 0.999):.2e}; "
           f"bifurcated {split}; episodes ended {ndone}")
+    _record(f"baseline_size_task{task}", envs=n, steps=K, dq_median=np.median(dq), dq_p999=np.quantile(dq, 0.999), dq_max=dq.max(),
+            rate_above_2e5=rate, dv_p999=np.quantile(dv, 0.999), drew_p999=np.quantile(drew, 0.999), bifurcated=split, episodes_ended=ndone)
     assert ndone > 0                                   # auto-reset ran inside the compared window
     assert np.median(dq) < 1e-6 and np.quantile(dq, 0.999) < 5e-6
     assert rate < 4e-5
@@ -410,6 +425,8 @@ def test_arm_floor_contact_parity(task):
     rate = float((dq > TOL_Q).mean())
     print(f"task {task} with arm-floor contact: {touching / (steps * n):.1%} of the (env, step) samples end touching the floor; "
           f"|dq| median {np.median(dq):.2e} p99 {np.quantile(dq, 0.99):.2e} max {dq.max():.2e}; rate(|dq| > {TOL_Q:g}) {rate:.2e}")
+    _record(f"arm_floor_contact_task{task}", envs=n, steps=steps, touching_frac=touching / (steps * n), dq_median=np.median(dq),
+            dq_p90=np.quantile(dq, 0.9), dq_p99=np.quantile(dq, 0.99), dq_max=dq.max(), rate_above_2e5=rate)
     assert touching > 0.05 * steps * n         # the contact path really ran
     assert below == 0                          # the end-effector point never goes through the floor any more
     assert np.median(dq) < 1e-6 and np.quantile(dq, 0.9) < 5e-6
