@@ -60,6 +60,7 @@ enum { STREAM_RESET = 0, STREAM_TASK = 1, STREAM_NOISE = 2, STREAM_API_RESET = 3
 
 struct TaskC {
   int task, n, max_steps, n_start, lost_limit, nsub;
+  int contact_warps;  // warps of a CTA over which the touching envs are dealt (1..8)
   unsigned flags;
   unsigned seed_lo, seed_hi;
   long long env_offset;
@@ -459,7 +460,11 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
 #pragma unroll
     for (int w = 0; w < kBlock / 32; w++) { const int cw = warp_cnt[w]; total += cw; before += w < wid ? cw : 0; }
     const int rank_t = before + __popc(bal & ((1u << lane) - 1u));           // rank among the touching envs
-    const int dest = hint ? rank_t : total + ((int)threadIdx.x - rank_t);   // the others keep their order behind them
+    int dest = hint ? rank_t : total + ((int)threadIdx.x - rank_t);   // the others keep their order behind them
+    // ... and the first 32 * W positions are dealt round-robin to W warps: W contact warps with 1/W of the touching envs
+    // each (a warp's solve takes as long as its slowest lane, and more contact warps per scheduler hide more latency)
+    const int W = t.contact_warps;
+    if (dest < 32 * W) dest = (dest % W) * 32 + dest / W;
     perm[dest] = (unsigned short)threadIdx.x;
   }
   __syncthreads();
@@ -1233,6 +1238,8 @@ int so100_create(const so100_model* m, const so100_task_cfg* cfg, int device, so
   TaskC& t = C.t;
   t.task = cfg->task; t.n = cfg->num_envs; t.max_steps = cfg->max_episode_steps; t.n_start = cfg->n_start;
   t.lost_limit = cfg->lost_limit; t.nsub = m->nsubstep; t.flags = cfg->flags;
+  t.contact_warps = 1;
+  if (const char* e = getenv("SO100_CONTACT_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= kBlock / 32) t.contact_warps = v; }  // tuning knob
   t.seed_lo = (unsigned)(cfg->seed & 0xFFFFFFFFull); t.seed_hi = (unsigned)(cfg->seed >> 32);
   t.env_offset = cfg->env_offset;
   t.dt_env = (float)(m->timestep * m->nsubstep); t.step_scale = (float)cfg->joint_step_scale;
