@@ -10,6 +10,7 @@
 //   envs/env01_v1.py:15-63, envs/env02_v1.py:18-81, envs/env03_v1.py:35-215, envs/env05_v1.py:32-75,
 //   envs/env_base_01.py:107-270, envs/env_base_02.py:85-127, __init__.py:5-45, and mujoco.mj_step (3rd party).
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -294,17 +295,18 @@ __device__ __forceinline__ float reward_reach(const TaskC& t, EnvRegs& e, bool i
   return r;
 }
 
-// Shared-memory pool of contact-solve slots of one CTA (ContactShared in so100_dyn.cuh).  Slots are handed out anew in
-// every substep from one of two counters used in alternation: cnt[sub & 1] serves substep `sub`, and thread 0 clears the
-// other one right after the substep's CTA barrier, a full substep before it is used again.
-constexpr int kPoolSlots = 64;
+// Shared-memory pool of contact-solve slots of one CTA (CoopSlot in so100_dyn.cuh, slot-major).  Slots are handed out
+// anew in every substep from one of two counters used in alternation: cnt[sub & 1] serves substep `sub`, and thread 0
+// clears the other one right after the substep's CTA barrier, a full substep before it is used again.
+constexpr int kPoolSlots = 48;
 struct ContactPool {
   float* f;
   double* d;
   int* cnt;
-  int nslot;  // 0: no pool (debug kernels): every contact solve takes the out-of-line path
+  int nslot;  // 0: no pool (debug kernels): every contact solve takes the out-of-line serial path
+  __device__ __forceinline__ CoopSlot slot(int k) const { return CoopSlot{f + k * CoopSlot::kFloats, d + k * CoopSlot::kDoubles}; }
 };
-constexpr size_t kPoolBytes = (size_t)kPoolSlots * (ContactShared<SO_FAST_CON>::kDoubles * 8 + ContactShared<SO_FAST_CON>::kFloats * 4);
+constexpr size_t kPoolBytes = (size_t)kPoolSlots * (CoopSlot::kDoubles * 8 + CoopSlot::kFloats * 4);
 
 // 16 x mj_step on the arm.  ctrl is constant over the env step, so kp*clip(ctrl) is hoisted.
 // ctrl is carried as an unevaluated sum ctrl_hi + ctrl_lo so that Env01/02's closed loop ctrl = qpos + a*0.075 does not
@@ -361,54 +363,78 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
     float d = 0.0f;
     bool solved = false;
     const unsigned tmask = PADS ? __ballot_sync(0xffffffffu, touch != 0u) : 0u;
-    if (PADS && tmask) {  // (warp-uniform) some lane touches: hand out pool slots, one atomic per warp
-      int slot = kPoolSlots;
-      if (pool.nslot) {
-        const int lane = threadIdx.x & 31, leader = __ffs(tmask) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&pool.cnt[sub & 1], __popc(tmask));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        slot = base + __popc(tmask & ((1u << lane) - 1u));
+    if (PADS) {
+      // Phase A, the touching env's own thread: a pool slot (one atomic per warp), accurate trigonometry, the contacts
+      // with their Jacobians and row parameters, and the substep's M, b, per-dof rows and warm start -> the slot.
+      int myslot = -1;
+      if (tmask) {  // (warp-uniform) some lane touches
+        int slot = kPoolSlots;
+        if (pool.nslot) {
+          const int lane = threadIdx.x & 31, leader = __ffs(tmask) - 1;
+          int base = 0;
+          if (lane == leader) base = atomicAdd(&pool.cnt[sub & 1], __popc(tmask));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          slot = base + __popc(tmask & ((1u << lane) - 1u));
+        }
+        if (touch) {
+          float cs[SO_NJ], cc_[SO_NJ];
+#pragma unroll
+          for (int j = 0; j < SO_NJ; j++) {
+            float sj, cj;
+            sincosf(e.q[j], &sj, &cj);
+            cs[j] = fmaf(-e.qc[j], cj, sj); cc_[j] = fmaf(e.qc[j], sj, cj);  // sin / cos of q - qc to first order in qc (|qc| < 2e-7)
+          }
+          bool serial = slot >= pool.nslot;  // pool exhausted (> kPoolSlots touching envs in this CTA)
+          if (!serial) {
+            const int nc = coop_fill(C.dyn, C.kin, C.pad, C.con, pool.slot(slot), cs, cc_, e.q, e.qc, e.v, M, b, e.w, touch);
+            serial = nc < 0;            // > kCoopCon corners at once
+            if (nc > 0) myslot = slot;  // nc == 0: the accurate kinematics found no corner below the floor after all
+          }
+          if (serial) {  // thread-local storage, one thread, out of line
+            ContactIO<float> cio;
+#pragma unroll
+            for (int j = 0; j < SO_NJ; j++) { cio.s[j] = cs[j]; cio.c[j] = cc_[j]; cio.q[j] = e.q[j]; cio.qc[j] = e.qc[j]; cio.qd[j] = e.v[j]; cio.b[j] = b[j]; cio.a[j] = e.w[j]; }
+#pragma unroll
+            for (int k = 0; k < 21; k++) cio.M[k] = M[k];
+            int over = 0;
+            int st = contact_solve<float>(C.dyn, C.kin, C.pad, C.con, cio, touch, &over);
+            if (over && live) atomicAdd(&B.stats[2], 1ULL);
+            if (st != 0 && !over) {
+#pragma unroll
+              for (int j = 0; j < SO_NJ; j++) e.w[j] = cio.a[j];
+            }
+            if (over) st = 0;  // > SO_MAX_CON corners (never seen): counted, and this substep falls back to the contact-free solve
+            solved = st != 0;
+            if (st < 0) d = 1e30f;  // iteration cap / indefinite Hessian: counted with the Gauss-Seidel's unconverged substeps
+          }
+        }
       }
-      if (touch) {
-        float cs[SO_NJ], cc_[SO_NJ];
+      // Phase B, the whole CTA: groups of kCoopLanes threads run the Newton solves of the filled slots.  Consecutive slots
+      // go to different warps (slot = 8 * (group within its warp) + warp), so a few touching envs occupy every scheduler.
+      if (pool.nslot) {
+        __syncthreads();
+        const int nfill = min(pool.cnt[sub & 1], pool.nslot);  // CTA-uniform
+        if (nfill > 0) {
+          const int g = threadIdx.x / kCoopLanes, glane = threadIdx.x % kCoopLanes, gw = g & 3;
+          constexpr int kGroups = kBlock / kCoopLanes;
+          for (int base = 0; base < nfill; base += kGroups) {
+            if (base + (g >> 2) < nfill) {  // (warp-uniform) the warp's first group has a slot
+              const int sl = base + gw * (kGroups / 4) + (g >> 2);
+              float* sf = nullptr;
+              double* sd = nullptr;
+              if (sl < nfill && pool.slot(sl).F(CoopSlot::kNc) > 0.0f) { sf = pool.slot(sl).f; sd = pool.slot(sl).d; }
+              coop_solve_warp(sf, sd, glane, 8 * gw);
+            }
+          }
+          __syncthreads();
+          if (myslot >= 0) {
+            const CoopSlot S = pool.slot(myslot);
 #pragma unroll
-        for (int j = 0; j < SO_NJ; j++) {
-          float sj, cj;
-          sincosf(e.q[j], &sj, &cj);
-          cs[j] = fmaf(-e.qc[j], cj, sj); cc_[j] = fmaf(e.qc[j], sj, cj);  // sin / cos of q - qc to first order in qc (|qc| < 2e-7)
-        }
-        int st = 0, over = 0;
-        bool retry = slot >= pool.nslot;
-        if (!retry) {  // the normal case: storage in this lane's slot of the shared-memory pool
-          ContactShared<SO_FAST_CON> S{pool.f + slot, pool.d + slot, kPoolSlots};
-          float an[SO_NJ];
-#pragma unroll
-          for (int j = 0; j < SO_NJ; j++) an[j] = e.w[j];
-          st = contact_newton<float>(C.dyn, C.kin, C.pad, C.con, S, cs, cc_, e.q, e.qc, e.v, M, b, an, touch, false, &over, nullptr);
-          retry = over != 0;
-          if (!retry && st != 0) {
-#pragma unroll
-            for (int j = 0; j < SO_NJ; j++) e.w[j] = an[j];
+            for (int j = 0; j < SO_NJ; j++) e.w[j] = (float)S.D(CoopSlot::kX + j);
+            solved = true;
+            if (S.sc(10) != 1.0) d = 1e30f;
           }
         }
-        if (retry) {  // pool exhausted (> 64 touching envs in this CTA) or > 8 corners at once: thread-local storage, out of line
-          ContactIO<float> cio;
-#pragma unroll
-          for (int j = 0; j < SO_NJ; j++) { cio.s[j] = cs[j]; cio.c[j] = cc_[j]; cio.q[j] = e.q[j]; cio.qc[j] = e.qc[j]; cio.qd[j] = e.v[j]; cio.b[j] = b[j]; cio.a[j] = e.w[j]; }
-#pragma unroll
-          for (int k = 0; k < 21; k++) cio.M[k] = M[k];
-          over = 0;
-          st = contact_solve<float>(C.dyn, C.kin, C.pad, C.con, cio, touch, &over);
-          if (over && live) atomicAdd(&B.stats[2], 1ULL);
-          if (st != 0 && !over) {
-#pragma unroll
-            for (int j = 0; j < SO_NJ; j++) e.w[j] = cio.a[j];
-          }
-          if (over) st = 0;  // > SO_MAX_CON corners (never seen): counted, and this substep falls back to the contact-free solve
-        }
-        solved = st != 0;  // 0: the accurate kinematics found no corner below the floor after all
-        if (st < 0) d = 1e30f;  // iteration cap / indefinite Hessian: counted with the Gauss-Seidel's unconverged substeps
       }
     }
     if (!solved) d = solve_qacc<float>(K, M, b, e.q, e.qc, e.v, e.w, sub == 0 ? SO100_SWEEPS_FIRST : SO100_SWEEPS_REST);
@@ -446,7 +472,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
   __shared__ int warp_cnt[kBlock / 32];
   __shared__ int pool_cnt[2];
   extern __shared__ double pool_mem[];  // kPoolBytes when the model has pads, else nothing
-  const ContactPool pool{reinterpret_cast<float*>(pool_mem + (size_t)kPoolSlots * ContactShared<SO_FAST_CON>::kDoubles), pool_mem, pool_cnt,
+  const ContactPool pool{reinterpret_cast<float*>(pool_mem + (size_t)kPoolSlots * CoopSlot::kDoubles), pool_mem, pool_cnt,
                          PADS && C.pad.n > 0 ? kPoolSlots : 0};
   if (threadIdx.x < 2) pool_cnt[threadIdx.x] = 0;
   {
@@ -1039,6 +1065,26 @@ void flatten_solver(const ConC<float>& K, const ActC<float>& A, const BlkC<float
 // computes, incl. the compensated position sum) or T = double.  No GPU needed: the CPU-side development and test
 // vehicle of the contact path.  stats: [0] contact substeps, [1] gradient/Hessian evaluations, [2] line-search
 // evaluations, [3] largest evaluation count of one solve, [4] unconverged solves.
+// The cooperative solve on the host (fp32 only; kNoCoop: not applicable - fp64 emulation, > kCoopCon corners, or
+// SO100_HOST_SERIAL_CONTACT set - and the caller takes the serial solve).
+constexpr int kNoCoop = INT_MIN;
+static int host_coop_solve(const DynC<double>&, const KinC<double>&, const PadC<double>&, const ConC<double>&, ContactIO<double>&, unsigned, int*) { return kNoCoop; }
+static int host_coop_solve(const DynC<float>& D, const KinC<float>& Kn, const PadC<float>& P, const ConC<float>& K, ContactIO<float>& io, unsigned touch,
+                           int* nls) {
+  static const bool serial = getenv("SO100_HOST_SERIAL_CONTACT") != nullptr;
+  if (serial) return kNoCoop;
+  float sf[CoopSlot::kFloats];
+  double sd[CoopSlot::kDoubles];
+  memset(sf, 0, sizeof sf); memset(sd, 0, sizeof sd);
+  const CoopSlot S{sf, sd};
+  const int nc = coop_fill(D, Kn, P, K, S, io.s, io.c, io.q, io.qc, io.qd, io.M, io.b, io.a, touch);
+  if (nc < 0) return kNoCoop;
+  if (nc == 0) return 0;
+  const int st = coop_solve_host(S, nls);
+  for (int j = 0; j < SO_NJ; j++) io.a[j] = (float)S.D(CoopSlot::kX + j);
+  return st;
+}
+
 template <typename T>
 static void host_substeps_t(const DynC<T>& D, const KinC<T>& Kn, const PadC<T>& P, const ConC<T>& K, const ActC<T>& A, int n, double* qpos,
                             double* qvel, double* warm, const double* ctrl, int nsub, int64_t* stats, bool coarse_sincos = false) {
@@ -1073,7 +1119,8 @@ static void host_substeps_t(const DynC<T>& D, const KinC<T>& Kn, const PadC<T>& 
         memcpy(cio.M, M, sizeof M);
         int nls = 0;
         int over = 0;
-        const int st = contact_solve<T>(D, Kn, P, K, cio, touch, &over, &nls);
+        int st = host_coop_solve(D, Kn, P, K, cio, touch, &nls);  // fp32: the device's cooperative solve, lanes in sequence
+        if (st == kNoCoop) st = contact_solve<T>(D, Kn, P, K, cio, touch, &over, &nls);
         solved = st != 0;
         if (solved) memcpy(w, cio.a, sizeof w);
         if (stats && solved) {

@@ -599,28 +599,12 @@ SO_HD bool chol_solve6(Store& S, const T* r, T* x) {
   return true;
 }
 
-// qacc of an env whose pads touch the floor: primal Newton on the full convex problem
-//   min_a  1/2 a'Ma - b'a + sum_j [friction_j(a_j) + limit_j(a_j)] + sum_contacts sum_4 rows  D/2 min(0, J a - aref)^2
-// with the exact generalised Hessian, a Cholesky solve per iteration, and an exact line search: phi'(alpha) along the
-// Newton direction is piecewise linear and increasing, and it is evaluated from stored row residuals and slopes (no
-// Jacobians), so a safeguarded Newton iteration on it costs a few operations per row.  If no row switched state along
-// the step, the step ended on the minimiser of the quadratic piece it started in and the solve is finished.
-//
-// Two number types.  TC is the kernel's own (float on the device): constants, the substep's inputs, the contact geometry
-// and Jacobians.  The SOLVE (residuals, gradient, Hessian, Cholesky, line search) runs in double: the Hessian
-// M + sum D J J' mixes a stiffness of ~250 with an inertia of 0.1, so a float solve leaves ~1e-3 of every step in the
-// soft directions; measured on 1 024 envs x 16 steps against the fp64 oracle (tools/contact_precision.py): float solve
-// p99.9 |dq| 5.7e-4 rad, double solve 2.7e-7.  B200 issues DFMA at half the FFMA rate.
-//
-// s, c must be ACCURATE sin / cos of the joint angles (not MUFU's): a resting contact penetrates ~2e-7 m.
-// Returns the number of gradient/Hessian evaluations (0: no corner is below the floor), negated if the iteration cap
-// was hit or the Hessian was not positive definite; *overflow is set if more than Store::kMaxCon corners penetrated
-// (the solve is then not attempted with this store: the caller retries with a larger one).
+// Kinematics of the contact path: world frames of the links from ACCURATE sin / cos, the pads' penetrating corners
+// (MuJoCo mjc_PlaneBox), and per contact its three Jacobian rows and row parameters written into the store.
+// Returns the number of contacts; -1 (and nothing usable in the store) if more than Store::kMaxCon corners penetrate.
 template <typename TC, typename Store>
-SO_HD int contact_newton(const DynC<TC>& C, const KinC<TC>& Kc, const PadC<TC>& P, const ConC<TC>& K, Store& S, const TC* s, const TC* c,
-                         const TC* q, const TC* qc, const TC* qd, const TC* M, const TC* b, TC* a, unsigned pad_mask, bool exact_in,
-                         int* overflow, int* ls_evals) {
-  typedef double T;
+SO_HD int contact_setup(const DynC<TC>& C, const KinC<TC>& Kc, const PadC<TC>& P, Store& S, const TC* s, const TC* c, const TC* qd,
+                        unsigned pad_mask) {
   constexpr int NC = Store::kMaxCon;
   int nc = 0;
   {
@@ -663,7 +647,7 @@ SO_HD int contact_newton(const DynC<TC>& C, const KinC<TC>& Kc, const PadC<TC>& 
           if (dist > TC(0) || ld > TC(0)) continue;
           found++;
           if (!(dist < TC(0))) continue;  // in the gap: detected, not instantiated
-          if (nc >= NC) { *overflow = 1; return 0; }
+          if (nc >= NC) return -1;
           const TC px = cw[0] + s0 * h[0][0] + s1 * h[1][0] + s2 * h[2][0], py = cw[1] + s0 * h[0][1] + s1 * h[1][1] + s2 * h[2][1],
                    pz = TC(0.5) * dist;  // corner - n dist / 2
           // point Jacobian, columns j <= i:  z_j x (pos - o_j);  velocity of the point
@@ -690,6 +674,33 @@ SO_HD int contact_newton(const DynC<TC>& C, const KinC<TC>& Kc, const PadC<TC>& 
       }
     }
   }
+  return nc;
+}
+
+// qacc of an env whose pads touch the floor: primal Newton on the full convex problem
+//   min_a  1/2 a'Ma - b'a + sum_j [friction_j(a_j) + limit_j(a_j)] + sum_contacts sum_4 rows  D/2 min(0, J a - aref)^2
+// with the exact generalised Hessian, a Cholesky solve per iteration, and an exact line search: phi'(alpha) along the
+// Newton direction is piecewise linear and increasing, and it is evaluated from stored row residuals and slopes (no
+// Jacobians), so a safeguarded Newton iteration on it costs a few operations per row.  If no row switched state along
+// the step, the step ended on the minimiser of the quadratic piece it started in and the solve is finished.
+//
+// Two number types.  TC is the kernel's own (float on the device): constants, the substep's inputs, the contact geometry
+// and Jacobians.  The SOLVE (residuals, gradient, Hessian, Cholesky, line search) runs in double: the Hessian
+// M + sum D J J' mixes a stiffness of ~250 with an inertia of 0.1, so a float solve leaves ~1e-3 of every step in the
+// soft directions; measured on 1 024 envs x 16 steps against the fp64 oracle (tools/contact_precision.py): float solve
+// p99.9 |dq| 5.7e-4 rad, double solve 2.7e-7.  B200 issues DFMA at half the FFMA rate.
+//
+// s, c must be ACCURATE sin / cos of the joint angles (not MUFU's): a resting contact penetrates ~2e-7 m.
+// Returns the number of gradient/Hessian evaluations (0: no corner is below the floor), negated if the iteration cap
+// was hit or the Hessian was not positive definite; *overflow is set if more than Store::kMaxCon corners penetrated
+// (the solve is then not attempted with this store: the caller retries with a larger one).
+template <typename TC, typename Store>
+SO_HD int contact_newton(const DynC<TC>& C, const KinC<TC>& Kc, const PadC<TC>& P, const ConC<TC>& K, Store& S, const TC* s, const TC* c,
+                         const TC* q, const TC* qc, const TC* qd, const TC* M, const TC* b, TC* a, unsigned pad_mask, bool exact_in,
+                         int* overflow, int* ls_evals) {
+  typedef double T;
+  const int nc = contact_setup<TC>(C, Kc, P, S, s, c, qd, pad_mask);
+  if (nc < 0) { *overflow = 1; return 0; }
   if (nc == 0) return 0;
 #if defined(SO100_CONTACT_EXP) && SO100_CONTACT_EXP == 1
   return 1;
@@ -876,3 +887,402 @@ SO_NOINLINE int contact_solve(const DynC<TC>& C, const KinC<TC>& Kc, const PadC<
   if (over && overflow) *overflow = 1;
   return over ? -1 : st;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The contact solve spread over a GROUP of lanes.  contact_newton above is one thread's serial chain of ~30 k
+// instructions per solve, sixteen of them in a row per env step, with one or two such warps per SM: nothing hides its
+// latency (DESIGN.md "Arm-floor contact").  Here the same Newton iteration runs on kCoopLanes lanes per env: the lanes
+// split the contacts (residuals, activity, slopes, line-search rows), the 21 Hessian entries, the 6 gradient entries and
+// the rows of M p / M x; one lane does the 6x6 Cholesky.  Lanes only talk through the env's SLOT (shared memory on the
+// device), in phases separated by a group barrier, and every phase is a function of (slot, lane): the device runs the
+// lanes of a phase in parallel, the host (tests, so100_host_substeps) runs them one after the other and gets
+// bit-identical numbers.
+//
+// A slot is self-contained (the solve reads nothing else): it is filled by the env's own thread (coop_fill: accurate
+// kinematics, contact enumeration, Jacobians, row parameters, the substep's M, b, per-dof rows and warm start).
+constexpr int kCoopLanes = 8;
+constexpr int kCoopCon = 8;  // contacts per slot (== kCoopLanes: one lane per contact)
+
+struct CoopSlot {  // slot-major storage: consecutive words of one slot are consecutive in memory (the lanes of a group read different words)
+  float* f;
+  double* d;
+  // float words
+  static constexpr int kJ = 0, kPar = kJ + kCoopCon * 18, kM = kPar + kCoopCon * 4, kB = kM + 21, kAf = kB + 6, kXl = kAf + 6, kSDl = kXl + 6,
+                       kX0 = kSDl + 6, kFrD = kX0 + 6, kFrL = kFrD + 6, kMu = kFrL + 6, kNc = kMu + 1, kAct = kNc + 1, kFloats = kAct + kCoopCon;
+  // double words
+  static constexpr int kX = 0, kG = 6, kP = 12, kH = 18, kRes = 39, kDiag = kRes + kCoopCon * 6, kRed = kDiag + 6, kSc = kRed + kCoopLanes * 2,
+                       kDoubles = kSc + 12;
+  static_assert(kFloats % 2 == 1 && kDoubles % 2 == 1, "odd slot sizes spread the slots of a warp over the shared-memory banks");
+  SO_HD float& F(int w) const { return f[w]; }
+  SO_HD double& D(int w) const { return d[w]; }
+  SO_HD float& J(int c, int axis, int j) const { return f[kJ + (c * 3 + axis) * 6 + j]; }
+  SO_HD float& par(int c, int m) const { return f[kPar + c * 4 + m]; }
+  SO_HD double& res(int c, int m) const { return d[kRes + c * 6 + m]; }
+  SO_HD double& sc(int k) const { return d[kSc + k]; }
+};
+// sc[10]: state of the solve (0 running, 1 converged, 2 failed: Hessian not positive definite / iteration cap)
+
+// the store interface of contact_setup over a slot
+struct CoopStore {
+  static constexpr int kMaxCon = kCoopCon;
+  CoopSlot s;
+  SO_HD float& J(int c, int axis, int j) { return s.J(c, axis, j); }
+  SO_HD float& par(int c, int m) { return s.par(c, m); }
+};
+
+// Fill a slot (the env's own thread).  Returns the number of contacts: 0 = the accurate kinematics found no corner below
+// the floor (no solve), -1 = more than kCoopCon corners (the caller takes the out-of-line serial solve).
+SO_HD int coop_fill(const DynC<float>& C, const KinC<float>& Kc, const PadC<float>& P, const ConC<float>& K, const CoopSlot& S, const float* s,
+                    const float* c, const float* q, const float* qc, const float* qd, const float* M, const float* b, const float* a0,
+                    unsigned pad_mask) {
+  CoopStore st{S};
+  const int nc = contact_setup<float>(C, Kc, P, st, s, c, qd, pad_mask);
+  S.F(CoopSlot::kNc) = (float)(nc > 0 ? nc : 0);
+  if (nc <= 0) return nc;
+#pragma unroll
+  for (int k = 0; k < 21; k++) S.F(CoopSlot::kM + k) = M[k];
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) {
+    float xl = 0.0f, sDl = 0.0f;
+    if ((q[j] - K.lo[j]) - qc[j] < 0.0f || (K.hi[j] - q[j]) + qc[j] < 0.0f) {
+      float rm2, kap2;
+      limit_row(K, j, M[midx(j, j)], q[j], qc[j], qd[j], xl, sDl, rm2, kap2);
+    }
+    S.F(CoopSlot::kB + j) = b[j]; S.F(CoopSlot::kAf + j) = -K.fr_B[j] * qd[j]; S.F(CoopSlot::kXl + j) = xl; S.F(CoopSlot::kSDl + j) = sDl;
+    S.F(CoopSlot::kX0 + j) = a0[j]; S.F(CoopSlot::kFrD + j) = K.fr_D[j]; S.F(CoopSlot::kFrL + j) = K.fr_loss[j];
+  }
+  S.F(CoopSlot::kMu) = P.mu;
+  return nc;
+}
+
+// ---- phases.  `lane` in [0, kCoopLanes).  P1-P3 and P7 exchange through the slot (a group barrier after each); P4 and
+// the line search keep their rows in the lane's registers (CoopLane) and exchange through butterfly reductions over the
+// group's lanes (coop_sum / coop_max / coop_all: shuffles on the device, loops on the host - the same additions in the
+// same order, and a + b == b + a, so every lane ends with the same bits).
+//
+// P1: lane = contact: residuals at x, the rows' activity and the contact's gradient coefficients;
+//     lane = dof: x (first iteration: the warm start), smooth + per-dof part of the gradient, per-dof curvature
+SO_HD void coop_p1(const CoopSlot& S, int lane, bool first) {
+  const int nc = (int)S.F(CoopSlot::kNc);
+  const double mu = (double)S.F(CoopSlot::kMu);
+  double x[SO_NJ];
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) x[j] = first ? (double)S.F(CoopSlot::kX0 + j) : S.D(CoopSlot::kX + j);
+  if (lane < nc) {
+    double jz = 0.0, jy = 0.0, jx = 0.0;
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) { jz += (double)S.J(lane, 0, j) * x[j]; jy += (double)S.J(lane, 1, j) * x[j]; jx += (double)S.J(lane, 2, j) * x[j]; }
+    const double e = jz - (double)S.par(lane, 0), ty = mu * jy + (double)S.par(lane, 1), tx = mu * jx + (double)S.par(lane, 2), D = (double)S.par(lane, 3);
+    const double r1 = e + ty, r2 = e - ty, r3 = e + tx, r4 = e - tx;
+    const double a1 = r1 < 0.0 ? 1.0 : 0.0, a2 = r2 < 0.0 ? 1.0 : 0.0, a3 = r3 < 0.0 ? 1.0 : 0.0, a4 = r4 < 0.0 ? 1.0 : 0.0;
+    S.res(lane, 0) = e; S.res(lane, 1) = ty; S.res(lane, 2) = tx;
+    S.res(lane, 3) = D * (a1 * r1 + a2 * r2 + a3 * r3 + a4 * r4); S.res(lane, 4) = D * mu * (a1 * r1 - a2 * r2); S.res(lane, 5) = D * mu * (a3 * r3 - a4 * r4);
+    S.F(CoopSlot::kAct + lane) = (float)((r1 < 0.0 ? 1 : 0) | (r2 < 0.0 ? 2 : 0) | (r3 < 0.0 ? 4 : 0) | (r4 < 0.0 ? 8 : 0));
+  }
+  if (lane < SO_NJ) {
+    const int i = lane;
+    double v = -(double)S.F(CoopSlot::kB + i);
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) v += (double)S.F(CoopSlot::kM + (j <= i ? midx(i, j) : midx(j, i))) * x[j];
+    double xi = x[0];
+#pragma unroll
+    for (int j = 1; j < SO_NJ; j++) xi = j == i ? x[j] : xi;
+    const double fD = (double)S.F(CoopSlot::kFrD + i), fL = (double)S.F(CoopSlot::kFrL + i);
+    const double t = fD * (xi - (double)S.F(CoopSlot::kAf + i));  // Huber friction row: force -clamp(D r, +-loss)
+    double cv = 0.0;
+    if (t > -fL && t < fL) { v += t; cv = fD; }
+    else v += t < 0.0 ? -fL : fL;
+    const double sd = (double)S.F(CoopSlot::kSDl + i), xl = (double)S.F(CoopSlot::kXl + i);
+    if (sd != 0.0 && sd * (xi - xl) < 0.0) { const double Dl = sd < 0.0 ? -sd : sd; v += Dl * (xi - xl); cv += Dl; }  // limit row active
+    S.D(CoopSlot::kG + i) = v;
+    S.D(CoopSlot::kDiag + i) = cv;
+    if (first) S.D(CoopSlot::kX + i) = xi;
+  }
+  if (first && lane == kCoopLanes - 1) S.sc(10) = 0.0;
+}
+// P2: the generalised Hessian's 21 entries over the lanes, and the contacts' part of the gradient (lane = dof)
+SO_HD void coop_p2(const CoopSlot& S, int lane) {
+  const int nc = (int)S.F(CoopSlot::kNc);
+  const double mu = (double)S.F(CoopSlot::kMu);
+  int ei[3], ej[3];
+  double h[3];
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    const int k = lane + m * kCoopLanes;  // entry k = midx(i, j); k >= 21: this lane has no m-th entry
+    int i = 0;
+#pragma unroll
+    for (int r = 1; r < SO_NJ; r++) i += (k >= midx(r, 0)) ? 1 : 0;
+    ei[m] = i; ej[m] = k < 21 ? k - midx(i, 0) : 0;
+    h[m] = k < 21 ? (double)S.F(CoopSlot::kM + k) + (i == ej[m] ? S.D(CoopSlot::kDiag + i) : 0.0) : 0.0;
+  }
+  double g = lane < SO_NJ ? S.D(CoopSlot::kG + lane) : 0.0;
+  const int gl = lane < SO_NJ ? lane : 0;
+  for (int c = 0; c < nc; c++) {
+    const int act = (int)S.F(CoopSlot::kAct + c);
+    if (act == 0) continue;
+    const double D = (double)S.par(c, 3), Dm = D * mu, Dmm = Dm * mu;
+    const double a1 = (act & 1) ? 1.0 : 0.0, a2 = (act & 2) ? 1.0 : 0.0, a3 = (act & 4) ? 1.0 : 0.0, a4 = (act & 8) ? 1.0 : 0.0;
+    const double hzz = D * (a1 + a2 + a3 + a4), hzy = Dm * (a1 - a2), hyy = Dmm * (a1 + a2), hzx = Dm * (a3 - a4), hxx = Dmm * (a3 + a4);
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const double zi = S.J(c, 0, ei[m]), yi = S.J(c, 1, ei[m]), xi = S.J(c, 2, ei[m]), zj = S.J(c, 0, ej[m]), yj = S.J(c, 1, ej[m]), xj = S.J(c, 2, ej[m]);
+      h[m] += (hzz * zi + hzy * yi + hzx * xi) * zj + (hzy * zi + hyy * yi) * yj + (hzx * zi + hxx * xi) * xj;
+    }
+    g += S.res(c, 3) * (double)S.J(c, 0, gl) + S.res(c, 4) * (double)S.J(c, 1, gl) + S.res(c, 5) * (double)S.J(c, 2, gl);
+  }
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+    if (lane + m * kCoopLanes < 21) S.D(CoopSlot::kH + lane + m * kCoopLanes) = h[m];
+  if (lane < SO_NJ) S.D(CoopSlot::kG + lane) = g;
+}
+// 1/sqrt(x) to double rounding from the float unit's estimate and two Newton steps (a libm sqrt + divide is ~120 instructions)
+SO_HD double coop_rsqrt(double x) {
+  double y = (double)so_rsqrt((float)x);
+  const double hx = 0.5 * x;
+  y = y * (1.5 - hx * y * y);
+  y = y * (1.5 - hx * y * y);
+  return y;
+}
+// P3 (lane 0): Cholesky in registers and the Newton direction p = -H^-1 g
+SO_HD void coop_p3(const CoopSlot& S, int lane) {
+  if (lane != 0) return;
+  double H[21], y[SO_NJ], p[SO_NJ];
+#pragma unroll
+  for (int k = 0; k < 21; k++) H[k] = S.D(CoopSlot::kH + k);
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) {
+    double dj = H[midx(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; k++) dj -= H[midx(j, k)] * H[midx(j, k)];
+    ok = ok && dj > 0.0;
+    const double rd = coop_rsqrt(dj > 0.0 ? dj : 1.0);
+    H[midx(j, j)] = rd;  // the diagonal holds 1 / L_jj
+#pragma unroll
+    for (int i = j + 1; i < SO_NJ; i++) {
+      double v = H[midx(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) v -= H[midx(i, k)] * H[midx(j, k)];
+      H[midx(i, j)] = v * rd;
+    }
+  }
+  if (!ok) { S.sc(10) = 2.0; return; }
+#pragma unroll
+  for (int i = 0; i < SO_NJ; i++) {
+    double v = -S.D(CoopSlot::kG + i);
+#pragma unroll
+    for (int k = 0; k < i; k++) v -= H[midx(i, k)] * y[k];
+    y[i] = v * H[midx(i, i)];
+  }
+#pragma unroll
+  for (int i = SO_NJ - 1; i >= 0; i--) {
+    double v = y[i];
+#pragma unroll
+    for (int k = i + 1; k < SO_NJ; k++) v -= H[midx(k, i)] * p[k];
+    p[i] = v * H[midx(i, i)];
+  }
+#pragma unroll
+  for (int i = 0; i < SO_NJ; i++) S.D(CoopSlot::kP + i) = p[i];
+}
+
+// one lane's registers from P4 to P7: its rows of the line search (dof `lane`: friction + limit; contact `lane`: four
+// pyramid rows) and the scalars every lane of the group holds identically
+struct CoopLane {
+  double fD, fL, r0, pj, sdl, l0;         // dof rows (fD = 0, sdl = 0: none)
+  double e0, ty0, tx0, se, sty, stx, D;   // contact rows (D = 0: none)
+  double d0, pMp, ds, pmax, xmax;         // P4: this lane's terms; after the reduction: g.p, p'Mp, (Mx - b).p, max |p|, max(1, |x|)
+  double alpha, lo, dlo, hi, dhi;         // line-search bracket
+  int ls;                                 // 0 searching, 1 accepted and no row switched along the step, 2 accepted
+};
+// P4: slopes of this lane's contact residuals along p, its dof rows, and the i-th terms of g.p, p'Mp and (Mx - b).p
+SO_HD void coop_p4(const CoopSlot& S, int lane, CoopLane& L) {
+  const int nc = (int)S.F(CoopSlot::kNc);
+  const double mu = (double)S.F(CoopSlot::kMu);
+  double p[SO_NJ];
+#pragma unroll
+  for (int j = 0; j < SO_NJ; j++) p[j] = S.D(CoopSlot::kP + j);
+  L.e0 = L.ty0 = L.tx0 = L.se = L.sty = L.stx = L.D = 0.0;
+  if (lane < nc) {
+    double jz = 0.0, jy = 0.0, jx = 0.0;
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) { jz += (double)S.J(lane, 0, j) * p[j]; jy += (double)S.J(lane, 1, j) * p[j]; jx += (double)S.J(lane, 2, j) * p[j]; }
+    L.se = jz; L.sty = mu * jy; L.stx = mu * jx;
+    L.e0 = S.res(lane, 0); L.ty0 = S.res(lane, 1); L.tx0 = S.res(lane, 2); L.D = (double)S.par(lane, 3);
+  }
+  L.fD = L.fL = L.r0 = L.pj = L.sdl = L.l0 = 0.0;
+  L.d0 = L.pMp = L.ds = L.pmax = L.xmax = 0.0;
+  if (lane < SO_NJ) {
+    const int i = lane;
+    double v = 0.0, w = -(double)S.F(CoopSlot::kB + i), pi = p[0], xi = 0.0;
+#pragma unroll
+    for (int j = 0; j < SO_NJ; j++) {
+      const double mij = (double)S.F(CoopSlot::kM + (j <= i ? midx(i, j) : midx(j, i))), xj = S.D(CoopSlot::kX + j);
+      v += mij * p[j]; w += mij * xj;
+      pi = j == i ? p[j] : pi; xi = j == i ? xj : xi;
+    }
+    L.d0 = S.D(CoopSlot::kG + i) * pi; L.pMp = pi * v; L.ds = w * pi;
+    L.pmax = pi < 0.0 ? -pi : pi; L.xmax = xi < 0.0 ? -xi : xi;
+    L.fD = (double)S.F(CoopSlot::kFrD + i); L.fL = (double)S.F(CoopSlot::kFrL + i); L.r0 = xi - (double)S.F(CoopSlot::kAf + i); L.pj = pi;
+    L.sdl = (double)S.F(CoopSlot::kSDl + i); L.l0 = xi - (double)S.F(CoopSlot::kXl + i);
+  }
+}
+// after the reduction of P4's terms: start the line search at alpha = 1.  Returns false if x is stationary to rounding.
+SO_HD bool coop_ls_begin(CoopLane& L) {
+  L.xmax = L.xmax > 1.0 ? L.xmax : 1.0;
+  L.alpha = 1.0; L.lo = 0.0; L.dlo = L.d0; L.hi = -1.0; L.dhi = 0.0; L.ls = 0;
+  return L.d0 < 0.0;
+}
+// this lane's share of phi'(alpha), phi''(alpha) and of "every row is in the state it had at alpha = 0"
+SO_HD void coop_ls_eval(const CoopLane& L, double& d, double& cv, bool& same) {
+  const double al = L.alpha;
+  d = 0.0; cv = 0.0; same = true;
+  {
+    const double t0 = L.fD * L.r0, t = L.fD * (L.r0 + al * L.pj);
+    const bool q0 = t0 > -L.fL && t0 < L.fL, q1 = t > -L.fL && t < L.fL;
+    if (q1) { d += t * L.pj; cv += L.fD * L.pj * L.pj; }
+    else d += (t < 0.0 ? -L.fL : L.fL) * L.pj;
+    same = same && (q0 == q1) && (q1 || ((t0 < 0.0) == (t < 0.0)));
+    if (L.sdl != 0.0) {
+      const double l1 = L.l0 + al * L.pj;
+      const bool b0 = L.sdl * L.l0 < 0.0, b1 = L.sdl * l1 < 0.0;
+      if (b1) { const double Dl = L.sdl < 0.0 ? -L.sdl : L.sdl; d += Dl * l1 * L.pj; cv += Dl * L.pj * L.pj; }
+      same = same && (b0 == b1);
+    }
+  }
+  {
+    const double e = L.e0 + al * L.se, ty = L.ty0 + al * L.sty, tx = L.tx0 + al * L.stx;
+    const double r[4] = {e + ty, e - ty, e + tx, e - tx}, r00[4] = {L.e0 + L.ty0, L.e0 - L.ty0, L.e0 + L.tx0, L.e0 - L.tx0},
+                 sl[4] = {L.se + L.sty, L.se - L.sty, L.se + L.stx, L.se - L.stx};
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      if (r[m] < 0.0) { d += L.D * r[m] * sl[m]; cv += L.D * sl[m] * sl[m]; }
+      same = same && ((r[m] < 0.0) == (r00[m] < 0.0));
+    }
+  }
+}
+// (every lane, identically) with the reduced phi', phi'' and flag: accept alpha, or the next alpha of the safeguarded
+// Newton iteration on phi' (piecewise linear and increasing: Newton is exact within a piece)
+SO_HD void coop_ls_decide(CoopLane& L, double dsum, double cvsum, bool same, double lstol, double atol_, int ls_iter) {
+  const double alpha = L.alpha, d = L.ds + alpha * L.pMp + dsum, cv = L.pMp + cvsum;
+  const double ad = d < 0.0 ? -d : d;
+  bool done = ad <= lstol * -L.d0 || ls_iter >= 23;
+  if (!done) {
+    if (d < 0.0) { L.lo = alpha; L.dlo = d; } else { L.hi = alpha; L.dhi = d; }
+    double an = alpha - d / cv;  // exact if no row switches in between
+    const bool inside = an > L.lo && (L.hi < 0.0 || an < L.hi);
+    if (!inside) an = L.hi < 0.0 ? 2.0 * alpha : L.lo + (L.hi - L.lo) * (-L.dlo) / (L.dhi - L.dlo);
+    const double da = an - alpha;
+    L.alpha = an;
+    if ((da < 0.0 ? -da : da) <= atol_ * an) { done = true; same = false; }  // alpha converged to rounding: the flag belongs to the previous point
+  }
+  if (done) L.ls = same ? 1 : 2;
+}
+// P7: take the step (lane = dof).  Returns (every lane, identically) whether the solve is finished: the minimiser of the
+// quadratic piece x started in was reached without any row switching state, or the step is below the tolerance.
+SO_HD bool coop_p7(const CoopSlot& S, int lane, const CoopLane& L, double tol) {
+  if (lane < SO_NJ) S.D(CoopSlot::kX + lane) += L.alpha * L.pj;
+  return L.ls == 1 || L.alpha * L.pmax <= tol * L.xmax;
+}
+
+struct CoopTol { double tol, lstol, atol_; };
+SO_HD CoopTol coop_tolerances() { return CoopTol{1e-9, 1e-8, 1e-10}; }  // fp32 inputs (contact_newton's exact_in = false)
+constexpr int kCoopMaxIter = 30, kCoopMaxLs = 24;
+
+// host: the phases with the lanes in sequence, the reductions as the device's butterflies.  Returns the number of
+// gradient/Hessian evaluations, negated if the solve did not converge (iteration cap, indefinite Hessian).
+inline void coop_host_sum(double* v) {
+  for (int k = 1; k < kCoopLanes; k <<= 1) { double t[kCoopLanes]; for (int l = 0; l < kCoopLanes; l++) t[l] = v[l] + v[l ^ k]; for (int l = 0; l < kCoopLanes; l++) v[l] = t[l]; }
+}
+inline void coop_host_max(double* v) {
+  for (int k = 1; k < kCoopLanes; k <<= 1) { double t[kCoopLanes]; for (int l = 0; l < kCoopLanes; l++) t[l] = v[l] > v[l ^ k] ? v[l] : v[l ^ k]; for (int l = 0; l < kCoopLanes; l++) v[l] = t[l]; }
+}
+inline int coop_solve_host(const CoopSlot& S, int* ls_evals = nullptr) {
+  const CoopTol T = coop_tolerances();
+  CoopLane L[kCoopLanes];
+  int evals = 0, nls = 0;
+  bool conv = false;
+  for (int it = 0; it < kCoopMaxIter && !conv; it++) {
+    for (int l = 0; l < kCoopLanes; l++) coop_p1(S, l, it == 0);
+    for (int l = 0; l < kCoopLanes; l++) coop_p2(S, l);
+    for (int l = 0; l < kCoopLanes; l++) coop_p3(S, l);
+    evals++;
+    if (S.sc(10) != 0.0) break;
+    for (int l = 0; l < kCoopLanes; l++) coop_p4(S, l, L[l]);
+    {
+      double a[kCoopLanes], b[kCoopLanes], c[kCoopLanes], d[kCoopLanes], e[kCoopLanes];
+      for (int l = 0; l < kCoopLanes; l++) { a[l] = L[l].d0; b[l] = L[l].pMp; c[l] = L[l].ds; d[l] = L[l].pmax; e[l] = L[l].xmax; }
+      coop_host_sum(a); coop_host_sum(b); coop_host_sum(c); coop_host_max(d); coop_host_max(e);
+      for (int l = 0; l < kCoopLanes; l++) { L[l].d0 = a[l]; L[l].pMp = b[l]; L[l].ds = c[l]; L[l].pmax = d[l]; L[l].xmax = e[l]; }
+    }
+    bool descent = true;
+    for (int l = 0; l < kCoopLanes; l++) descent = coop_ls_begin(L[l]);
+    if (!descent) { conv = true; break; }  // stationary to rounding
+    for (int ls = 0; ls < kCoopMaxLs && L[0].ls == 0; ls++) {
+      double d[kCoopLanes], cv[kCoopLanes];
+      bool same = true;
+      for (int l = 0; l < kCoopLanes; l++) { bool s1; coop_ls_eval(L[l], d[l], cv[l], s1); same = same && s1; }
+      coop_host_sum(d); coop_host_sum(cv);
+      for (int l = 0; l < kCoopLanes; l++) coop_ls_decide(L[l], d[l], cv[l], same, T.lstol, T.atol_, ls);
+      nls++;
+    }
+    for (int l = 0; l < kCoopLanes; l++) conv = coop_p7(S, l, L[l], T.tol);
+  }
+  if (S.sc(10) == 0.0) S.sc(10) = conv ? 1.0 : 2.0;
+  if (ls_evals) *ls_evals = nls;
+  return S.sc(10) == 1.0 ? evals : -evals;
+}
+
+#ifdef __CUDACC__
+// device: one WARP runs the solves of four slots in lockstep, kCoopLanes lanes each (sf == nullptr: this group has no
+// slot).  All control flow is warp-uniform - a group that is finished, or waiting for the others' line searches, skips the
+// phase bodies - so the four solves cost the longest of them, not their sum (groups that diverge are serialised by the
+// hardware).  Out of line: the solve's registers are its own (the caller is the step kernel at its 128-register cap).
+__device__ __forceinline__ double coop_shfl_xor(double v, int k) { return __shfl_xor_sync(0xffffffffu, v, k); }
+__device__ __forceinline__ double coop_sum(double v) {
+#pragma unroll
+  for (int k = 1; k < kCoopLanes; k <<= 1) v += coop_shfl_xor(v, k);
+  return v;
+}
+__device__ __forceinline__ double coop_max(double v) {
+#pragma unroll
+  for (int k = 1; k < kCoopLanes; k <<= 1) { const double o = coop_shfl_xor(v, k); v = v > o ? v : o; }
+  return v;
+}
+__device__ __noinline__ void coop_solve_warp(float* sf, double* sd, int lane, int gshift) {
+  const CoopSlot S{sf, sd};
+  const CoopTol T = coop_tolerances();
+  bool active = sf != nullptr, conv = false;
+  CoopLane L;
+  for (int it = 0; it < kCoopMaxIter; it++) {
+    if (!__any_sync(0xffffffffu, active)) break;
+    if (active) coop_p1(S, lane, it == 0);
+    __syncwarp();
+    if (active) coop_p2(S, lane);
+    __syncwarp();
+    if (active) coop_p3(S, lane);
+    __syncwarp();
+    if (active && S.sc(10) != 0.0) active = false;  // Hessian not positive definite
+    if (active) coop_p4(S, lane, L);
+    else { L.d0 = L.pMp = L.ds = L.pmax = L.xmax = 0.0; L.fD = L.fL = L.r0 = L.pj = L.sdl = L.l0 = 0.0; L.e0 = L.ty0 = L.tx0 = L.se = L.sty = L.stx = L.D = 0.0; }
+    L.d0 = coop_sum(L.d0); L.pMp = coop_sum(L.pMp); L.ds = coop_sum(L.ds); L.pmax = coop_max(L.pmax); L.xmax = coop_max(L.xmax);
+    const bool descent = coop_ls_begin(L);
+    if (active && !descent) { active = false; conv = true; }  // stationary to rounding
+    if (!active) L.ls = 2;
+    for (int ls = 0; ls < kCoopMaxLs; ls++) {
+      if (!__any_sync(0xffffffffu, L.ls == 0)) break;
+      double d, cv;
+      bool same;
+      coop_ls_eval(L, d, cv, same);
+      d = coop_sum(d); cv = coop_sum(cv);
+      same = ((__ballot_sync(0xffffffffu, same) >> gshift) & 0xffu) == 0xffu;
+      if (L.ls == 0) coop_ls_decide(L, d, cv, same, T.lstol, T.atol_, ls);
+    }
+    if (active) {
+      conv = coop_p7(S, lane, L, T.tol);
+      if (conv) active = false;
+    }
+    __syncwarp();
+  }
+  if (sf != nullptr && lane == 0 && S.sc(10) == 0.0) S.sc(10) = conv ? 1.0 : 2.0;
+}
+#endif
