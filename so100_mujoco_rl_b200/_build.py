@@ -9,7 +9,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libso100_b200.so")
 SOURCES = ["so100_b200.cu"]
-HEADERS = ["so100_dyn.cuh", "so100_dyn_gen.cuh", "so100_ppo_kernels.cuh", os.path.join("..", "..", "include", "so100_b200.h"),
+HEADERS = ["so100_dyn.cuh", "so100_dyn_gen.cuh", "so100_ppo_kernels.cuh", "so100_tc.cuh", os.path.join("..", "..", "include", "so100_b200.h"),
            os.path.join("..", "..", "include", "so100_ppo.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -18,6 +18,7 @@
 // partials; a second kernel adds the partials in a fixed order, so the result is deterministic.  A tcgen05 / TMEM
 // version is the step after this one.
 #pragma once
+#include "so100_tc.cuh"
 
 namespace ppo {
 
@@ -256,6 +257,201 @@ __global__ void __launch_bounds__(NT) act_kernel(Layout L, const float* __restri
       if (value) value[g] = out[7 * TB + tid];
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------ rollout inference, tcgen05
+// The same computation on the 5th-generation tensor cores (csrc/so100_tc.cuh): tiles of 128 samples, D[sample][feature] =
+// act[sample][k] W[feature][k] issued by ONE thread as tcgen05.mma kind::tf32 with M = 128, the accumulator in TMEM, and
+// the 3xTF32 split done ONCE per value when it is written to shared memory (hi and lo copies of every operand in the
+// no-swizzle K-major layout) instead of at every fragment load.  Thread r of a warpgroup owns TMEM lane r = sample r of the
+// tile: it reads its row with tcgen05.ld, adds the bias, applies tanh and writes the row of the next layer's A operand
+// as float4 stores; the two warpgroups split the 64 columns.  Per tile and tower: layer 1 (6 MMAs), layer 2 (24), head (24,
+// N = 16); one mbarrier, committed after every layer.  One CTA per SM (176 KB of shared memory), persistent.
+constexpr int TM = 128, NTC = 256;
+struct ActTc {  // byte offsets into dynamic shared memory
+  static constexpr int W1 = 0;                         // [tower][hi, lo][64 x 16]
+  static constexpr int W2 = W1 + 2 * 2 * 64 * 16 * 4;  // [tower][hi, lo][64 x 64]
+  static constexpr int W3 = W2 + 2 * 2 * 64 * 64 * 4;  // [tower][hi, lo][16 x 64]
+  static constexpr int X = W3 + 2 * 2 * 16 * 64 * 4;   // [hi, lo][128 x 16]
+  static constexpr int H = X + 2 * TM * 16 * 4;        // [hi, lo][128 x 64]
+  static constexpr int BIAS = H + 2 * TM * 64 * 4;     // b1[2][64], b2[2][64], b3[2][8], log_std[8]
+  static constexpr int BAR = BIAS + (2 * 64 + 2 * 64 + 16 + 8) * 4;
+  static constexpr int BYTES = BAR + 16;
+};
+static_assert(ActTc::BYTES <= 227 * 1024, "act_kernel_tc: shared memory");
+
+// one layer's epilogue for this thread's half of the 64 columns: h = tanh(D + bias) -> the A operand of the next layer
+__device__ __forceinline__ void tc_epilogue_tanh(uint32_t tmem_row, int col0, const float* bias, unsigned char* Hh, unsigned char* Hl, int row) {
+#pragma unroll
+  for (int c0 = col0; c0 < col0 + 32; c0 += 16) {
+    float v[16];
+    tc::tmem_ld16(tmem_row + c0, v);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      float hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) tc::split(tanhf(v[4 * q + i] + bias[c0 + 4 * q + i]), hi[i], lo[i]);
+      const int off = tc::op_offset<TM>(row, c0 + 4 * q);
+      *reinterpret_cast<float4*>(Hh + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(Hl + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+// D (+)= A B^T over K with the 3xTF32 split: small terms first
+template <int NROWS_B, int K>
+__device__ __forceinline__ void tc_gemm3(uint32_t tmem_d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t idesc) {
+#pragma unroll
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    tc::mma_tf32(tmem_d, tc::op_desc<TM>(al, k0 / 4), tc::op_desc<NROWS_B>(bh, k0 / 4), idesc, k0 > 0);
+    tc::mma_tf32(tmem_d, tc::op_desc<TM>(ah, k0 / 4), tc::op_desc<NROWS_B>(bl, k0 / 4), idesc, true);
+    tc::mma_tf32(tmem_d, tc::op_desc<TM>(ah, k0 / 4), tc::op_desc<NROWS_B>(bh, k0 / 4), idesc, true);
+  }
+}
+
+__global__ void __launch_bounds__(NTC, 1) act_kernel_tc(Layout L, const float* __restrict__ P, const float* __restrict__ obs, int n, unsigned seed_lo,
+                                                        unsigned seed_hi, long long env_offset, unsigned tick, int deterministic, float* act_raw,
+                                                        float* act_clip, float* logp, float* value, float* obs_copy) {
+  extern __shared__ __align__(128) unsigned char smc[];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, od = L.od;
+  const int row = tid & (TM - 1), half = tid >> 7;  // TMEM lane = sample of the tile; which 32 of a layer's 64 columns
+  float* bias = reinterpret_cast<float*>(smc + ActTc::BIAS);
+  float *b1 = bias, *b2 = bias + 128, *b3 = bias + 256, *ls = bias + 272;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smc + ActTc::BAR);
+  unsigned char *Xh = smc + ActTc::X, *Xl = Xh + TM * 16 * 4, *Hh = smc + ActTc::H, *Hl = Hh + TM * 64 * 4;
+  auto W1 = [&](int t, int lo) { return smc + ActTc::W1 + (2 * t + lo) * 64 * 16 * 4; };
+  auto W2 = [&](int t, int lo) { return smc + ActTc::W2 + (2 * t + lo) * 64 * 64 * 4; };
+  auto W3 = [&](int t, int lo) { return smc + ActTc::W3 + (2 * t + lo) * 16 * 64 * 4; };
+
+  if (tid == 0) { tc::bar_init(bar, 1); tc::bar_init_fence(); }
+  if (warp == 0) tc::tmem_alloc<256>(&tmem_slot);
+  // weights -> hi / lo operand images (once per CTA)
+  for (int t = 0; t < 2; t++) {
+    const int nout = t == 0 ? ACT : 1;
+    for (int e = tid; e < HID * K1; e += NTC) {
+      const int m = e / K1, k = e % K1;
+      float hi, lo;
+      tc::split(k < od ? P[L.W1[t] + m * od + k] : 0.0f, hi, lo);
+      const int off = tc::op_offset<64>(m, k);
+      *reinterpret_cast<float*>(W1(t, 0) + off) = hi; *reinterpret_cast<float*>(W1(t, 1) + off) = lo;
+    }
+    for (int e = tid; e < HID * HID; e += NTC) {
+      float hi, lo;
+      tc::split(P[L.W2[t] + e], hi, lo);
+      const int off = tc::op_offset<64>(e / HID, e % HID);
+      *reinterpret_cast<float*>(W2(t, 0) + off) = hi; *reinterpret_cast<float*>(W2(t, 1) + off) = lo;
+    }
+    for (int e = tid; e < 16 * HID; e += NTC) {
+      float hi, lo;
+      tc::split(e < nout * HID ? P[L.W3[t] + e] : 0.0f, hi, lo);
+      const int off = tc::op_offset<16>(e / HID, e % HID);
+      *reinterpret_cast<float*>(W3(t, 0) + off) = hi; *reinterpret_cast<float*>(W3(t, 1) + off) = lo;
+    }
+    for (int e = tid; e < HID; e += NTC) { b1[64 * t + e] = P[L.b1[t] + e]; b2[64 * t + e] = P[L.b2[t] + e]; }
+    for (int e = tid; e < 8; e += NTC) b3[8 * t + e] = e < nout ? P[L.b3[t] + e] : 0.0f;
+  }
+  if (tid < 8) ls[tid] = tid < ACT ? P[L.log_std + tid] : 0.0f;
+  for (int e = tid; e < TM * K1; e += NTC) {  // the padding columns of X stay zero for the whole kernel
+    const int off = tc::op_offset<TM>(e / K1, e % K1);
+    *reinterpret_cast<float*>(Xh + off) = 0.0f; *reinterpret_cast<float*>(Xl + off) = 0.0f;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot, tmem_row = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+  const uint32_t xh = tc::smem_u32(Xh), xl = tc::smem_u32(Xl), hh = tc::smem_u32(Hh), hl = tc::smem_u32(Hl);
+  constexpr uint32_t kDa = 0, kDb = 64, kDc = 128;  // TMEM columns: layer 1, layer 2, heads (16 per tower)
+  uint32_t phase = 0;
+  const int ntiles = (n + TM - 1) / TM;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int base = tile * TM;
+    for (int e = tid; e < TM * od; e += NTC) {  // coalesced over the tile's od * 128 observation words
+      const int s = e / od, f = e % od, g = base + s;
+      float v = 0.0f;
+      if (g < n) {
+        v = obs[(size_t)base * od + e];
+        if (obs_copy) obs_copy[(size_t)base * od + e] = v;
+      }
+      float hi, lo;
+      tc::split(v, hi, lo);
+      const int off = tc::op_offset<TM>(s, f);
+      *reinterpret_cast<float*>(Xh + off) = hi; *reinterpret_cast<float*>(Xl + off) = lo;
+    }
+    tc::fence_smem_to_mma();
+    tc::fence_before_sync();
+    __syncthreads();
+#pragma unroll 1
+    for (int t = 1; t >= 0; t--) {  // value tower first, as in act_kernel
+      if (tid == 0) {
+        tc::fence_after_sync();
+        tc_gemm3<64, K1>(tmem + kDa, xh, xl, tc::smem_u32(W1(t, 0)), tc::smem_u32(W1(t, 1)), tc::idesc_tf32(TM, 64));
+        tc::mma_commit(bar);
+      }
+      tc::bar_wait(bar, phase); phase ^= 1;
+      tc::fence_after_sync();
+      tc_epilogue_tanh(tmem_row + kDa, 32 * half, b1 + 64 * t, Hh, Hl, row);
+      tc::fence_smem_to_mma();
+      tc::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc::fence_after_sync();
+        tc_gemm3<64, HID>(tmem + kDb, hh, hl, tc::smem_u32(W2(t, 0)), tc::smem_u32(W2(t, 1)), tc::idesc_tf32(TM, 64));
+        tc::mma_commit(bar);
+      }
+      tc::bar_wait(bar, phase); phase ^= 1;
+      tc::fence_after_sync();
+      tc_epilogue_tanh(tmem_row + kDb, 32 * half, b2 + 64 * t, Hh, Hl, row);  // h2 over h1: the layer-2 MMAs have finished reading it
+      tc::fence_smem_to_mma();
+      tc::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc::fence_after_sync();
+        tc_gemm3<16, HID>(tmem + kDc + 16 * t, hh, hl, tc::smem_u32(W3(t, 0)), tc::smem_u32(W3(t, 1)), tc::idesc_tf32(TM, 16));
+        tc::mma_commit(bar);
+      }
+      tc::bar_wait(bar, phase); phase ^= 1;  // the head has consumed h2: the next tower may overwrite H
+      tc::fence_after_sync();
+      __syncthreads();  // no thread is still polling this phase when the next commit arrives
+    }
+    // heads: warpgroup 0 samples the action from the six means, warpgroup 1 stores the value
+    const int g = base + row;
+    float o16[16];
+    tc::tmem_ld16(tmem_row + kDc + 16 * (half ? 1 : 0), o16);
+    if (g < n) {
+      if (half) {
+        if (value) value[g] = o16[0] + b3[8];
+      } else {
+        float eps[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (!deterministic) {  // 8 standard normals from two Philox blocks (Box-Muller), as act_kernel
+#pragma unroll
+          for (int b = 0; b < 2; b++) {
+            const uint4 r = philox4x32(seed_lo, seed_hi, (unsigned)(env_offset + g), tick, 0x5050u + b, 0u);
+            const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+              const float u1 = ((float)(w[2 * q] >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = (float)(w[2 * q + 1] >> 8) * (1.0f / 16777216.0f);
+              const float rad = sqrtf(-2.0f * logf(u1));
+              float sn, cs;
+              sincospif(2.0f * u2, &sn, &cs);
+              eps[4 * b + 2 * q] = rad * cs; eps[4 * b + 2 * q + 1] = rad * sn;
+            }
+          }
+        }
+        float lp = 0.0f;
+#pragma unroll
+        for (int k = 0; k < ACT; k++) {
+          const float mean = o16[k] + b3[k], a = mean + expf(ls[k]) * eps[k];
+          lp += -0.5f * eps[k] * eps[k] - ls[k] - LOG_SQRT_2PI;
+          if (act_raw) act_raw[(size_t)g * ACT + k] = a;
+          if (act_clip) act_clip[(size_t)g * ACT + k] = fminf(fmaxf(a, -1.0f), 1.0f);
+        }
+        if (logp) logp[g] = lp;
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();  // every thread has read its head row: the next tile may overwrite TMEM and X
+  }
+  if (warp == 0) tc::tmem_free<256>(tmem);
 }
 
 // value tower for single rows, weights from global memory: used where truncations (rare) need V(terminal_obs)
@@ -806,11 +1002,21 @@ int so100_ppo_act(int obs_dim, const float* params, const float* obs, int n, uin
   if (!params || !obs || n <= 0) return fail(SO100_ERR_ARG, "bad argument");
   int rc = ppo_use_device_of(params);
   if (rc) return rc;
-  rc = ppo_smem_optin((const void*)ppo::act_kernel, ppo::kActSmemFloats);
-  if (rc) return rc;
   int dev = 0, sms = 0;
   CU(cudaGetDevice(&dev));
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static const bool use_mma = getenv("SO100_PPO_ACT_MMA") != nullptr;  // A/B knob: the warp-level mma.sync version
+  if (!use_mma) {  // tcgen05 / TMEM: 128-sample tiles, one persistent CTA per SM
+    CU(cudaFuncSetAttribute((const void*)ppo::act_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ppo::ActTc::BYTES));
+    const int ntiles = (n + ppo::TM - 1) / ppo::TM, grid = ntiles < sms ? ntiles : sms;
+    ppo::act_kernel_tc<<<grid, ppo::NTC, ppo::ActTc::BYTES, (cudaStream_t)stream>>>(
+        ppo::make_layout(obs_dim), params, obs, n, (unsigned)(seed & 0xFFFFFFFFull), (unsigned)(seed >> 32), env_offset, tick, deterministic,
+        act_raw, act_clip, logp, value, obs_copy);
+    CU(cudaGetLastError());
+    return SO100_OK;
+  }
+  rc = ppo_smem_optin((const void*)ppo::act_kernel, ppo::kActSmemFloats);
+  if (rc) return rc;
   const int ntiles = (n + ppo::TB - 1) / ppo::TB, grid = ntiles < 2 * sms ? ntiles : 2 * sms;  // 85 KB of shared memory: two CTAs per SM
   ppo::act_kernel<<<grid, ppo::NT, ppo::kActSmemFloats * 4, (cudaStream_t)stream>>>(
       ppo::make_layout(obs_dim), params, obs, n, (unsigned)(seed & 0xFFFFFFFFull), (unsigned)(seed >> 32), env_offset, tick, deterministic,
