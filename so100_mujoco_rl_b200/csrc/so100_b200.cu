@@ -409,6 +409,11 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
           }
         }
       }
+      // every other env: the per-dof Gauss-Seidel, BEFORE the cooperative phase, so that M and b are dead across it
+      if (!solved && myslot < 0) {
+        d = solve_qacc<float>(K, M, b, e.q, e.qc, e.v, e.w, sub == 0 ? SO100_SWEEPS_FIRST : SO100_SWEEPS_REST);
+        solved = true;
+      }
       // Phase B, the whole CTA: groups of kCoopLanes threads run the Newton solves of the filled slots.  Consecutive slots
       // go to different warps (slot = 8 * (group within its warp) + warp), so a few touching envs occupy every scheduler.
       if (pool.nslot) {
@@ -437,7 +442,7 @@ __device__ __forceinline__ void physics(const Consts& C, const Bufs& B, EnvRegs&
         }
       }
     }
-    if (!solved) d = solve_qacc<float>(K, M, b, e.q, e.qc, e.v, e.w, sub == 0 ? SO100_SWEEPS_FIRST : SO100_SWEEPS_REST);
+    if (!PADS) d = solve_qacc<float>(K, M, b, e.q, e.qc, e.v, e.w, sub == 0 ? SO100_SWEEPS_FIRST : SO100_SWEEPS_REST);
     float amax = 1.0f;
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {

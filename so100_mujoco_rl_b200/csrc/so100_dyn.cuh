@@ -984,9 +984,7 @@ SO_HD void coop_p1(const CoopSlot& S, int lane, bool first) {
     double v = -(double)S.F(CoopSlot::kB + i);
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) v += (double)S.F(CoopSlot::kM + (j <= i ? midx(i, j) : midx(j, i))) * x[j];
-    double xi = x[0];
-#pragma unroll
-    for (int j = 1; j < SO_NJ; j++) xi = j == i ? x[j] : xi;
+    const double xi = first ? (double)S.F(CoopSlot::kX0 + i) : S.D(CoopSlot::kX + i);
     const double fD = (double)S.F(CoopSlot::kFrD + i), fL = (double)S.F(CoopSlot::kFrL + i);
     const double t = fD * (xi - (double)S.F(CoopSlot::kAf + i));  // Huber friction row: force -clamp(D r, +-loss)
     double cv = 0.0;
@@ -1043,46 +1041,156 @@ SO_HD double coop_rsqrt(double x) {
   y = y * (1.5 - hx * y * y);
   return y;
 }
-// P3 (lane 0): Cholesky in registers and the Newton direction p = -H^-1 g
+// P3 (lane 0): Cholesky and the Newton direction p = -H^-1 g, written out as straight-line code on named scalars (generated:
+// a loop nest over a local array is not reliably unrolled here, and an array in local memory puts an L1 round trip behind
+// every step of the dependent chain)
 SO_HD void coop_p3(const CoopSlot& S, int lane) {
   if (lane != 0) return;
-  double H[21], y[SO_NJ], p[SO_NJ];
-#pragma unroll
-  for (int k = 0; k < 21; k++) H[k] = S.D(CoopSlot::kH + k);
+  double h0 = S.D(CoopSlot::kH + 0);
+  double h1 = S.D(CoopSlot::kH + 1);
+  double h2 = S.D(CoopSlot::kH + 2);
+  double h3 = S.D(CoopSlot::kH + 3);
+  double h4 = S.D(CoopSlot::kH + 4);
+  double h5 = S.D(CoopSlot::kH + 5);
+  double h6 = S.D(CoopSlot::kH + 6);
+  double h7 = S.D(CoopSlot::kH + 7);
+  double h8 = S.D(CoopSlot::kH + 8);
+  double h9 = S.D(CoopSlot::kH + 9);
+  double h10 = S.D(CoopSlot::kH + 10);
+  double h11 = S.D(CoopSlot::kH + 11);
+  double h12 = S.D(CoopSlot::kH + 12);
+  double h13 = S.D(CoopSlot::kH + 13);
+  double h14 = S.D(CoopSlot::kH + 14);
+  double h15 = S.D(CoopSlot::kH + 15);
+  double h16 = S.D(CoopSlot::kH + 16);
+  double h17 = S.D(CoopSlot::kH + 17);
+  double h18 = S.D(CoopSlot::kH + 18);
+  double h19 = S.D(CoopSlot::kH + 19);
+  double h20 = S.D(CoopSlot::kH + 20);
   bool ok = true;
-#pragma unroll
-  for (int j = 0; j < SO_NJ; j++) {
-    double dj = H[midx(j, j)];
-#pragma unroll
-    for (int k = 0; k < j; k++) dj -= H[midx(j, k)] * H[midx(j, k)];
-    ok = ok && dj > 0.0;
-    const double rd = coop_rsqrt(dj > 0.0 ? dj : 1.0);
-    H[midx(j, j)] = rd;  // the diagonal holds 1 / L_jj
-#pragma unroll
-    for (int i = j + 1; i < SO_NJ; i++) {
-      double v = H[midx(i, j)];
-#pragma unroll
-      for (int k = 0; k < j; k++) v -= H[midx(i, k)] * H[midx(j, k)];
-      H[midx(i, j)] = v * rd;
-    }
-  }
+  ok = ok && h0 > 0.0;
+  h0 = coop_rsqrt(h0 > 0.0 ? h0 : 1.0);  // the diagonal holds 1 / L_00
+  h1 *= h0;
+  h3 *= h0;
+  h6 *= h0;
+  h10 *= h0;
+  h15 *= h0;
+  h2 -= h1 * h1;
+  ok = ok && h2 > 0.0;
+  h2 = coop_rsqrt(h2 > 0.0 ? h2 : 1.0);  // the diagonal holds 1 / L_11
+  h4 -= h3 * h1;
+  h4 *= h2;
+  h7 -= h6 * h1;
+  h7 *= h2;
+  h11 -= h10 * h1;
+  h11 *= h2;
+  h16 -= h15 * h1;
+  h16 *= h2;
+  h5 -= h3 * h3;
+  h5 -= h4 * h4;
+  ok = ok && h5 > 0.0;
+  h5 = coop_rsqrt(h5 > 0.0 ? h5 : 1.0);  // the diagonal holds 1 / L_22
+  h8 -= h6 * h3;
+  h8 -= h7 * h4;
+  h8 *= h5;
+  h12 -= h10 * h3;
+  h12 -= h11 * h4;
+  h12 *= h5;
+  h17 -= h15 * h3;
+  h17 -= h16 * h4;
+  h17 *= h5;
+  h9 -= h6 * h6;
+  h9 -= h7 * h7;
+  h9 -= h8 * h8;
+  ok = ok && h9 > 0.0;
+  h9 = coop_rsqrt(h9 > 0.0 ? h9 : 1.0);  // the diagonal holds 1 / L_33
+  h13 -= h10 * h6;
+  h13 -= h11 * h7;
+  h13 -= h12 * h8;
+  h13 *= h9;
+  h18 -= h15 * h6;
+  h18 -= h16 * h7;
+  h18 -= h17 * h8;
+  h18 *= h9;
+  h14 -= h10 * h10;
+  h14 -= h11 * h11;
+  h14 -= h12 * h12;
+  h14 -= h13 * h13;
+  ok = ok && h14 > 0.0;
+  h14 = coop_rsqrt(h14 > 0.0 ? h14 : 1.0);  // the diagonal holds 1 / L_44
+  h19 -= h15 * h10;
+  h19 -= h16 * h11;
+  h19 -= h17 * h12;
+  h19 -= h18 * h13;
+  h19 *= h14;
+  h20 -= h15 * h15;
+  h20 -= h16 * h16;
+  h20 -= h17 * h17;
+  h20 -= h18 * h18;
+  h20 -= h19 * h19;
+  ok = ok && h20 > 0.0;
+  h20 = coop_rsqrt(h20 > 0.0 ? h20 : 1.0);  // the diagonal holds 1 / L_55
   if (!ok) { S.sc(10) = 2.0; return; }
-#pragma unroll
-  for (int i = 0; i < SO_NJ; i++) {
-    double v = -S.D(CoopSlot::kG + i);
-#pragma unroll
-    for (int k = 0; k < i; k++) v -= H[midx(i, k)] * y[k];
-    y[i] = v * H[midx(i, i)];
-  }
-#pragma unroll
-  for (int i = SO_NJ - 1; i >= 0; i--) {
-    double v = y[i];
-#pragma unroll
-    for (int k = i + 1; k < SO_NJ; k++) v -= H[midx(k, i)] * p[k];
-    p[i] = v * H[midx(i, i)];
-  }
-#pragma unroll
-  for (int i = 0; i < SO_NJ; i++) S.D(CoopSlot::kP + i) = p[i];
+  double y0 = -S.D(CoopSlot::kG + 0);
+  y0 *= h0;
+  double y1 = -S.D(CoopSlot::kG + 1);
+  y1 -= h1 * y0;
+  y1 *= h2;
+  double y2 = -S.D(CoopSlot::kG + 2);
+  y2 -= h3 * y0;
+  y2 -= h4 * y1;
+  y2 *= h5;
+  double y3 = -S.D(CoopSlot::kG + 3);
+  y3 -= h6 * y0;
+  y3 -= h7 * y1;
+  y3 -= h8 * y2;
+  y3 *= h9;
+  double y4 = -S.D(CoopSlot::kG + 4);
+  y4 -= h10 * y0;
+  y4 -= h11 * y1;
+  y4 -= h12 * y2;
+  y4 -= h13 * y3;
+  y4 *= h14;
+  double y5 = -S.D(CoopSlot::kG + 5);
+  y5 -= h15 * y0;
+  y5 -= h16 * y1;
+  y5 -= h17 * y2;
+  y5 -= h18 * y3;
+  y5 -= h19 * y4;
+  y5 *= h20;
+  double p5 = y5;
+  p5 *= h20;
+  double p4 = y4;
+  p4 -= h19 * p5;
+  p4 *= h14;
+  double p3 = y3;
+  p3 -= h13 * p4;
+  p3 -= h18 * p5;
+  p3 *= h9;
+  double p2 = y2;
+  p2 -= h8 * p3;
+  p2 -= h12 * p4;
+  p2 -= h17 * p5;
+  p2 *= h5;
+  double p1 = y1;
+  p1 -= h4 * p2;
+  p1 -= h7 * p3;
+  p1 -= h11 * p4;
+  p1 -= h16 * p5;
+  p1 *= h2;
+  double p0 = y0;
+  p0 -= h1 * p1;
+  p0 -= h3 * p2;
+  p0 -= h6 * p3;
+  p0 -= h10 * p4;
+  p0 -= h15 * p5;
+  p0 *= h0;
+  S.D(CoopSlot::kP + 0) = p0;
+  S.D(CoopSlot::kP + 1) = p1;
+  S.D(CoopSlot::kP + 2) = p2;
+  S.D(CoopSlot::kP + 3) = p3;
+  S.D(CoopSlot::kP + 4) = p4;
+  S.D(CoopSlot::kP + 5) = p5;
 }
 
 // one lane's registers from P4 to P7: its rows of the line search (dof `lane`: friction + limit; contact `lane`: four
@@ -1113,12 +1221,12 @@ SO_HD void coop_p4(const CoopSlot& S, int lane, CoopLane& L) {
   L.d0 = L.pMp = L.ds = L.pmax = L.xmax = 0.0;
   if (lane < SO_NJ) {
     const int i = lane;
-    double v = 0.0, w = -(double)S.F(CoopSlot::kB + i), pi = p[0], xi = 0.0;
+    double v = 0.0, w = -(double)S.F(CoopSlot::kB + i);
+    const double pi = S.D(CoopSlot::kP + i), xi = S.D(CoopSlot::kX + i);
 #pragma unroll
     for (int j = 0; j < SO_NJ; j++) {
-      const double mij = (double)S.F(CoopSlot::kM + (j <= i ? midx(i, j) : midx(j, i))), xj = S.D(CoopSlot::kX + j);
-      v += mij * p[j]; w += mij * xj;
-      pi = j == i ? p[j] : pi; xi = j == i ? xj : xi;
+      const double mij = (double)S.F(CoopSlot::kM + (j <= i ? midx(i, j) : midx(j, i)));
+      v += mij * p[j]; w += mij * S.D(CoopSlot::kX + j);
     }
     L.d0 = S.D(CoopSlot::kG + i) * pi; L.pMp = pi * v; L.ds = w * pi;
     L.pmax = pi < 0.0 ? -pi : pi; L.xmax = xi < 0.0 ? -xi : xi;
@@ -1197,7 +1305,9 @@ inline void coop_host_max(double* v) {
   for (int k = 1; k < kCoopLanes; k <<= 1) { double t[kCoopLanes]; for (int l = 0; l < kCoopLanes; l++) t[l] = v[l] > v[l ^ k] ? v[l] : v[l ^ k]; for (int l = 0; l < kCoopLanes; l++) v[l] = t[l]; }
 }
 inline int coop_solve_host(const CoopSlot& S, int* ls_evals = nullptr) {
-  const CoopTol T = coop_tolerances();
+  CoopTol T = coop_tolerances();
+  static const double lstol_env = getenv("SO100_COOP_LSTOL") ? atof(getenv("SO100_COOP_LSTOL")) : 0.0;  // experiments
+  if (lstol_env > 0.0) T.lstol = lstol_env;
   CoopLane L[kCoopLanes];
   int evals = 0, nls = 0;
   bool conv = false;
