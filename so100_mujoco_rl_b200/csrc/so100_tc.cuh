@@ -33,9 +33,14 @@ __device__ __forceinline__ uint64_t op_desc(uint32_t base_addr, int kc0) {
          | ((sbo >> 4) << 32)                // bits [32,46): stride dimension byte offset >> 4
          | (1ull << 46);                     // bits [46,48): descriptor version 1 (sm_100); layout type 0 = no swizzle
 }
-// instruction descriptor: D fp32, A and B tf32, both K-major, M x N
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major operands.  The image above is also the no-swizzle MN-major canonical image of the TRANSPOSED matrix (strides
+// exchanged), which would let every backward product of an MLP read the forward pass's buffers as they are - but kind::tf32
+// does not take it: with either major bit set and a no-swizzle descriptor the MMA writes zeros, whatever the two stride
+// fields say (tools/tcgen05_probe.cu sweeps them; CUTLASS's sm100 builder states the rule: "for mn-major tf32 operands,
+// SW128_32B is the only available smem layout").  Only K-major operands are used here.
+// instruction descriptor: D fp32, A and B tf32, M x N; a_mn / b_mn: the operand is MN-major (default K-major)
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn = false, bool b_mn = false) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] B[smem]^T : one thread issues for the CTA

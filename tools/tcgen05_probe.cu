@@ -117,7 +117,148 @@ static int run(const char* name) {
   return maxerr < tol ? 0 : 1;
 }
 
+// MN-major operands: D[m][n] = sum_k SA[k][m] SB[k][n] with SA ([KT][128]) and SB ([KT][N]) stored as K-major IMAGES of
+// their own shape (rows = k) and read through MN-major descriptors whose two stride fields and K-block step are runtime
+// parameters (the probe tries the candidates).  mode bit 0: A MN-major (else A is given K-major as [128][KT]); bit 1: B
+// MN-major (else K-major [N][KT]); bit 2: M = 64, all 128 TMEM lanes dumped so that the host can say where the rows live.
+__device__ __forceinline__ uint64_t raw_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+template <int N, int KT>
+__global__ void __launch_bounds__(128) probe_mn_kernel(const float* __restrict__ SA, const float* __restrict__ SB, float* __restrict__ D, int mode,
+                                                       uint32_t lbo, uint32_t sbo_a, uint32_t sbo_b, uint32_t kstep) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* Ah = reinterpret_cast<float*>(smem);  // image [KT][128] (MN-major) or [128][KT] (K-major)
+  float* Al = Ah + KT * 128;
+  float* Bh = Al + KT * 128;                   // image [KT][N] or [N][KT]
+  float* Bl = Bh + KT * N;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool amn = mode & 1, bmn = mode & 2, m64 = mode & 4;
+  if (tid == 0) { tc::bar_init(&bar, 1); tc::bar_init_fence(); }
+  if (warp == 0) tc::tmem_alloc<64>(&tmem_slot);
+  for (int e = tid; e < KT * 128; e += 128) {  // SA[k][m]
+    float hi, lo;
+    tc::split(SA[e], hi, lo);
+    const int k = e / 128, m = e % 128;
+    const int off = amn ? tc::op_offset<KT>(k, m) : tc::op_offset<128>(m, k);
+    *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Ah) + off) = hi;
+    *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Al) + off) = lo;
+  }
+  for (int e = tid; e < KT * N; e += 128) {  // SB[k][n]
+    float hi, lo;
+    tc::split(SB[e], hi, lo);
+    const int k = e / N, n = e % N;
+    const int off = bmn ? tc::op_offset<KT>(k, n) : tc::op_offset<N>(n, k);
+    *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Bh) + off) = hi;
+    *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Bl) + off) = lo;
+  }
+  tc::fence_smem_to_mma();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = tc::idesc_tf32(m64 ? 64 : 128, N, amn, bmn);
+    const uint32_t ah = tc::smem_u32(Ah), al = tc::smem_u32(Al), bh = tc::smem_u32(Bh), bl = tc::smem_u32(Bl);
+    for (int kb = 0; kb < KT / 8; kb++) {
+      const uint64_t dah = amn ? raw_desc(ah + kb * kstep, lbo, sbo_a) : tc::op_desc<128>(ah, 2 * kb);
+      const uint64_t dal = amn ? raw_desc(al + kb * kstep, lbo, sbo_a) : tc::op_desc<128>(al, 2 * kb);
+      const uint64_t dbh = bmn ? raw_desc(bh + kb * kstep, lbo, sbo_b) : tc::op_desc<N>(bh, 2 * kb);
+      const uint64_t dbl = bmn ? raw_desc(bl + kb * kstep, lbo, sbo_b) : tc::op_desc<N>(bl, 2 * kb);
+      tc::mma_tf32(tmem, dal, dbh, idesc, kb > 0);
+      tc::mma_tf32(tmem, dah, dbl, idesc, true);
+      tc::mma_tf32(tmem, dah, dbh, idesc, true);
+    }
+    tc::mma_commit(&bar);
+  }
+  tc::bar_wait(&bar, 0);
+  tc::fence_after_sync();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tc::tmem_ld16(tmem + ((uint32_t)(32 * warp) << 16) + c0, v);
+    for (int i = 0; i < 16; i++) D[tid * N + c0 + i] = v[i];
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_free<64>(tmem);
+}
+
+template <int N, int KT>
+static int run_mn(const char* name, int mode, uint32_t lbo, uint32_t sbo_a, uint32_t sbo_b, uint32_t kstep) {
+  std::vector<float> A(KT * 128), B(KT * N), D(128 * N);
+  srand(2);
+  for (auto& x : A) x = (float)rand() / RAND_MAX * 2 - 1;
+  for (auto& x : B) x = (float)rand() / RAND_MAX * 2 - 1;
+  float *dA, *dB, *dD;
+  cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dD, D.size() * 4);
+  cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemset(dD, 0, D.size() * 4);
+  const int smem = (KT * 128 + KT * N) * 2 * 4;
+  cudaFuncSetAttribute(probe_mn_kernel<N, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  probe_mn_kernel<N, KT><<<1, 128, smem>>>(dA, dB, dD, mode, lbo, sbo_a, sbo_b, kstep);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s: CUDA error %s\n", name, cudaGetErrorString(e)); exit(1); }
+  cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+  std::vector<double> R(128 * N);
+  for (int m = 0; m < 128; m++)
+    for (int n = 0; n < N; n++) {
+      double s = 0;
+      for (int k = 0; k < KT; k++) s += (double)A[k * 128 + m] * (double)B[k * N + n];
+      R[m * N + n] = s;
+    }
+  double maxerr = 0;
+  if (!(mode & 4)) {
+    for (int i = 0; i < 128 * N; i++) maxerr = fmax(maxerr, fabs(R[i] - (double)D[i]));
+    int nzq = 0;
+    for (int i = 0; i < 128 * N; i++) nzq += D[i] != 0.0f;
+    if (!(mode & 8) || nzq > 0)
+      printf("%s: mode %d N=%d K=%d lbo %u sbo_a %u sbo_b %u kstep %u  max|err| %.3e nonzero %d %s\n", name, mode, N, KT, lbo, sbo_a, sbo_b, kstep, maxerr,
+             nzq, maxerr < 2e-5 ? "OK" : "");
+    if (maxerr >= 2e-5 && !(mode & 8)) {
+      printf("     D[0][0..5] = %g %g %g %g %g %g   ref %g %g %g %g %g %g\n", D[0], D[1], D[2], D[3], D[4], D[5], R[0], R[1], R[2], R[3], R[4], R[5]);
+      printf("     D[1][0..3] = %g %g %g %g   ref %g %g %g %g;  D[5][0..1] = %g %g ref %g %g\n", D[N], D[N + 1], D[N + 2], D[N + 3], R[N], R[N + 1], R[N + 2], R[N + 3], D[5 * N], D[5 * N + 1], R[5 * N], R[5 * N + 1]);
+      // does D match the product with the image read K-major (i.e. the flag had no effect)?
+      int nz = 0;
+      for (int i = 0; i < 128 * N; i++) nz += D[i] != 0.0f;
+      printf("     nonzero entries of D: %d of %d\n", nz, 128 * N);
+    }
+  } else {  // where did row m go?
+    printf("%s: mode %d N=%d K=%d  row -> TMEM lane:", name, mode, N, KT);
+    int found = 0;
+    for (int m = 0; m < 64; m++) {
+      int where = -1;
+      for (int lane = 0; lane < 128 && where < 0; lane++) {
+        double err = 0;
+        for (int n = 0; n < N; n++) err = fmax(err, fabs(R[m * N + n] - (double)D[lane * N + n]));
+        if (err < 2e-5) where = lane;
+      }
+      if (where >= 0) found++;
+      if (m % 8 == 0) printf(" %d->%d", m, where);
+    }
+    printf("  (%d of 64 rows found)\n", found);
+    maxerr = found == 64 ? 0 : 1;
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  return maxerr < 2e-5 ? 0 : 1;
+}
+
 int main() {
+  // informational (not part of the verdict): where M = 64 puts its rows, and what MN-major no-swizzle operands return
+  run_mn<64, 64>("M64 K-major          ", 4, 0, 0, 0, 0);
+  {  // the image of SA [KT = 64][128]: 4-wide chunks of the operand's M/N index are (KT / 8) * 128 = 1024 B apart, 8-row K groups 128 B
+    const uint32_t big = 1024, small = 128;
+    run_mn<64, 64>("B mn: lbo=K sbo=MN   ", 2, small, big, big, small);
+    run_mn<64, 64>("B mn: lbo=MN sbo=K   ", 2, big, small, small, small);
+    run_mn<64, 64>("A mn: lbo=K sbo=MN   ", 1, small, big, big, small);
+    int any = 0;
+    const uint32_t v[] = {16, 32, 64, 128, 256, 512, 1024, 2048};
+    for (uint32_t lbo : v)
+      for (uint32_t sbo : v) any += run_mn<64, 8>("grid B mn K8", 2 | 8, lbo, sbo, sbo, 128) == 0;
+    printf("MN-major no-swizzle tf32, 64 (lbo, sbo) combinations: %d give the product\n", any);
+  }
   int bad = 0;
   bad += run<64, 64, 0>("tf32      ");
   bad += run<64, 64, 1>("3xtf32    ");
