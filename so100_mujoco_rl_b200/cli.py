@@ -47,6 +47,8 @@ def cli(ctx, algorithm, model_path):
 def train(ctx, environment, num_envs, device, trainer, total_timesteps, n_steps, seed, out, learner_kind, eval_freq, eval_envs,
           eval_steps, save_freq, tensorboard_log):
     algo = ctx.obj["ALGORITHM_NAME"]
+    if trainer != "sb3" and algo != "PPO":  # refuse before anything is created on disk
+        raise click.UsageError("the native trainer implements PPO; use --trainer sb3 for other algorithms")
     folder = os.path.join(out, f"{environment}_{algo}")
     os.makedirs(folder, exist_ok=True)
     if trainer == "sb3":
@@ -58,8 +60,6 @@ def train(ctx, environment, num_envs, device, trainer, total_timesteps, n_steps,
         model.learn(total_timesteps=total_timesteps)
         model.save(os.path.join(folder, "final_model"))
         return
-    if algo != "PPO":
-        raise click.UsageError("the native trainer implements PPO; use --trainer sb3 for other algorithms")
     import torch
     from .batched_env import BatchedSo100Env
     from .callbacks import TrainCallbacks
