@@ -469,10 +469,11 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
   const TaskC& t = C.t;
   const int n = t.n, base = io.env_lo + blockIdx.x * kBlock, hi = io.env_hi;
   const unsigned tick = io.tick;
-  // Envs whose jaw pads touched the floor last step take the (much longer) contact path in most substeps of this one.
-  // They are ~10 % of the envs under random actions, so almost every warp would hold one and wait for it; instead the
-  // CTA re-deals its 256 envs to its threads with the touching ones first (a stable partition on the hint bit), which
-  // confines the contact path to one or two of the eight warps.  `slot` is the env this thread now owns.
+  // Envs whose jaw pads touched the floor last step take the contact path in most substeps of this one (~4-10 % of the
+  // envs under random actions).  The CTA re-deals its 256 envs to its threads with the touching ones first (a stable
+  // partition on the hint bit) and deals those round-robin over W warps: phase A of the contact path (the env's own
+  // thread fills its slot) then costs every warp a few lanes instead of one warp all of its lanes.  `slot` is the env
+  // this thread now owns.
   __shared__ unsigned short perm[kBlock];
   __shared__ int warp_cnt[kBlock / 32];
   __shared__ int pool_cnt[2];
@@ -492,8 +493,7 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
     for (int w = 0; w < kBlock / 32; w++) { const int cw = warp_cnt[w]; total += cw; before += w < wid ? cw : 0; }
     const int rank_t = before + __popc(bal & ((1u << lane) - 1u));           // rank among the touching envs
     int dest = hint ? rank_t : total + ((int)threadIdx.x - rank_t);   // the others keep their order behind them
-    // ... and the first 32 * W positions are dealt round-robin to W warps: W contact warps with 1/W of the touching envs
-    // each (a warp's solve takes as long as its slowest lane, and more contact warps per scheduler hide more latency)
+    // ... and the first 32 * W positions are dealt round-robin to W warps: W contact warps with 1/W of the touching envs each
     const int W = t.contact_warps;
     if (dest < 32 * W) dest = (dest % W) * 32 + dest / W;
     perm[dest] = (unsigned short)threadIdx.x;

@@ -493,7 +493,6 @@ SO_HD void task_kinematics(const DynC<T>& C, const KinC<T>& Kc, const T* s, cons
 // contact_solve() instead.
 #define SO_MAX_PAD 8
 #define SO_MAX_CON 16  // contacts the out-of-line solve keeps (4 per pad possible; > 4 at once is 0.3 % of the touching envs, > 8 unseen)
-#define SO_FAST_CON 8  // ... and a slot of the device's shared-memory pool
 
 template <typename T>
 struct PadC {
@@ -534,11 +533,10 @@ SO_HD unsigned pads_touch(const DynC<T>& C, const KinC<T>& Kc, const PadC<T>& P,
   return touch;
 }
 
-// ---- storage of one contact solve.  The solve keeps, per contact, its three Jacobian rows (float), four parameters
-// (c0, b_y, b_x, D: float), six residual / slope values for the line search (double), and the 6x6 Hessian (double).
-// Two homes: the thread's local memory (host, and the device fallback), or a slot of a shared-memory pool laid out
-// [word][slot] so that the lanes of a warp hit different banks (the device's normal case: local memory would put a
-// ~300-cycle L2 round trip behind every dependent access of a chain that is thousands of instructions long).
+// ---- storage of the SERIAL contact solve (contact_newton: the host's fp64 path and the device's fallback).  It keeps, per
+// contact, its three Jacobian rows (float), four parameters (c0, b_y, b_x, D: float), six residual / slope values for the
+// line search (double), and the 6x6 Hessian (double), in the thread's local memory.  The device's normal path is the
+// cooperative solve further down, whose storage is a CoopSlot in shared memory.
 template <typename TC, int NC>
 struct ContactLocal {
   static constexpr int kMaxCon = NC;
@@ -549,19 +547,6 @@ struct ContactLocal {
   SO_HD double& res(int c, int m) { return rd[c * 6 + m]; }
   SO_HD double& H(int k) { return hd[k]; }
 };
-template <int NC>
-struct ContactShared {  // device only: f = float words, d = double words of the pool, this lane's slot already added
-  static constexpr int kMaxCon = NC;
-  static constexpr int kFloats = NC * 22, kDoubles = NC * 6 + 21;
-  float* f;
-  double* d;
-  int stride;
-  SO_HD float& J(int c, int axis, int j) { return f[((c * 3 + axis) * 6 + j) * stride]; }
-  SO_HD float& par(int c, int m) { return f[(NC * 18 + c * 4 + m) * stride]; }
-  SO_HD double& res(int c, int m) { return d[(c * 6 + m) * stride]; }
-  SO_HD double& H(int k) { return d[(NC * 6 + k) * stride]; }
-};
-
 // In-place Cholesky of the packed lower-triangular 6x6 SPD matrix held by the store, then solve H x = r.
 template <typename T, typename Store>
 SO_HD bool chol_solve6(Store& S, const T* r, T* x) {
@@ -702,9 +687,6 @@ SO_HD int contact_newton(const DynC<TC>& C, const KinC<TC>& Kc, const PadC<TC>& 
   const int nc = contact_setup<TC>(C, Kc, P, S, s, c, qd, pad_mask);
   if (nc < 0) { *overflow = 1; return 0; }
   if (nc == 0) return 0;
-#if defined(SO100_CONTACT_EXP) && SO100_CONTACT_EXP == 1
-  return 1;
-#endif
   // per-dof rows (the ones solve_qacc handles): friction loss, and the limit row of a joint outside its range
   TC af[SO_NJ], xl[SO_NJ], sDl[SO_NJ];
 #pragma unroll
@@ -793,10 +775,6 @@ SO_HD int contact_newton(const DynC<TC>& C, const KinC<TC>& Kc, const PadC<TC>& 
       pmax = ap > pmax ? ap : pmax; xmax = ax > xmax ? ax : xmax;
     }
     if (!(d0 < T(0))) { ok = true; break; }  // stationary to rounding
-#if defined(SO100_CONTACT_EXP) && SO100_CONTACT_EXP == 2
-    for (int j = 0; j < SO_NJ; j++) x[j] += p[j];
-    ok = true; break;
-#endif
     for (int k = 0; k < nc; k++) {  // slopes of the contact residuals along p
       T jx = T(0), jy = T(0), jz = T(0);
 #pragma unroll
@@ -859,9 +837,6 @@ SO_HD int contact_newton(const DynC<TC>& C, const KinC<TC>& Kc, const PadC<TC>& 
     for (int j = 0; j < SO_NJ; j++) x[j] += alpha * p[j];
     // the minimiser of the quadratic piece x started in, reached without any row switching state: done
     ok = same || alpha * pmax <= tol * xmax;
-#if defined(SO100_CONTACT_EXP) && SO100_CONTACT_EXP == 3
-    ok = true;
-#endif
   }
 #pragma unroll
   for (int j = 0; j < SO_NJ; j++) a[j] = (TC)x[j];
