@@ -481,9 +481,10 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
   const ContactPool pool{reinterpret_cast<float*>(pool_mem + (size_t)kPoolSlots * CoopSlot::kDoubles), pool_mem, pool_cnt,
                          PADS && C.pad.n > 0 ? kPoolSlots : 0};
   if (threadIdx.x < 2) pool_cnt[threadIdx.x] = 0;
-  {
+  int slot = threadIdx.x;
+  if (PADS && C.pad.n > 0) {  // (compile-time for the default kernel: thread t owns env t, every access coalesced)
     const int mine = base + (int)threadIdx.x;
-    const bool hint = PADS && C.pad.n > 0 && mine < hi && (B.cnt[n + mine] & F_TOUCH);
+    const bool hint = mine < hi && (B.cnt[n + mine] & F_TOUCH);
     const unsigned bal = __ballot_sync(0xffffffffu, hint);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) warp_cnt[wid] = __popc(bal);
@@ -491,15 +492,31 @@ __global__ void __launch_bounds__(kBlock, SO100_MINBLOCKS) step_kernel(const __g
     int before = 0, total = 0;  // touching envs in earlier warps / in the CTA
 #pragma unroll
     for (int w = 0; w < kBlock / 32; w++) { const int cw = warp_cnt[w]; total += cw; before += w < wid ? cw : 0; }
-    const int rank_t = before + __popc(bal & ((1u << lane) - 1u));           // rank among the touching envs
-    int dest = hint ? rank_t : total + ((int)threadIdx.x - rank_t);   // the others keep their order behind them
-    // ... and the first 32 * W positions are dealt round-robin to W warps: W contact warps with 1/W of the touching envs each
-    const int W = t.contact_warps;
-    if (dest < 32 * W) dest = (dest % W) * 32 + dest / W;
+    const int rank_t = before + __popc(bal & ((1u << lane) - 1u));  // rank among the touching envs
+    // Touching env r goes to lane r / W of warp r % W (W = contact_warps): warp w < W holds c_w = ceil((total - w) / W) of
+    // them in its first lanes.  The other envs fill the remaining lanes in their original order, so their state accesses
+    // stay (piecewise) coalesced.  With fewer than 32 * W positions for the touching ones (never at W = 8) the rest queue
+    // behind them in order as well.
+    const int W = t.contact_warps, cap = 32 * W;
+    int dest;
+    if (hint && rank_t < cap) dest = (rank_t % W) * 32 + rank_t / W;
+    else {
+      const int dealt = total < cap ? total : cap;
+      int k = hint ? (rank_t - cap) : (total - dealt) + ((int)threadIdx.x - rank_t);  // rank among the envs that are not dealt
+      dest = 0;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; w++) {
+        int cw = w < W ? (dealt - w + W - 1) / W : 0;
+        cw = cw < 0 ? 0 : (cw > 32 ? 32 : cw);
+        const int free_w = 32 - cw;
+        if (k >= 0 && k < free_w) dest = w * 32 + cw + k;
+        k -= free_w;
+      }
+    }
     perm[dest] = (unsigned short)threadIdx.x;
+    __syncthreads();
+    slot = perm[threadIdx.x];
   }
-  __syncthreads();
-  const int slot = perm[threadIdx.x];
   const bool live = base + slot < hi;
   const int i = live ? base + slot : hi - 1;  // tail threads shadow the last env (they must reach every barrier); nothing they compute is stored
   // coalesced load of the CTA's action rows through shared memory
