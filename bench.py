@@ -400,11 +400,34 @@ def main():
         pipe_s = time.perf_counter() - t0
         done_rows = float((host["terminated"] | host["truncated"]).sum())
         env.host_groups(1)
+        # (c) what the host link alone could carry: the per-step payloads in both directions at once by copy engine, no
+        # kernel, no dependency between the directions - on every rank at the same time (tools/pcie_bw.py's measurement)
+        link_ms = float("nan")
+        if not args.e2e_device_buffers:
+            in_b, out_b = n * 6 * 4, n * (od * 4 + 6)
+            h_in, h_out = torch.empty(in_b, dtype=torch.uint8).pin_memory(), torch.empty(out_b, dtype=torch.uint8).pin_memory()
+            d_in, d_out = torch.empty(in_b, dtype=torch.uint8, device=dev), torch.empty(out_b, dtype=torch.uint8, device=dev)
+            s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+            def both(reps):
+                for _ in range(reps):
+                    with torch.cuda.stream(s1):
+                        d_in.copy_(h_in, non_blocking=True)
+                    with torch.cuda.stream(s2):
+                        h_out.copy_(d_out, non_blocking=True)
+            both(20)
+            torch.cuda.synchronize(dev)
+            barrier()
+            t0 = time.perf_counter()
+            both(200)
+            torch.cuda.synchronize(dev)
+            link_ms = (time.perf_counter() - t0) / 200 * 1e3
         # bytes per step: actions in; obs + reward + terminated + truncated out, plus the terminal rows
         # (terminal_obs + ep_return + ep_len) of the ~n/max_steps envs whose episode ended in that step
         per_done = od * 4 + 8
         e2e = {"pipe_s": max_over_ranks(pipe_s, dev), "sync_s": max_over_ranks(sync_s, dev), "groups": G, "h2d": n * 6 * 4,
-               "d2h": n * (od * 4 + 4 + 1 + 1) + int(round(n / MAX_EPISODE_STEPS[task])) * per_done, "done_rows_last_step": done_rows}
+               "d2h": n * (od * 4 + 4 + 1 + 1) + int(round(n / MAX_EPISODE_STEPS[task])) * per_done, "done_rows_last_step": done_rows,
+               "link_ms": max_over_ranks(link_ms, dev)}
 
     total_ms = max_over_ranks(total_ms, dev)
 
@@ -535,6 +558,12 @@ def main():
                            "how": f"so100_step_host_async / _wait over {e2e['groups']} env groups in rotation (pinned host buffers in place "
                                   "over the host link; every group's rows are on the host before its next step is issued)",
                            "groups": e2e["groups"]}
+            if e2e["link_ms"] == e2e["link_ms"]:  # (not NaN) the link alone, all ranks copying at once
+                ceiling = total_envs / (e2e["link_ms"] * 1e-3)
+                line["e2e"]["host_link"] = {"ms_per_step_both_directions": e2e["link_ms"], "ceiling_env_steps_per_s": ceiling,
+                                            "frac_of_ceiling": line["e2e"]["value"] / ceiling,
+                                            "how": "per-step payloads H2D and D2H at once by copy engine from / to pinned memory, no kernel, "
+                                                   "every rank at the same time (max over ranks)"}
             line["e2e_sync"] = {"value": total_envs * steps / e2e["sync_s"], "unit": "env-steps/s",
                                 "how": "so100_step_host: one synchronous call per step for the whole batch (the SB3 VecEnv adapter's call)"}
         if tasks_rec:
