@@ -14,6 +14,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=65536)
     ap.add_argument("--steps", type=int, default=100000)
+    ap.add_argument("--flags", type=int, default=0, help="SO100_FLAG_* bits (16 = arm-floor contact)")
+    ap.add_argument("--tasks", type=int, nargs="+", default=[1, 2, 5, 6])
     args = ap.parse_args()
     import torch
     from so100_mujoco_rl_b200.batched_env import BatchedSo100Env
@@ -21,8 +23,8 @@ def main():
     g = torch.Generator(device=dev).manual_seed(3)
     ring = [torch.rand((args.envs, 6), device=dev, generator=g) * 2 - 1 for _ in range(97)]
     out = {}
-    for task in (1, 2, 5, 6):
-        env = BatchedSo100Env(task, args.envs, device=0, seed=5)
+    for task in args.tasks:
+        env = BatchedSo100Env(task, args.envs, device=0, seed=5, flags=args.flags)
         env.reset()
         dones = torch.zeros((), device=dev, dtype=torch.int64)
         rsum = torch.zeros((), device=dev, dtype=torch.float64)
@@ -32,7 +34,7 @@ def main():
                 dones += (r.terminated | r.truncated).sum()
                 rsum += r.reward.double().sum()
         st, s = env.get_state(), env.stats()
-        out[f"Env0{task}"] = {"env_steps": args.envs * args.steps, **s, "qpos_abs_max": float(st["qpos"].abs().max()),
+        out[f"Env0{task}"] = {"env_steps": args.envs * args.steps, "flags": args.flags, **s, "qpos_abs_max": float(st["qpos"].abs().max()),
                               "qvel_abs_max": float(st["qvel"].abs().max()), "all_finite": bool(torch.isfinite(st["qpos"]).all() and torch.isfinite(st["qvel"]).all()),
                               "sampled_mean_reward": float(rsum) / (args.envs * ((args.steps + 63) // 64)), "sampled_dones": int(dones)}
         env.close()
