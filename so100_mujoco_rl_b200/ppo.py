@@ -192,7 +192,7 @@ class _LearnLoop:
             self._acc.zero_()
             rec = {"iter": s.iterations, "samples": s.samples, "mean_step_reward": raw / (self.cfg.n_steps * self.env.num_envs),
                    "ep_return_mean": ers / cnt if cnt else None, "ep_len_mean": els / cnt if cnt else None,
-                   "episodes": int(cnt), "log_std_mean": self._log_std_mean(), **info}
+                   "episodes": int(cnt), "log_std_mean": self._log_std_mean(), "rollout_s": t1 - t0, "update_s": t2 - t1, **info}
             s.history.append(rec)
             if callback is not None:
                 callback(rec)

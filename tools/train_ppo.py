@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--epochs", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--max-episode-steps", type=int, default=0)
+    ap.add_argument("--flags", type=int, default=0, help="SO100_FLAG_* bits for the env (16 = arm-floor contact)")
+    ap.add_argument("--tag", default="", help="suffix of the output file name")
     ap.add_argument("--learner", default="fused", choices=["fused", "torch"], help="fused = include/so100_ppo.h kernels; torch = the PyTorch reference learner")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out"))
     args = ap.parse_args()
@@ -42,7 +44,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     env = BatchedSo100Env(args.env, args.num_envs, device=local_rank, seed=args.seed, env_offset=rank * args.num_envs,
-                          max_episode_steps=args.max_episode_steps or None)
+                          max_episode_steps=args.max_episode_steps or None, flags=args.flags)
     cfg = PPOConfig(n_steps=args.n_steps, n_minibatches=args.minibatches, n_epochs=args.epochs, seed=args.seed)
     algo = FusedPPO(env, cfg, env_offset=rank * args.num_envs) if args.learner == "fused" else PPO(env, cfg)
     hist = []
@@ -67,9 +69,9 @@ def main():
     out = {"env": args.env, "learner": args.learner, "num_envs": args.num_envs, "n_gpus": world, "cuda_graph_update": graphed, "n_steps": args.n_steps, "samples": st.samples, "wall_s": wall,
            "rollout_s": st.rollout_s, "update_s": st.update_s, "samples_per_s": st.samples / wall,
            "rollout_env_steps_per_s": st.samples / st.rollout_s, "history": hist[:: max(1, len(hist) // 200)] + hist[-1:],
-           "kernel_variant": env.kernel_variant, "stats": env.stats()}
+           "kernel_variant": env.kernel_variant, "stats": env.stats(), "env_flags": args.flags}
     os.makedirs(args.out, exist_ok=True)
-    path = os.path.join(args.out, f"ppo_{args.env}_{args.learner}_s{args.seed}" + (f"_{world}gpu" if world > 1 else "") + ".json")
+    path = os.path.join(args.out, f"ppo_{args.env}_{args.learner}_s{args.seed}" + (f"_{world}gpu" if world > 1 else "") + args.tag + ".json")
     json.dump(out, open(path, "w"), indent=1)
     print("wrote", path, {k: out[k] for k in ("n_gpus", "samples", "wall_s", "rollout_s", "update_s", "samples_per_s", "cuda_graph_update")})
     if world > 1:
