@@ -260,3 +260,47 @@ def test_torch_learner_resume_keeps_adam_state_under_cuda_graph():
         c.buf[k].copy_(a.buf[k])
     c.update(adv, ret)
     assert not torch.allclose(pack_params(a.policy), pack_params(c.policy), atol=2e-5)
+
+
+_ACT_SNIPPET = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r})
+from so100_mujoco_rl_b200 import _native
+from so100_mujoco_rl_b200.ppo import MlpPolicy, pack_params
+L = _native.lib()
+od, n = {od}, {n}
+torch.manual_seed(0)
+p = MlpPolicy(od, 6).cuda()
+with torch.no_grad():
+    for t in p.parameters():
+        t.add_(0.1 * torch.randn_like(t))
+P = pack_params(p)
+obs = torch.randn(n, od, device="cuda")
+f = dict(device="cuda", dtype=torch.float32)
+a, lp, v = torch.zeros(n, 6, **f), torch.zeros(n, **f), torch.zeros(n, **f)
+_native.check(L.so100_ppo_act(od, P.data_ptr(), obs.data_ptr(), n, 7, 0, 3, 0, a.data_ptr(), None, lp.data_ptr(), v.data_ptr(), None,
+                              torch.cuda.current_stream().cuda_stream))
+torch.cuda.synchronize()
+np.savez({out!r}, a=a.cpu().numpy(), lp=lp.cpu().numpy(), v=v.cpu().numpy())
+"""
+
+
+@pytest.mark.parametrize("od,n", [(15, 777), (8, 4096)])
+def test_act_tcgen05_and_mma_kernels_agree(od, n, tmp_path):
+    """The rollout-inference kernel on tcgen05 / TMEM (the default) and the warp-level mma.sync one (SO100_PPO_ACT_MMA=1,
+    read once per process, hence the subprocesses) compute the same fp32-level forward pass: same noise, values and
+    log-probs to re-association error."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, env in (("tc", {}), ("mma", {"SO100_PPO_ACT_MMA": "1"})):
+        out = str(tmp_path / f"act_{tag}.npz")
+        e = dict(os.environ, **env)
+        e.pop("SO100_PPO_ACT_MMA", None) if not env else None
+        subprocess.run([sys.executable, "-c", _ACT_SNIPPET.format(root=root, od=od, n=n, out=out)], check=True, env=e, timeout=300)
+        res[tag] = np.load(out)
+    assert np.abs(res["tc"]["v"] - res["mma"]["v"]).max() < 2e-5
+    assert np.abs(res["tc"]["a"] - res["mma"]["a"]).max() < 2e-5
+    assert np.abs(res["tc"]["lp"] - res["mma"]["lp"]).max() < 2e-4
