@@ -261,64 +261,61 @@ __global__ void __launch_bounds__(NT) act_kernel(Layout L, const float* __restri
 
 // ------------------------------------------------------------------------------------------------ rollout inference, tcgen05
 // The same computation on the 5th-generation tensor cores (csrc/so100_tc.cuh): tiles of 128 samples, D[sample][feature] =
-// act[sample][k] W[feature][k] issued by ONE thread as tcgen05.mma kind::tf32 with M = 128, the accumulator in TMEM, and
-// the 3xTF32 split done ONCE per value when it is written to shared memory (hi and lo copies of every operand in the
-// no-swizzle K-major layout) instead of at every fragment load.  Thread r of a warpgroup owns TMEM lane r = sample r of the
-// tile: it reads its row with tcgen05.ld, adds the bias, applies tanh and writes the row of the next layer's A operand
-// as float4 stores; the two warpgroups split the 64 columns.  Per tile and tower: layer 1 (6 MMAs), layer 2 (24), head (24,
-// N = 16); one mbarrier, committed after every layer.  One CTA per SM (176 KB of shared memory), persistent.
+// act[sample][k] W[feature][k] issued by ONE thread as tcgen05.mma kind::tf32 with M = 128.  The ACTIVATIONS NEVER TOUCH
+// SHARED MEMORY: the A operand of every product is read from TMEM (row = TMEM lane = sample, K along the columns), where
+// the thread that owns the sample has put it with tcgen05.st - the observation row at the start of a tile, then after
+// each layer tcgen05.ld of its accumulator row -> bias + tanh -> the 3xTF32 split (hi and lo copies, made ONCE per value)
+// -> tcgen05.st of its row of the next layer's A.  Only the weights sit in shared memory (hi and lo images in the no-
+// swizzle K-major layout, 96 KB), so TWO CTAs share an SM (and its 512 TMEM columns: 256 each) and one's epilogue overlaps
+// the other's MMAs.  The two warpgroups of a CTA split a layer's 64 columns.  Per tile and tower: layer 1 (6 MMAs), layer 2
+// (24), head (24, N = 16); one mbarrier, committed after every layer.  Persistent over tiles.
 constexpr int TM = 128, NTC = 256;
 struct ActTc {  // byte offsets into dynamic shared memory
   static constexpr int W1 = 0;                         // [tower][hi, lo][64 x 16]
   static constexpr int W2 = W1 + 2 * 2 * 64 * 16 * 4;  // [tower][hi, lo][64 x 64]
   static constexpr int W3 = W2 + 2 * 2 * 64 * 64 * 4;  // [tower][hi, lo][16 x 64]
-  static constexpr int X = W3 + 2 * 2 * 16 * 64 * 4;   // [hi, lo][128 x 16]
-  static constexpr int H = X + 2 * TM * 16 * 4;        // [hi, lo][128 x 64]
-  static constexpr int BIAS = H + 2 * TM * 64 * 4;     // b1[2][64], b2[2][64], b3[2][8], log_std[8]
+  static constexpr int BIAS = W3 + 2 * 2 * 16 * 64 * 4;  // b1[2][64], b2[2][64], b3[2][8], log_std[8]
   static constexpr int BAR = BIAS + (2 * 64 + 2 * 64 + 16 + 8) * 4;
   static constexpr int BYTES = BAR + 16;
+  // TMEM columns (256 per CTA)
+  static constexpr uint32_t cD = 0, cAh = 64, cAl = 128, cXh = 192, cXl = 208, cHead = 224;
 };
-static_assert(ActTc::BYTES <= 227 * 1024, "act_kernel_tc: shared memory");
+static_assert(2 * (ActTc::BYTES + 1024) <= 227 * 1024, "act_kernel_tc: two CTAs per SM");
 
-// one layer's epilogue for this thread's half of the 64 columns: h = tanh(D + bias) -> the A operand of the next layer
-__device__ __forceinline__ void tc_epilogue_tanh(uint32_t tmem_row, int col0, const float* bias, unsigned char* Hh, unsigned char* Hl, int row) {
+// one layer's epilogue for this thread's half of the 64 columns: h = tanh(D + bias) -> hi / lo rows of the next layer's A (TMEM)
+__device__ __forceinline__ void tc_epilogue_tanh(uint32_t tmem_row, int col0, const float* bias) {
 #pragma unroll
   for (int c0 = col0; c0 < col0 + 32; c0 += 16) {
-    float v[16];
-    tc::tmem_ld16(tmem_row + c0, v);
+    float v[16], hi[16], lo[16];
+    tc::tmem_ld16(tmem_row + ActTc::cD + c0, v);
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      float hi[4], lo[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) tc::split(tanhf(v[4 * q + i] + bias[c0 + 4 * q + i]), hi[i], lo[i]);
-      const int off = tc::op_offset<TM>(row, c0 + 4 * q);
-      *reinterpret_cast<float4*>(Hh + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<float4*>(Hl + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-    }
+    for (int i = 0; i < 16; i++) tc::split(tanhf(v[i] + bias[c0 + i]), hi[i], lo[i]);
+    tc::tmem_st16(tmem_row + ActTc::cAh + c0, hi);
+    tc::tmem_st16(tmem_row + ActTc::cAl + c0, lo);
   }
+  tc::tmem_st_wait();
 }
-// D (+)= A B^T over K with the 3xTF32 split: small terms first
+// D (+)= A B^T over K with the 3xTF32 split (small terms first); A (hi at column ah, lo at al) in TMEM, B in shared memory
 template <int NROWS_B, int K>
 __device__ __forceinline__ void tc_gemm3(uint32_t tmem_d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, uint32_t idesc) {
 #pragma unroll
   for (int k0 = 0; k0 < K; k0 += 8) {
-    tc::mma_tf32(tmem_d, tc::op_desc<TM>(al, k0 / 4), tc::op_desc<NROWS_B>(bh, k0 / 4), idesc, k0 > 0);
-    tc::mma_tf32(tmem_d, tc::op_desc<TM>(ah, k0 / 4), tc::op_desc<NROWS_B>(bl, k0 / 4), idesc, true);
-    tc::mma_tf32(tmem_d, tc::op_desc<TM>(ah, k0 / 4), tc::op_desc<NROWS_B>(bh, k0 / 4), idesc, true);
+    tc::mma_tf32_ts(tmem_d, al + k0, tc::op_desc<NROWS_B>(bh, k0 / 4), idesc, k0 > 0);
+    tc::mma_tf32_ts(tmem_d, ah + k0, tc::op_desc<NROWS_B>(bl, k0 / 4), idesc, true);
+    tc::mma_tf32_ts(tmem_d, ah + k0, tc::op_desc<NROWS_B>(bh, k0 / 4), idesc, true);
   }
 }
 
-__global__ void __launch_bounds__(NTC, 1) act_kernel_tc(Layout L, const float* __restrict__ P, const float* __restrict__ obs, int n, unsigned seed_lo,
+__global__ void __launch_bounds__(NTC, 2) act_kernel_tc(Layout L, const float* __restrict__ P, const float* __restrict__ obs, int n, unsigned seed_lo,
                                                         unsigned seed_hi, long long env_offset, unsigned tick, int deterministic, float* act_raw,
                                                         float* act_clip, float* logp, float* value, float* obs_copy) {
   extern __shared__ __align__(128) unsigned char smc[];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, od = L.od;
-  const int row = tid & (TM - 1), half = tid >> 7;  // TMEM lane = sample of the tile; which 32 of a layer's 64 columns
+  const int row = tid & (TM - 1), half = tid >> 7;  // TMEM lane = sample of the tile; which half of a layer's columns
   float* bias = reinterpret_cast<float*>(smc + ActTc::BIAS);
   float *b1 = bias, *b2 = bias + 128, *b3 = bias + 256, *ls = bias + 272;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smc + ActTc::BAR);
-  unsigned char *Xh = smc + ActTc::X, *Xl = Xh + TM * 16 * 4, *Hh = smc + ActTc::H, *Hl = Hh + TM * 64 * 4;
   auto W1 = [&](int t, int lo) { return smc + ActTc::W1 + (2 * t + lo) * 64 * 16 * 4; };
   auto W2 = [&](int t, int lo) { return smc + ActTc::W2 + (2 * t + lo) * 64 * 64 * 4; };
   auto W3 = [&](int t, int lo) { return smc + ActTc::W3 + (2 * t + lo) * 16 * 64 * 4; };
@@ -351,72 +348,71 @@ __global__ void __launch_bounds__(NTC, 1) act_kernel_tc(Layout L, const float* _
     for (int e = tid; e < 8; e += NTC) b3[8 * t + e] = e < nout ? P[L.b3[t] + e] : 0.0f;
   }
   if (tid < 8) ls[tid] = tid < ACT ? P[L.log_std + tid] : 0.0f;
-  for (int e = tid; e < TM * K1; e += NTC) {  // the padding columns of X stay zero for the whole kernel
-    const int off = tc::op_offset<TM>(e / K1, e % K1);
-    *reinterpret_cast<float*>(Xh + off) = 0.0f; *reinterpret_cast<float*>(Xl + off) = 0.0f;
-  }
+  tc::fence_smem_to_mma();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot, tmem_row = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-  const uint32_t xh = tc::smem_u32(Xh), xl = tc::smem_u32(Xl), hh = tc::smem_u32(Hh), hl = tc::smem_u32(Hl);
-  constexpr uint32_t kDa = 0, kDb = 64, kDc = 128;  // TMEM columns: layer 1, layer 2, heads (16 per tower)
   uint32_t phase = 0;
   const int ntiles = (n + TM - 1) / TM;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int base = tile * TM;
-    for (int e = tid; e < TM * od; e += NTC) {  // coalesced over the tile's od * 128 observation words
-      const int s = e / od, f = e % od, g = base + s;
-      float v = 0.0f;
-      if (g < n) {
-        v = obs[(size_t)base * od + e];
-        if (obs_copy) obs_copy[(size_t)base * od + e] = v;
+    const int base = tile * TM, g = base + row;
+    {  // this sample's observation row -> the hi (warpgroup 0) or lo (warpgroup 1) copy of X in TMEM; padding columns zero
+      float x[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) x[k] = (g < n && k < od) ? obs[(size_t)g * od + k] : 0.0f;
+      if (half == 0 && obs_copy && g < n) {
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+          if (k < od) obs_copy[(size_t)g * od + k] = x[k];
       }
-      float hi, lo;
-      tc::split(v, hi, lo);
-      const int off = tc::op_offset<TM>(s, f);
-      *reinterpret_cast<float*>(Xh + off) = hi; *reinterpret_cast<float*>(Xl + off) = lo;
+      float part[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        float hi, lo;
+        tc::split(x[k], hi, lo);
+        part[k] = half ? lo : hi;
+      }
+      tc::tmem_st16(tmem_row + (half ? ActTc::cXl : ActTc::cXh), part);
+      tc::tmem_st_wait();
     }
-    tc::fence_smem_to_mma();
     tc::fence_before_sync();
     __syncthreads();
 #pragma unroll 1
     for (int t = 1; t >= 0; t--) {  // value tower first, as in act_kernel
       if (tid == 0) {
         tc::fence_after_sync();
-        tc_gemm3<64, K1>(tmem + kDa, xh, xl, tc::smem_u32(W1(t, 0)), tc::smem_u32(W1(t, 1)), tc::idesc_tf32(TM, 64));
+        tc_gemm3<64, K1>(tmem + ActTc::cD, tmem + ActTc::cXh, tmem + ActTc::cXl, tc::smem_u32(W1(t, 0)), tc::smem_u32(W1(t, 1)), tc::idesc_tf32(TM, 64));
         tc::mma_commit(bar);
       }
       tc::bar_wait(bar, phase); phase ^= 1;
       tc::fence_after_sync();
-      tc_epilogue_tanh(tmem_row + kDa, 32 * half, b1 + 64 * t, Hh, Hl, row);
-      tc::fence_smem_to_mma();
+      tc_epilogue_tanh(tmem_row, 32 * half, b1 + 64 * t);
       tc::fence_before_sync();
       __syncthreads();
       if (tid == 0) {
         tc::fence_after_sync();
-        tc_gemm3<64, HID>(tmem + kDb, hh, hl, tc::smem_u32(W2(t, 0)), tc::smem_u32(W2(t, 1)), tc::idesc_tf32(TM, 64));
+        tc_gemm3<64, HID>(tmem + ActTc::cD, tmem + ActTc::cAh, tmem + ActTc::cAl, tc::smem_u32(W2(t, 0)), tc::smem_u32(W2(t, 1)), tc::idesc_tf32(TM, 64));
         tc::mma_commit(bar);
       }
       tc::bar_wait(bar, phase); phase ^= 1;
       tc::fence_after_sync();
-      tc_epilogue_tanh(tmem_row + kDb, 32 * half, b2 + 64 * t, Hh, Hl, row);  // h2 over h1: the layer-2 MMAs have finished reading it
-      tc::fence_smem_to_mma();
+      tc_epilogue_tanh(tmem_row, 32 * half, b2 + 64 * t);  // h2 over h1: the layer-2 MMAs have finished reading it
       tc::fence_before_sync();
       __syncthreads();
       if (tid == 0) {
         tc::fence_after_sync();
-        tc_gemm3<16, HID>(tmem + kDc + 16 * t, hh, hl, tc::smem_u32(W3(t, 0)), tc::smem_u32(W3(t, 1)), tc::idesc_tf32(TM, 16));
+        tc_gemm3<16, HID>(tmem + ActTc::cHead + 16 * t, tmem + ActTc::cAh, tmem + ActTc::cAl, tc::smem_u32(W3(t, 0)), tc::smem_u32(W3(t, 1)),
+                          tc::idesc_tf32(TM, 16));
         tc::mma_commit(bar);
       }
-      tc::bar_wait(bar, phase); phase ^= 1;  // the head has consumed h2: the next tower may overwrite H
+      tc::bar_wait(bar, phase); phase ^= 1;  // the head has consumed h2: the next tower may overwrite A
       tc::fence_after_sync();
       __syncthreads();  // no thread is still polling this phase when the next commit arrives
     }
     // heads: warpgroup 0 samples the action from the six means, warpgroup 1 stores the value
-    const int g = base + row;
     float o16[16];
-    tc::tmem_ld16(tmem_row + kDc + 16 * (half ? 1 : 0), o16);
+    tc::tmem_ld16(tmem_row + ActTc::cHead + 16 * (half ? 1 : 0), o16);
     if (g < n) {
       if (half) {
         if (value) value[g] = o16[0] + b3[8];
@@ -449,7 +445,7 @@ __global__ void __launch_bounds__(NTC, 1) act_kernel_tc(Layout L, const float* _
       }
     }
     tc::fence_before_sync();
-    __syncthreads();  // every thread has read its head row: the next tile may overwrite TMEM and X
+    __syncthreads();  // every thread has read its head row: the next tile may overwrite TMEM
   }
   if (warp == 0) tc::tmem_free<256>(tmem);
 }
@@ -1006,9 +1002,9 @@ int so100_ppo_act(int obs_dim, const float* params, const float* obs, int n, uin
   CU(cudaGetDevice(&dev));
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   static const bool use_mma = getenv("SO100_PPO_ACT_MMA") != nullptr;  // A/B knob: the warp-level mma.sync version
-  if (!use_mma) {  // tcgen05 / TMEM: 128-sample tiles, one persistent CTA per SM
+  if (!use_mma) {  // tcgen05 / TMEM: 128-sample tiles, two persistent CTAs per SM
     CU(cudaFuncSetAttribute((const void*)ppo::act_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ppo::ActTc::BYTES));
-    const int ntiles = (n + ppo::TM - 1) / ppo::TM, grid = ntiles < sms ? ntiles : sms;
+    const int ntiles = (n + ppo::TM - 1) / ppo::TM, grid = ntiles < 2 * sms ? ntiles : 2 * sms;
     ppo::act_kernel_tc<<<grid, ppo::NTC, ppo::ActTc::BYTES, (cudaStream_t)stream>>>(
         ppo::make_layout(obs_dim), params, obs, n, (unsigned)(seed & 0xFFFFFFFFull), (unsigned)(seed >> 32), env_offset, tick, deterministic,
         act_raw, act_clip, logp, value, obs_copy);

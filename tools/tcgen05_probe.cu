@@ -245,7 +245,95 @@ static int run_mn(const char* name, int mode, uint32_t lbo, uint32_t sbo_a, uint
   return maxerr < 2e-5 ? 0 : 1;
 }
 
+// A from TMEM: thread r writes row r of A (hi and lo copies) into TMEM columns with tcgen05.st, B stays in shared memory.
+template <int N, int K>
+__global__ void __launch_bounds__(128) probe_ts_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* Bh = reinterpret_cast<float*>(smem);
+  float* Bl = Bh + N * K;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) { tc::bar_init(&bar, 1); tc::bar_init_fence(); }
+  if (warp == 0) tc::tmem_alloc<256>(&tmem_slot);
+  for (int e = tid; e < N * K; e += 128) {
+    float hi, lo;
+    tc::split(B[e], hi, lo);
+    const int off = tc::op_offset<N>(e / K, e % K);
+    *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Bh) + off) = hi;
+    *reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(Bl) + off) = lo;
+  }
+  tc::fence_smem_to_mma();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot, row = tmem + ((uint32_t)(32 * warp) << 16);
+  constexpr uint32_t kD = 0, kAh = 64, kAl = 64 + K;
+  for (int c0 = 0; c0 < K; c0 += 16) {
+    float hi[16], lo[16];
+    for (int i = 0; i < 16; i++) tc::split(A[tid * K + c0 + i], hi[i], lo[i]);
+    tc::tmem_st16(row + kAh + c0, hi);
+    tc::tmem_st16(row + kAl + c0, lo);
+  }
+  tc::tmem_st_wait();
+  tc::fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    tc::fence_after_sync();
+    const uint32_t idesc = tc::idesc_tf32(128, N);
+    const uint32_t bh = tc::smem_u32(Bh), bl = tc::smem_u32(Bl);
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      tc::mma_tf32_ts(tmem + kD, tmem + kAl + k0, tc::op_desc<N>(bh, k0 / 4), idesc, k0 > 0);
+      tc::mma_tf32_ts(tmem + kD, tmem + kAh + k0, tc::op_desc<N>(bl, k0 / 4), idesc, true);
+      tc::mma_tf32_ts(tmem + kD, tmem + kAh + k0, tc::op_desc<N>(bh, k0 / 4), idesc, true);
+    }
+    tc::mma_commit(&bar);
+  }
+  tc::bar_wait(&bar, 0);
+  tc::fence_after_sync();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tc::tmem_ld16(row + kD + c0, v);
+    for (int i = 0; i < 16; i++) D[tid * N + c0 + i] = v[i];
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_free<256>(tmem);
+}
+template <int N, int K>
+static int run_ts(const char* name) {
+  std::vector<float> A(128 * K), B(N * K), D(128 * N);
+  srand(3);
+  for (auto& x : A) x = (float)rand() / RAND_MAX * 2 - 1;
+  for (auto& x : B) x = (float)rand() / RAND_MAX * 2 - 1;
+  float *dA, *dB, *dD;
+  cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dD, D.size() * 4);
+  cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemset(dD, 0, D.size() * 4);
+  const int smem = N * K * 2 * 4;
+  cudaFuncSetAttribute(probe_ts_kernel<N, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  probe_ts_kernel<N, K><<<1, 128, smem>>>(dA, dB, dD);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s: CUDA error %s\n", name, cudaGetErrorString(e)); return 1; }
+  cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+  double maxerr = 0;
+  for (int r = 0; r < 128; r++)
+    for (int n = 0; n < N; n++) {
+      double s = 0;
+      for (int k = 0; k < K; k++) s += (double)A[r * K + k] * (double)B[n * K + k];
+      maxerr = fmax(maxerr, fabs(s - (double)D[r * N + n]));
+    }
+  printf("%s: N=%d K=%d  A from TMEM (tcgen05.st), B from shared memory: max|err| %.3e  D[0][0..3] = %g %g %g %g %s\n", name, N, K, maxerr, D[0], D[1],
+         D[2], D[3], maxerr < 2e-5 ? "OK" : "");
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  return maxerr < 2e-5 ? 0 : 1;
+}
+
 int main() {
+  run_ts<64, 64>("TS 3xtf32 ");
+  run_ts<16, 64>("TS N16    ");
+
   // informational (not part of the verdict): where M = 64 puts its rows, and what MN-major no-swizzle operands return
   run_mn<64, 64>("M64 K-major          ", 4, 0, 0, 0, 0);
   {  // the image of SA [KT = 64][128]: 4-wide chunks of the operand's M/N index are (KT / 8) * 128 = 1024 B apart, 8-row K groups 128 B
