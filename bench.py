@@ -335,17 +335,33 @@ def main():
             e.step(ring[w % 64])
         return e
 
+    # The clock sampler starts FIRST and the GPU is kept busy (the FP32 peak probe: no env state involved) until nvidia-smi
+    # has delivered a sample and at least half a second has passed: on a fresh box the first nvidia-smi call takes longer
+    # than the whole timed region, and a GPU coming out of idle clocks is not what the metric is about.  The same probe
+    # runs for a quarter of a second after the timed region, so that the 100 ms sampling grid has points under load on
+    # both sides of it; every sample kept was taken between the first and the last of these launches.
+    import ctypes
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def spin(seconds, need_sample=False):
+        tf_ = ctypes.c_double(0.0)
+        t_end, t_max = time.perf_counter() + seconds, time.perf_counter() + 6.0
+        while time.perf_counter() < t_end or (need_sample and not sampler.rows and time.perf_counter() < t_max):
+            _native.check(_native.lib().so100_bench_fp32_peak(local_rank, 4096, ctypes.byref(tf_)))
+
     env = fresh_env(task)
+    spin(0.5, need_sample=True)
+    sampler.rows.clear()  # (samples from before the GPU was under load)
     for w in range(warmup):
         env.step(ring[w % 64])
     launches0 = env.stats()["launches"]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     t_wall0 = time.perf_counter()
     ev, res = timed_steps(env, ring, steps, flush, torch)
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    spin(0.25)
     clocks = sampler.stop()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = env.stats()["launches"] - launches0
@@ -507,7 +523,6 @@ def main():
         e.close()
 
     if rank == 0:
-        import ctypes
         total_envs = n * world
         value = total_envs * steps / (total_ms * 1e-3)
         per_gpu = value / world
